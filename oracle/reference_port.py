@@ -1,0 +1,564 @@
+"""oracle/reference_port.py — CPU oracle for Lethe's GLS Navier–Stokes hot path.
+
+TEST INFRASTRUCTURE, NOT PRODUCT.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / ``--impl reference`` legs may import this module.  The product package
+(softx_2020_200_b200/) never imports anything under oracle/.
+
+Parity status: PINNED against the reference's golden files (tests/test_oracle_golden.py):
+``tests/solvers/restart_01.output`` (GMRES iterations 8/6/10, true residuals, L2 error) and
+``applications_tests/gls_navier_stokes_3d/mms3d_gls.output`` (3D Q1-Q1 MMS errors).
+
+What is restated here (numpy) and in gls_oracle.c (the heavy loops), with the reference file:line:
+
+* the host-side objects deal.II provides to the hot path on a uniform hyper_cube mesh: FE_Q shape
+  tables on QGauss points, DoF numbering + Cuthill–McKee (gls_navier_stokes.cc:69-70), homogeneous /
+  inhomogeneous Dirichlet constraints (:79-183), the sparsity pattern with
+  keep_constrained_dofs=false (:204-213);
+* assembleGLS (:231-777)                       -> gls_oracle.c: glso_assemble
+* setup_ILU (:1161-1176)                       -> gls_oracle.c: glso_ilu0
+* solve_system_GMRES (:1242-1289)              -> gls_oracle.c: glso_gmres
+* NewtonNonLinearSolver::solve (include/core/newton_non_linear_solver.h:76-139) -> newton_solve
+* calculate_L2_error (source/solvers/navier_stokes_base.cc:255-380)              -> l2_error
+* bdf_coefficients (source/core/bdf.cc:46-75), sdirk_coefficients (source/core/sdirk.cc:11-44)
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_double_p = C.POINTER(C.c_double)
+c_i32_p = C.POINTER(C.c_int32)
+c_i64_p = C.POINTER(C.c_int64)
+c_u8_p = C.POINTER(C.c_uint8)
+
+
+class _FE(C.Structure):
+    _fields_ = [("dim", C.c_int), ("n_su", C.c_int), ("n_sp", C.c_int), ("nq", C.c_int),
+                ("vel_degree", C.c_int),
+                ("Nu", c_double_p), ("dNu", c_double_p), ("d2Nu", c_double_p),
+                ("Np", c_double_p), ("dNp", c_double_p), ("wq", c_double_p)]
+
+
+class _Cells(C.Structure):
+    _fields_ = [("ncell", C.c_int64), ("cell_dofs", c_i32_p), ("cell_invJ", c_double_p),
+                ("cell_detJ", c_double_p), ("cell_measure", c_double_p),
+                ("qpoints", c_double_p), ("force", c_double_p)]
+
+
+class _Params(C.Structure):
+    _fields_ = [("viscosity", C.c_double), ("transient", C.c_int), ("sdt", C.c_double),
+                ("coefs", C.c_double * 4), ("srf", C.c_int), ("omega", C.c_double * 3)]
+
+
+def build_lib(force=False):
+    """Compile gls_oracle.c (see oracle/Makefile) and return the path of the .so."""
+    so = os.path.join(_HERE, "_build", "libgls_oracle.so")
+    src = os.path.join(_HERE, "gls_oracle.c")
+    stamp = os.path.join(_HERE, "_build", "cpu.stamp")
+    cpu = _cpu_id()
+    old = open(stamp).read() if os.path.exists(stamp) else ""
+    # -march=native: a library built on another host (it travels with gpurun) must be rebuilt
+    if force or not os.path.exists(so) or old != cpu or (
+            os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src)):
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE])
+        with open(stamp, "w") as f:
+            f.write(cpu)
+    return so
+
+
+def _cpu_id():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build_lib())
+        _LIB.glso_num_threads.restype = C.c_int
+    return _LIB
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+# ----------------------------------------------------------------------------------------------
+# finite element tables (what FEValues precomputes on the reference cell [0,1]^dim)
+# ----------------------------------------------------------------------------------------------
+def gauss01(nq1):
+    """QGauss<1>(nq1) on [0,1]."""
+    x, w = np.polynomial.legendre.leggauss(nq1)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def lagrange1d(p, x):
+    """Lagrange basis of degree p on equispaced nodes of [0,1] (FE_Q support points for p<=2):
+    values, first and second derivatives at points x. Shapes [p+1, len(x)]."""
+    nodes = np.linspace(0.0, 1.0, p + 1)
+    x = np.asarray(x, dtype=np.float64)
+    V = np.zeros((p + 1, x.size))
+    D = np.zeros((p + 1, x.size))
+    D2 = np.zeros((p + 1, x.size))
+    for a in range(p + 1):
+        coef = np.poly1d([1.0])
+        for b in range(p + 1):
+            if b != a:
+                coef = coef * np.poly1d([1.0, -nodes[b]]) / (nodes[a] - nodes[b])
+        V[a] = coef(x)
+        D[a] = coef.deriv(1)(x) if p >= 1 else 0.0
+        D2[a] = coef.deriv(2)(x) if p >= 2 else 0.0
+    return V, D, D2
+
+
+def _tensor_tables(dim, p, xq1):
+    """Scalar FE_Q(p) tables at the tensor-product points built from xq1 (x fastest):
+    N[q,a], dN[q,a,d], d2N[q,a,d,e]; local shape index a lexicographic, x fastest."""
+    V, D, D2 = lagrange1d(p, xq1)
+    n1, q1 = p + 1, len(xq1)
+    ns, nq = n1 ** dim, q1 ** dim
+    N = np.zeros((nq, ns))
+    dN = np.zeros((nq, ns, dim))
+    d2N = np.zeros((nq, ns, dim, dim))
+    for q in range(nq):
+        qi = [(q // q1 ** d) % q1 for d in range(dim)]
+        for a in range(ns):
+            ai = [(a // n1 ** d) % n1 for d in range(dim)]
+            N[q, a] = np.prod([V[ai[d], qi[d]] for d in range(dim)])
+            for d in range(dim):
+                dN[q, a, d] = np.prod([(D if e == d else V)[ai[e], qi[e]] for e in range(dim)])
+                for e in range(dim):
+                    if d == e:
+                        f = [(D2 if g == d else V)[ai[g], qi[g]] for g in range(dim)]
+                    else:
+                        f = [(D if g in (d, e) else V)[ai[g], qi[g]] for g in range(dim)]
+                    d2N[q, a, d, e] = np.prod(f)
+    return N, dN, d2N
+
+
+class FETables:
+    """FESystem(FE_Q(pu)^dim, FE_Q(pp)) on QGauss(nq1) (navier_stokes_base.cc:62,70,93-94)."""
+
+    def __init__(self, dim, pu, pp, nq1=None):
+        self.dim, self.pu, self.pp = dim, pu, pp
+        self.nq1 = nq1 if nq1 else pu + 1
+        x, w = gauss01(self.nq1)
+        self.xq1, self.wq1 = x, w
+        self.Nu, self.dNu, self.d2Nu = _tensor_tables(dim, pu, x)
+        self.Np, self.dNp, _ = _tensor_tables(dim, pp, x)
+        self.nq = self.nq1 ** dim
+        self.n_su, self.n_sp = (pu + 1) ** dim, (pp + 1) ** dim
+        self.n = dim * self.n_su + self.n_sp
+        wq = np.ones(self.nq)
+        xq = np.zeros((self.nq, dim))
+        for q in range(self.nq):
+            for d in range(dim):
+                i = (q // self.nq1 ** d) % self.nq1
+                wq[q] *= w[i]
+                xq[q, d] = x[i]
+        self.wq, self.xq = wq, xq
+
+    def cstruct(self):
+        keep = [np.ascontiguousarray(a) for a in
+                (self.Nu, self.dNu, self.d2Nu, self.Np, self.dNp, self.wq)]
+        s = _FE(self.dim, self.n_su, self.n_sp, self.nq, self.pu,
+                *[_p(a, c_double_p) for a in keep])
+        s._keep = keep
+        return s
+
+
+# ----------------------------------------------------------------------------------------------
+# mesh / DoFs / constraints / sparsity: the deal.II side of the boundary
+# ----------------------------------------------------------------------------------------------
+class BoxMesh:
+    """GridGenerator::hyper_cube / subdivided_hyper_cube on [lo,hi]^dim with n cells per direction
+    and the DoFHandler objects the hot path consumes.
+
+    bcs: {face_id: ("noslip",) | ("function", callable(x[:, dim]) -> [:, dim])}; face ids as
+    deal.II colorize=true: 0:x=lo 1:x=hi 2:y=lo 3:y=hi 4:z=lo 5:z=hi; ``None`` key = every boundary
+    face (colorize=false, boundary id 0). First listed bc wins on shared edges/corners, as
+    VectorTools::interpolate_boundary_values does not overwrite existing constraint lines.
+    renumber: "cm" (Cuthill–McKee, gls_navier_stokes.cc:70), "none", or an explicit new-index array.
+    """
+
+    def __init__(self, dim, n, pu, pp, lo=-1.0, hi=1.0, bcs=None, renumber="cm", nq1=None):
+        assert pu % pp == 0
+        self.dim, self.ncd, self.pu, self.pp = dim, n, pu, pp
+        self.lo, self.hi = float(lo), float(hi)
+        self.fe = FETables(dim, pu, pp, nq1)
+        fe = self.fe
+        self.hx = (self.hi - self.lo) / n
+        gu = pu * n + 1                      # velocity node grid size per direction
+        ratio = pu // pp
+        self.gu = gu
+        nnode = gu ** dim
+        idx = np.indices((gu,) * dim).reshape(dim, -1)[::-1]   # idx[d] = index along d, x fastest
+        # numpy's indices with C order makes the LAST axis fastest; reverse so axis 0 = x fastest
+        self.node_idx = idx.T.copy()                              # [nnode, dim]
+        has_p = np.all(self.node_idx % ratio == 0, axis=1)
+        ndof_node = dim + has_p.astype(np.int64)
+        first = np.concatenate([[0], np.cumsum(ndof_node)])
+        self.ndof = int(first[-1])
+        self.vel_dof = first[:-1, None] + np.arange(dim)[None, :]     # [nnode, dim] provisional ids
+        self.p_dof = np.where(has_p, first[:-1] + dim, -1)
+        # cells
+        cidx = np.indices((n,) * dim).reshape(dim, -1)[::-1].T        # [ncell, dim], x fastest
+        self.ncell = cidx.shape[0]
+        self.cell_idx = cidx
+        stride = gu ** np.arange(dim)
+
+        def local_nodes(p):
+            n1 = p + 1
+            a = np.arange(n1 ** dim)
+            ai = np.stack([(a // n1 ** d) % n1 for d in range(dim)], axis=1)   # [ns, dim]
+            step = pu // p
+            nid = ((cidx[:, None, :] * pu + ai[None, :, :] * step) * stride).sum(axis=2)
+            return nid                                                         # [ncell, ns]
+
+        un, pn = local_nodes(pu), local_nodes(pp)
+        cd = [self.vel_dof[un, c] for c in range(dim)] + [self.p_dof[pn]]
+        cell_dofs = np.concatenate(cd, axis=1)
+        assert cell_dofs.min() >= 0
+        # dof meta
+        comp = np.zeros(self.ndof, dtype=np.int32)
+        dof_node = np.zeros(self.ndof, dtype=np.int64)
+        for c in range(dim):
+            comp[self.vel_dof[:, c]] = c
+            dof_node[self.vel_dof[:, c]] = np.arange(nnode)
+        comp[self.p_dof[has_p]] = dim
+        dof_node[self.p_dof[has_p]] = np.arange(nnode)[has_p]
+        coords = self.lo + self.node_idx * (self.hx / pu)
+        # constraints
+        constrained = np.zeros(self.ndof, dtype=np.uint8)
+        cvalue = np.zeros(self.ndof)
+        if bcs is None:
+            bcs = {None: ("noslip",)}
+        for face, bc in bcs.items():
+            if face is None:
+                on = np.any((self.node_idx == 0) | (self.node_idx == gu - 1), axis=1)
+            else:
+                d, side = face // 2, face % 2
+                on = self.node_idx[:, d] == (gu - 1 if side else 0)
+            nodes = np.nonzero(on)[0]
+            vals = np.zeros((nodes.size, dim)) if bc[0] == "noslip" else np.asarray(
+                bc[1](coords[nodes]), dtype=np.float64)
+            for c in range(dim):
+                d_ = self.vel_dof[nodes, c]
+                new = constrained[d_] == 0
+                constrained[d_[new]] = 1
+                cvalue[d_[new]] = vals[new, c]
+        # renumbering
+        if isinstance(renumber, str) and renumber == "cm":
+            new_of_old = self._cuthill_mckee(cell_dofs)
+        elif isinstance(renumber, str):
+            new_of_old = np.arange(self.ndof)
+        else:
+            new_of_old = np.asarray(renumber)
+        self.new_of_old = new_of_old
+        self.cell_dofs = np.ascontiguousarray(new_of_old[cell_dofs].astype(np.int32))
+        inv = np.empty_like(new_of_old)
+        inv[new_of_old] = np.arange(self.ndof)
+        self.dof_comp = comp[inv]
+        self.dof_coords = coords[dof_node[inv]]
+        self.constrained = np.ascontiguousarray(constrained[inv])
+        self.constraint_value = cvalue[inv]
+        # geometry (affine Cartesian cells)
+        self.cell_invJ = np.ascontiguousarray(
+            np.broadcast_to(np.eye(dim) / self.hx, (self.ncell, dim, dim)))
+        self.cell_detJ = np.full(self.ncell, self.hx ** dim)
+        self.cell_measure = np.full(self.ncell, self.hx ** dim)
+        self.qpoints = np.ascontiguousarray(
+            self.lo + (cidx[:, None, :] + fe.xq[None, :, :]) * self.hx)     # [ncell, nq, dim]
+        self.cell_color = (cidx % 2 * (2 ** np.arange(dim))).sum(axis=1).astype(np.int32)
+        self.rowptr, self.col = self._sparsity()
+
+    def _cuthill_mckee(self, cell_dofs):
+        """DoFRenumbering::Cuthill_McKee stand-in: plain Cuthill–McKee =
+        reversed scipy RCM on the dof graph where all dofs of a cell couple."""
+        import scipy.sparse as sp
+        from scipy.sparse.csgraph import reverse_cuthill_mckee
+        n = cell_dofs.shape[1]
+        rows = np.repeat(cell_dofs, n, axis=1).ravel()
+        cols = np.tile(cell_dofs, (1, n)).ravel()
+        G = sp.csr_matrix((np.ones(rows.size, dtype=np.int8), (rows, cols)),
+                          shape=(self.ndof, self.ndof))
+        G.sum_duplicates()
+        perm = reverse_cuthill_mckee(G, symmetric_mode=True)[::-1]     # perm[new] = old
+        new_of_old = np.empty(self.ndof, dtype=np.int64)
+        new_of_old[perm] = np.arange(self.ndof)
+        return new_of_old
+
+    def _sparsity(self):
+        """DoFTools::make_sparsity_pattern(dof_handler, dsp, constraints, keep_constrained=false)
+        (gls_navier_stokes.cc:204-208): couplings between unconstrained dofs of a cell, plus the
+        diagonal of every row. CSR with sorted columns, int64 row pointers, int32 columns."""
+        import scipy.sparse as sp
+        n = self.cell_dofs.shape[1]
+        cd = self.cell_dofs.astype(np.int64)
+        free = self.constrained[cd] == 0
+        rows = np.repeat(cd, n, axis=1)
+        cols = np.tile(cd, (1, n))
+        keep = np.repeat(free, n, axis=1) & np.tile(free, (1, n))
+        rows, cols = rows[keep], cols[keep]
+        rows = np.concatenate([rows, np.arange(self.ndof)])
+        cols = np.concatenate([cols, np.arange(self.ndof)])
+        A = sp.csr_matrix((np.ones(rows.size, dtype=np.int8), (rows, cols)),
+                          shape=(self.ndof, self.ndof))
+        A.sum_duplicates()
+        A.sort_indices()
+        return A.indptr.astype(np.int64), A.indices.astype(np.int32)
+
+    # ---- data handed to C -----------------------------------------------------------------
+    def cells_struct(self, force=None, with_qpoints=True):
+        keep = [self.cell_dofs, self.cell_invJ, self.cell_detJ, self.cell_measure,
+                self.qpoints if with_qpoints else None,
+                None if force is None else np.ascontiguousarray(force, dtype=np.float64)]
+        s = _Cells(self.ncell, _p(keep[0], c_i32_p), *[_p(a, c_double_p) for a in keep[1:]])
+        s._keep = keep
+        return s
+
+    def color_lists(self):
+        order = np.argsort(self.cell_color, kind="stable").astype(np.int32)
+        ncolor = int(self.cell_color.max()) + 1
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(self.cell_color, minlength=ncolor))])
+        return ptr.astype(np.int32), order, ncolor
+
+    def evaluate_force(self, fn):
+        """Forcing values at the quadrature points (gls_navier_stokes.cc:364-369)."""
+        f = fn(self.qpoints.reshape(-1, self.dim))
+        return np.ascontiguousarray(f[:, :self.dim].reshape(self.ncell, self.fe.nq, self.dim))
+
+    def apply_nonzero_constraints(self, U):
+        """PhysicsSolver::apply_constraints -> nonzero_constraints.distribute
+        (include/core/physics_solver.h:98-102)."""
+        U = U.copy()
+        m = self.constrained != 0
+        U[m] = self.constraint_value[m]
+        return U
+
+
+# ----------------------------------------------------------------------------------------------
+# time integration scalars
+# ----------------------------------------------------------------------------------------------
+SCHEMES = ("steady", "bdf1", "bdf2", "bdf3", "sdirk2_1", "sdirk2_2", "sdirk3_1", "sdirk3_2",
+           "sdirk3_3")
+
+
+def bdf_coefficients(order, dts):
+    out = np.zeros(order + 1)
+    d = np.ascontiguousarray(dts, dtype=np.float64)
+    lib().glso_bdf_coefficients(C.c_int(order), _p(d, c_double_p), _p(out, c_double_p))
+    return out
+
+
+def sdirk_coefficients(order, dt):
+    """source/core/sdirk.cc:11-44."""
+    sdt = 1.0 / dt
+    if order == 2:
+        alpha = (2.0 - math.sqrt(2)) / 2.0
+        m = np.zeros((2, 3))
+        m[0, 0] = 1.0 / alpha * sdt
+        m[0, 1] = -1.0 / alpha * sdt
+        m[1, 0] = 1.0 / alpha * sdt
+        m[1, 1] = -(2 * alpha - 1) / alpha / alpha * sdt
+        m[1, 2] = -(1 - alpha) / alpha / alpha * sdt
+        return m
+    m = np.zeros((3, 4))
+    m[0, 0] = 2.29428036027904 * sdt
+    m[0, 1] = -2.29428036027904 * sdt
+    m[1, 0] = 2.29428036027904 * sdt
+    m[1, 1] = -0.809559354637498 * sdt
+    m[1, 2] = -1.48472100564154 * sdt
+    m[2, 0] = 2.29428036027904 * sdt
+    m[2, 1] = 2.87009860433106 * sdt
+    m[2, 2] = -8.55612780155264 * sdt
+    m[2, 3] = 3.39174883694255 * sdt
+    return m
+
+
+def scheme_params(scheme, dts, viscosity, srf=False, omega=(0.0, 0.0, 0.0)):
+    """The compile-time dispatch of assemble_matrix_and_rhs / assemble_rhs
+    (gls_navier_stokes.cc:916-1128) reduced to (transient, 1/dt, coefs[4])."""
+    p = _Params()
+    p.viscosity = viscosity
+    p.srf = 1 if srf else 0
+    p.omega[:] = omega
+    coefs = np.zeros(4)
+    if scheme == "steady":
+        p.transient, p.sdt = 0, 0.0
+    else:
+        p.transient, p.sdt = 1, 1.0 / dts[0]
+        if scheme.startswith("bdf"):
+            order = int(scheme[3])
+            coefs[:order + 1] = bdf_coefficients(order, dts)
+        else:
+            order, step = int(scheme[5]), int(scheme[7])
+            row = sdirk_coefficients(order, dts[0])[step - 1]
+            coefs[:step + 1] = row[:step + 1]
+    p.coefs[:] = coefs
+    return p
+
+
+# ----------------------------------------------------------------------------------------------
+# hot path wrappers
+# ----------------------------------------------------------------------------------------------
+def assemble(mesh, U, params, assemble_matrix=True, force=None, U1=None, U2=None, U3=None,
+             return_local=False, threads=1):
+    """assembleGLS. Returns (val or None, rhs[, localM, localb])."""
+    L = lib()
+    fe_s, cs = mesh.fe.cstruct(), mesh.cells_struct(force)
+    N, n = mesh.ndof, mesh.fe.n
+    nnz = int(mesh.rowptr[-1])
+    val = np.zeros(nnz) if assemble_matrix else None
+    rhs = np.zeros(N)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    hist = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (U1, U2, U3)]
+    common = [C.byref(fe_s), C.byref(cs), C.byref(params), C.c_int64(N), _p(U, c_double_p),
+              *[_p(a, c_double_p) for a in hist], _p(mesh.constrained, c_u8_p),
+              _p(mesh.rowptr, c_i64_p), _p(mesh.col, c_i32_p), C.c_int(1 if assemble_matrix else 0),
+              _p(val, c_double_p), _p(rhs, c_double_p)]
+    if threads == 1:
+        lM = np.zeros((mesh.ncell, n, n)) if (return_local and assemble_matrix) else None
+        lb = np.zeros((mesh.ncell, n)) if return_local else None
+        L.glso_assemble(*common, _p(lM, c_double_p), _p(lb, c_double_p))
+        if return_local:
+            return val, rhs, lM, lb
+    else:
+        ptr, order, ncolor = mesh.color_lists()
+        L.glso_set_num_threads(C.c_int(threads))
+        L.glso_assemble_mt(*common, _p(ptr, c_i32_p), _p(order, c_i32_p), C.c_int(ncolor))
+    return val, rhs
+
+
+def spmv(mesh, val, x):
+    y = np.zeros(mesh.ndof)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    lib().glso_spmv(C.c_int64(mesh.ndof), _p(mesh.rowptr, c_i64_p), _p(mesh.col, c_i32_p),
+                    _p(val, c_double_p), _p(x, c_double_p), _p(y, c_double_p))
+    return y
+
+
+def _blocks(ndof, block_ptr):
+    if block_ptr is None:
+        block_ptr = np.array([0, ndof], dtype=np.int64)
+    block_ptr = np.ascontiguousarray(block_ptr, dtype=np.int64)
+    return block_ptr, block_ptr.size - 1
+
+
+def ilu0(mesh, val, atol=1e-8, rtol=1.0, block_ptr=None):
+    """setup_ILU with fill 0. Returns (lu, diag_pos)."""
+    bp, nb = _blocks(mesh.ndof, block_ptr)
+    lu = np.zeros_like(val)
+    dp = np.zeros(mesh.ndof, dtype=np.int64)
+    st = lib().glso_ilu0(C.c_int64(mesh.ndof), _p(mesh.rowptr, c_i64_p), _p(mesh.col, c_i32_p),
+                         _p(val, c_double_p), C.c_double(atol), C.c_double(rtol), C.c_int(nb),
+                         _p(bp, c_i64_p), _p(lu, c_double_p), _p(dp, c_i64_p))
+    if st:
+        raise ZeroDivisionError("zero pivot in row %d" % (st - 1))
+    return lu, dp
+
+
+def ilu_apply(mesh, lu, dp, r, block_ptr=None):
+    bp, nb = _blocks(mesh.ndof, block_ptr)
+    z = np.zeros(mesh.ndof)
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    lib().glso_ilu_apply(C.c_int64(mesh.ndof), _p(mesh.rowptr, c_i64_p), _p(mesh.col, c_i32_p),
+                         _p(lu, c_double_p), _p(dp, c_i64_p), C.c_int(nb), _p(bp, c_i64_p),
+                         _p(r, c_double_p), _p(z, c_double_p))
+    return z
+
+
+def gmres(mesh, val, lu, dp, b, tol, max_iters=1000, restart=30, block_ptr=None):
+    """Returns (x, iterations, true_residual, converged, residual_history)."""
+    bp, nb = _blocks(mesh.ndof, block_ptr)
+    x = np.zeros(mesh.ndof)
+    it = C.c_int(0)
+    tr = C.c_double(0)
+    hist = np.zeros(max_iters + 1)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    st = lib().glso_gmres(C.c_int64(mesh.ndof), _p(mesh.rowptr, c_i64_p), _p(mesh.col, c_i32_p),
+                          _p(val, c_double_p), _p(lu, c_double_p), _p(dp, c_i64_p), C.c_int(nb),
+                          _p(bp, c_i64_p), _p(b, c_double_p), C.c_double(tol), C.c_int(max_iters),
+                          C.c_int(restart), _p(x, c_double_p), C.byref(it), C.byref(tr),
+                          _p(hist, c_double_p))
+    return x, it.value, tr.value, st == 0, hist[:it.value + 1]
+
+
+class NoConvergence(RuntimeError):
+    """SolverControl::NoConvergence stand-in."""
+
+
+def solve_linear_system(mesh, val, rhs, rel=1e-3, abs_=1e-8, max_iters=1000, ilu_atol=1e-8,
+                        ilu_rtol=1.0, restart=30, block_ptr=None):
+    """solve_system_GMRES (gls_navier_stokes.cc:1242-1289). Returns (newton_update, iters, res)."""
+    tol = max(rel * float(np.linalg.norm(rhs)), abs_)
+    lu, dp = ilu0(mesh, val, ilu_atol, ilu_rtol, block_ptr)
+    x, it, res, ok, _ = gmres(mesh, val, lu, dp, rhs, tol, max_iters, restart, block_ptr)
+    if not ok:
+        raise NoConvergence("GMRES did not converge in %d iterations" % it)
+    x[mesh.constrained != 0] = 0.0      # zero_constraints.distribute (:1287)
+    return x, it, res
+
+
+def newton_solve(mesh, U0, params, force=None, tol=1e-6, max_it=10, lin=None, hist=(None,) * 3,
+                 log=None):
+    """NewtonNonLinearSolver::solve (include/core/newton_non_linear_solver.h:76-139).
+    `log` collects (gmres_iters, true_res) per Newton step, like restart_01.output."""
+    lin = lin or {}
+    present = U0.copy()
+    current_res = last_res = 1.0
+    it = 0
+    U1, U2, U3 = hist
+    while current_res > tol and it < max_it:
+        evaluation_point = present
+        val, rhs = assemble(mesh, evaluation_point, params, True, force, U1, U2, U3)
+        if it == 0:
+            current_res = float(np.linalg.norm(rhs))
+            last_res = current_res
+        dx, k, res = solve_linear_system(mesh, val, rhs, **lin)
+        if log is not None:
+            log.append((k, res))
+        alpha = 1.0
+        while alpha > 1e-3:
+            local = mesh.apply_nonzero_constraints(present + alpha * dx)
+            evaluation_point = local
+            _, rhs = assemble(mesh, evaluation_point, params, False, force, U1, U2, U3)
+            current_res = float(np.linalg.norm(rhs))
+            if current_res < 0.9 * last_res or last_res < tol:
+                break
+            alpha *= 0.5
+        present = evaluation_point
+        last_res = current_res
+        it += 1
+    return present, it, current_res
+
+
+def l2_error(mesh, U, exact):
+    """calculate_L2_error (navier_stokes_base.cc:255-380): QGauss(nq1+1), mean-free pressure.
+    exact(x[:, dim]) -> [:, dim+1]. Returns (err_u, err_p)."""
+    dim = mesh.dim
+    fe = FETables(dim, mesh.pu, mesh.pp, mesh.fe.nq1 + 1)
+    xq = mesh.lo + (mesh.cell_idx[:, None, :] + fe.xq[None, :, :]) * mesh.hx
+    ex = exact(xq.reshape(-1, dim)).reshape(mesh.ncell, fe.nq, dim + 1)
+    JxW = mesh.cell_detJ[:, None] * fe.wq[None, :]
+    n_su = fe.n_su
+    Uc = U[mesh.cell_dofs]
+    uh = np.stack([Uc[:, c * n_su:(c + 1) * n_su] @ fe.Nu.T for c in range(dim)], axis=2)
+    ph = Uc[:, dim * n_su:] @ fe.Np.T
+    vol = JxW.sum()
+    pavg, pex_avg = (ph * JxW).sum() / vol, (ex[:, :, dim] * JxW).sum() / vol
+    eu = (((uh - ex[:, :, :dim]) ** 2).sum(axis=2) * JxW).sum()
+    ep = ((((ph - pavg) - (ex[:, :, dim] - pex_avg)) ** 2) * JxW).sum()
+    return math.sqrt(eu), math.sqrt(ep)

@@ -1,0 +1,72 @@
+"""Pins the CPU oracle against the reference's own golden files.
+
+The expected numbers below are copied from the reference's checked-in test outputs; the inputs
+(mesh, forcing, solver settings) are those of the corresponding reference test."""
+import numpy as np
+import pytest
+
+from tests import mms
+
+
+def test_bdf_coefficients_bdf_01_output(oracle):
+    # tests/core/bdf_01.output: dt = 0.1, 0.2, 0.3
+    dts = [0.1, 0.2, 0.3]
+    assert np.allclose(oracle.bdf_coefficients(1, dts), [10.0, -10.0], rtol=0, atol=5e-5)
+    assert np.allclose(oracle.bdf_coefficients(2, dts), [13.3333, -15.0, 1.66667], rtol=0, atol=5e-5)
+    assert np.allclose(oracle.bdf_coefficients(3, dts), [15.0, -18.0, 3.33333, -0.333333],
+                       rtol=0, atol=5e-6)
+
+
+def test_restart_01_output(oracle):
+    """tests/solvers/restart_01.output:2-8 — GMRES(30)+ILU(0) iteration count and true residual per
+    Newton step, then the velocity L2 error. 2D Q1-Q1, hyper_cube(-1,1) refined 4x, no-slip, nu=1,
+    all .prm defaults (Newton 1e-6/10; GMRES rel 1e-3, abs 1e-8, 1000; ILU 0, 1e-8, 1)."""
+    m = oracle.BoxMesh(2, 16, 1, 1)
+    assert m.ndof == 867
+    f = m.evaluate_force(mms.forcing_2d)
+    pr = oracle.scheme_params("steady", [1.0], 1.0)
+    log = []
+    U, it, res = oracle.newton_solve(m, np.zeros(m.ndof), pr, f, log=log)
+    assert [k for k, _ in log] == [8, 6, 10]
+    golden = [0.00204885, 9.85227e-05, 3.32384e-08]
+    for (_, r), g in zip(log, golden):
+        assert float("%.6g" % r) == g          # every printed digit
+    err_u, _ = oracle.l2_error(m, U, mms.exact_2d)
+    assert float("%.6g" % err_u) == 0.0343628
+    # "Error after zeroing the solution: 0.612372" = ||u_exact||
+    assert float("%.6g" % oracle.l2_error(m, np.zeros(m.ndof), mms.exact_2d)[0]) == 0.612372
+
+
+@pytest.mark.parametrize("n,ndof,eu,ep", [(4, 500, 5.4021e-01, 4.5537e-02),
+                                          (8, 2916, 1.3126e-01, 1.7717e-01)])
+def test_mms3d_gls_output(oracle, n, ndof, eu, ep):
+    """applications_tests/gls_navier_stokes_3d/mms3d_gls.output:13-18 (3D Q1-Q1, nu=1, Newton 1e-8).
+    The reference solves the linear systems with AMG; the converged Newton solution is
+    solver-independent, so GMRES+ILU(0) with that .prm's tolerances is used here."""
+    m = oracle.BoxMesh(3, n, 1, 1)
+    assert m.ndof == ndof and m.ncell == n ** 3
+    f = m.evaluate_force(mms.forcing_3d)
+    pr = oracle.scheme_params("steady", [1.0], 1.0)
+    U, it, res = oracle.newton_solve(m, np.zeros(m.ndof), pr, f, tol=1e-8,
+                                     lin=dict(rel=1e-4, abs_=1e-9, max_iters=5000, ilu_atol=1e-10))
+    assert res < 1e-8
+    err_u, err_p = oracle.l2_error(m, U, mms.exact_3d)
+    assert float("%.5g" % err_u) == eu
+    assert float("%.5g" % err_p) == ep
+
+
+@pytest.mark.parametrize("n,ndof,eu,ep", [(8, 243, 1.3284e-01, 1.7844e-01),
+                                          (16, 867, 3.4363e-02, 9.7118e-02),
+                                          (32, 3267, 8.7362e-03, 3.0300e-02)])
+def test_mms2d_gls_output(oracle, n, ndof, eu, ep):
+    """applications_tests/gls_navier_stokes_2d/mms2d_gls.output:24-26. The reference uses ILU(4) as
+    the preconditioner; the Newton-converged solution does not depend on it."""
+    m = oracle.BoxMesh(2, n, 1, 1)
+    assert m.ndof == ndof
+    f = m.evaluate_force(mms.forcing_mms2d)
+    pr = oracle.scheme_params("steady", [1.0], 1.0)
+    U, it, res = oracle.newton_solve(m, np.zeros(m.ndof), pr, f, tol=1e-8,
+                                     lin=dict(rel=1e-4, abs_=1e-9, max_iters=5000))
+    err_u, err_p = oracle.l2_error(m, U, mms.exact_mms2d)
+    assert float("%.5g" % err_u) == eu
+    assert float("%.5g" % err_p) == ep
