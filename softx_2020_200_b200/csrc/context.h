@@ -1,0 +1,203 @@
+// Internal state of a glsns_context (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/glsns.h"
+
+namespace glsns
+{
+  struct Error
+  {
+    glsns_status code;
+    std::string  msg;
+  };
+
+  // Device allocation owned by the context.
+  template <typename T>
+  struct DevBuf
+  {
+    T     *p = nullptr;
+    size_t n = 0;
+    void
+    release()
+    {
+      if (p)
+        cudaFree(p);
+      p = nullptr;
+      n = 0;
+    }
+  };
+
+  struct EventPair
+  {
+    cudaEvent_t a = nullptr, b = nullptr;
+  };
+
+  // One timer class: a pool of event pairs recorded around launches, drained
+  // (elapsed times summed) whenever the stream is known to be idle.
+  struct KernelTimer
+  {
+    std::vector<EventPair> pool;
+    size_t                 used = 0;
+    double                 ms   = 0;
+    int64_t                calls = 0;
+  };
+
+  enum TimerId
+  {
+    T_ASSEMBLE_SYSTEM = 0,
+    T_ASSEMBLE_RHS,
+    T_SETUP_ILU,
+    T_SOLVE,
+    T_SPMV,
+    T_TRSV,
+    T_ORTHOG,
+    T_COUNT
+  };
+} // namespace glsns
+
+struct glsns_context
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  std::string  err;
+
+  // ---- finite element tables ----
+  bool    have_fe = false;
+  int32_t dim = 0, vel_degree = 0, n_su = 0, n_sp = 0, n_q = 0, n_loc = 0;
+  glsns::DevBuf<double> shape_u, grad_u, hess_u, shape_p, grad_p, weights;
+
+  // ---- mesh ----
+  bool    have_mesh = false;
+  int64_t n_dofs = 0, n_owned = 0, n_cells = 0, nnz = 0;
+  int32_t geometry_per_q = 0, n_colors = 0;
+  glsns::DevBuf<int32_t> cell_dofs, col, color_cells, order_l, order_u;
+  glsns::DevBuf<int64_t> rowptr, diag_pos;
+  glsns::DevBuf<double>  inv_jac, det_jac, measure, q_points, force, cvalues;
+  glsns::DevBuf<uint8_t> constrained;
+  std::vector<int32_t>   color_ptr;
+  int32_t                levels_l = 0, levels_u = 0;
+  int32_t                max_row_len = 0;
+  double                 avg_row_len = 0;
+
+  // ---- physics ----
+  double  viscosity = 1.0;
+  int32_t srf       = 0;
+  double  omega[3]  = {0, 0, 0};
+  bool    have_force = false;
+
+  // ---- matrix / factors / vectors ----
+  glsns::DevBuf<double> val, lu;
+  bool                  have_matrix = false, have_ilu = false, have_rhs = false;
+  glsns::DevBuf<double> vec[7];
+  bool                  vec_set[7] = {false, false, false, false, false, false, false};
+
+  // ---- solver workspace ----
+  int32_t               krylov_m = 0;
+  glsns::DevBuf<double> V, w, zg, ytmp, tvec, partials, hbuf, ycoef;
+  glsns::DevBuf<int32_t> counters; // [0] ticket, [1] error flag
+  glsns::DevBuf<int32_t> row_done; // factorisation flags
+  int32_t               epoch = 0;
+  double               *h_pinned = nullptr; // 80 doubles
+  int32_t               n_sm = 148;
+
+  // ---- communication ----
+  int32_t n_ranks = 1, rank = 0;
+  void   *nccl_comm = nullptr;
+  int32_t n_neighbors = 0;
+  std::vector<int32_t>   neighbor_rank;
+  std::vector<int64_t>   send_ptr, recv_ptr;
+  glsns::DevBuf<int32_t> send_idx;
+  glsns::DevBuf<double>  send_buf;
+
+  // ---- timers ----
+  glsns::KernelTimer timers[glsns::T_COUNT];
+  int64_t            kernel_launches = 0;
+  bool               timing_enabled  = true;
+};
+
+namespace glsns
+{
+  // error helpers -----------------------------------------------------------
+  glsns_status fail(glsns_context *ctx, glsns_status code, const std::string &msg);
+  glsns_status cuda_fail(glsns_context *ctx, cudaError_t e, const char *what);
+
+#define GLSNS_CUDA(ctx, call)                                         \
+  do                                                                  \
+    {                                                                 \
+      cudaError_t e__ = (call);                                       \
+      if (e__ != cudaSuccess)                                         \
+        return glsns::cuda_fail(ctx, e__, #call);                     \
+    }                                                                 \
+  while (0)
+
+#define GLSNS_TRY(expr)                \
+  do                                   \
+    {                                  \
+      glsns_status s__ = (expr);       \
+      if (s__ != GLSNS_OK)             \
+        return s__;                    \
+    }                                  \
+  while (0)
+
+  template <typename T>
+  glsns_status
+  dev_alloc(glsns_context *ctx, DevBuf<T> &b, size_t n)
+  {
+    if (b.n == n && b.p)
+      return GLSNS_OK;
+    b.release();
+    if (n == 0)
+      return GLSNS_OK;
+    cudaError_t e = cudaMalloc((void **)&b.p, n * sizeof(T));
+    if (e != cudaSuccess)
+      return cuda_fail(ctx, e, "cudaMalloc");
+    b.n = n;
+    return GLSNS_OK;
+  }
+
+  template <typename T>
+  glsns_status
+  dev_upload(glsns_context *ctx, DevBuf<T> &b, const T *host, size_t n)
+  {
+    GLSNS_TRY(dev_alloc(ctx, b, n));
+    if (n)
+      GLSNS_CUDA(ctx, cudaMemcpyAsync(b.p, host, n * sizeof(T), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+    return GLSNS_OK;
+  }
+
+  // timers ------------------------------------------------------------------
+  void timer_begin(glsns_context *ctx, TimerId id);
+  void timer_end(glsns_context *ctx, TimerId id);
+  void timers_drain(glsns_context *ctx); // requires an idle stream
+
+  // kernels (host launchers) ---------------------------------------------------
+  // assembly.cu
+  glsns_status launch_assembly(glsns_context *ctx, bool assemble_matrix, bool transient,
+                               double sdt, const double coefs[4]);
+  // sparse.cu
+  glsns_status launch_spmv(glsns_context *ctx, const double *x, double *y);
+  glsns_status ilu_analyse(glsns_context *ctx, const int64_t *rowptr, const int32_t *col);
+  glsns_status launch_ilu_factor(glsns_context *ctx, double atol, double rtol);
+  glsns_status launch_ilu_apply(glsns_context *ctx, const double *r, double *z);
+  // krylov.cu
+  glsns_status ensure_workspace(glsns_context *ctx, int restart);
+  glsns_status device_norm2(glsns_context *ctx, const double *x, double *out);
+  glsns_status gmres_solve(glsns_context *ctx, const glsns_linear_solver_params *p,
+                           glsns_solve_info *info);
+  glsns_status time_orthog(glsns_context *ctx, int nvec);
+  glsns_status launch_axpy_constraints(glsns_context *ctx, double alpha);
+  glsns_status launch_zero_constrained(glsns_context *ctx, double *x);
+  // comm.cu
+  glsns_status comm_unique_id(uint8_t out[128]);
+  glsns_status comm_init(glsns_context *ctx, int32_t n_ranks, int32_t rank,
+                         const uint8_t unique_id[128]);
+  void         comm_destroy(glsns_context *ctx);
+  glsns_status allreduce_sum(glsns_context *ctx, double *dev, int n);
+  glsns_status halo_exchange(glsns_context *ctx, double *ghosted);
+} // namespace glsns

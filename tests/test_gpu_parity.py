@@ -1,0 +1,209 @@
+"""GPU parity tests: the CUDA hot path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Tolerances: matrix entries 1e-12 relative to the row max-abs, RHS 1e-12
+relative to its inf-norm (BASELINE.json north_star, SURVEY.md §8a note 5); GMRES iteration counts
+within +-2; Newton solution 1e-10 relative L2."""
+import numpy as np
+import pytest
+
+from tests import mms
+from tests.util import hotpath_from_oracle_mesh, random_state, row_scaled_error
+
+pytestmark = pytest.mark.gpu
+
+TOL_ENTRY = 1e-12
+
+CASES = [  # dim, n, pu, pp
+    (2, 6, 1, 1), (2, 5, 2, 2), (2, 5, 2, 1), (3, 3, 1, 1), (3, 3, 2, 2), (3, 2, 2, 1)]
+
+
+def _check_assembly(oracle, mesh, hp, U, scheme, dts, hist, force, nu, srf=False, omega=(0, 0, 0)):
+    pr = oracle.scheme_params(scheme, dts, nu, srf, omega)
+    a_ref, b_ref = oracle.assemble(mesh, U, pr, True, force, *hist)
+    hp.set_vector("evaluation_point", U)
+    for name, h in zip(("solution_m1", "solution_m2", "solution_m3"), hist):
+        if h is not None:
+            hp.set_vector(name, h)
+    hp.assemble(True, scheme, dts)
+    a_gpu, b_gpu = hp.get_matrix_values(), hp.get_vector("system_rhs")
+    assert row_scaled_error(mesh, a_gpu, a_ref) <= TOL_ENTRY
+    assert np.max(np.abs(b_gpu - b_ref)) <= TOL_ENTRY * np.max(np.abs(b_ref))
+    assert abs(hp.rhs_norm() - np.linalg.norm(b_ref)) <= 1e-12 * np.linalg.norm(b_ref)
+    # rhs-only assembly must give the same residual and leave the matrix untouched
+    hp.assemble(False, scheme, dts)
+    assert np.max(np.abs(hp.get_vector("system_rhs") - b_ref)) <= TOL_ENTRY * np.max(np.abs(b_ref))
+    assert np.array_equal(hp.get_matrix_values(), a_gpu)
+    return a_ref, b_ref
+
+
+@pytest.mark.parametrize("dim,n,pu,pp", CASES)
+def test_assembly_steady(oracle, dim, n, pu, pp):
+    mesh = oracle.BoxMesh(dim, n, pu, pp)
+    force = mesh.evaluate_force(mms.forcing_2d if dim == 2 else mms.forcing_3d)
+    hp = hotpath_from_oracle_mesh(mesh, 0.37, force)
+    _check_assembly(oracle, mesh, hp, random_state(mesh), "steady", None, (None,) * 3, force, 0.37)
+    hp.close()
+
+
+@pytest.mark.parametrize("scheme", ["bdf1", "bdf2", "bdf3", "sdirk2_1", "sdirk2_2", "sdirk3_1",
+                                    "sdirk3_2", "sdirk3_3"])
+@pytest.mark.parametrize("dim,n,pu,pp", [(2, 4, 2, 1), (3, 2, 2, 2)])
+def test_assembly_transient(oracle, scheme, dim, n, pu, pp):
+    mesh = oracle.BoxMesh(dim, n, pu, pp)
+    hp = hotpath_from_oracle_mesh(mesh, 0.05, None)
+    hist = tuple(random_state(mesh, seed=s) for s in (11, 12, 13))
+    _check_assembly(oracle, mesh, hp, random_state(mesh), scheme, [0.1, 0.2, 0.3], hist, None, 0.05)
+    hp.close()
+
+
+@pytest.mark.parametrize("dim,n,pu,pp,omega", [(2, 4, 1, 1, (0, 0, 1.7)), (3, 2, 2, 2, (0.3, -0.4, 1.1)),
+                                               (3, 3, 1, 1, (0, 0, -6.28318))])
+def test_assembly_rotating_frame(oracle, dim, n, pu, pp, omega):
+    mesh = oracle.BoxMesh(dim, n, pu, pp)
+    hp = hotpath_from_oracle_mesh(mesh, 0.2, None, True, omega)
+    _check_assembly(oracle, mesh, hp, random_state(mesh), "steady", None, (None,) * 3, None, 0.2,
+                    True, omega)
+    _check_assembly(oracle, mesh, hp, random_state(mesh, 5), "bdf2", [0.05, 0.05, 0.05],
+                    (random_state(mesh, 6), random_state(mesh, 7), None), None, 0.2, True, omega)
+    hp.close()
+
+
+def test_assembly_lid_driven_cavity_bcs(oracle):
+    """Inhomogeneous (lid) + homogeneous Dirichlet rows, 3D Q2-Q2 cavity (the bench workload)."""
+    lid = lambda x: np.stack([np.ones(len(x)), 0 * x[:, 0], 0 * x[:, 0]], axis=1)
+    bcs = {0: ("noslip",), 1: ("noslip",), 2: ("noslip",), 4: ("noslip",), 5: ("noslip",),
+           3: ("function", lid)}
+    mesh = oracle.BoxMesh(3, 3, 2, 2, bcs=bcs)
+    hp = hotpath_from_oracle_mesh(mesh, 0.005, None)
+    U = mesh.apply_nonzero_constraints(np.zeros(mesh.ndof))
+    _check_assembly(oracle, mesh, hp, U, "steady", None, (None,) * 3, None, 0.005)
+    _check_assembly(oracle, mesh, hp, random_state(mesh, 3, 0.3), "steady", None, (None,) * 3, None,
+                    0.005)
+    hp.close()
+
+
+@pytest.mark.parametrize("dim,n,pu,pp", CASES)
+def test_spmv_ilu_against_oracle(oracle, dim, n, pu, pp):
+    mesh = oracle.BoxMesh(dim, n, pu, pp)
+    hp = hotpath_from_oracle_mesh(mesh, 0.1, None)
+    U = random_state(mesh, scale=0.5)
+    a_ref, b_ref = oracle.assemble(mesh, U, oracle.scheme_params("steady", None, 0.1), True)
+    hp.set_matrix_values(a_ref)
+    x = np.random.default_rng(7).standard_normal(mesh.ndof)
+    y_ref = oracle.spmv(mesh, a_ref, x)
+    assert np.max(np.abs(hp.spmv(x) - y_ref)) <= 1e-13 * np.max(np.abs(y_ref))
+    lu_ref, dp = oracle.ilu0(mesh, a_ref, 1e-8, 1.0)
+    hp.setup_ilu(0, 1e-8, 1.0)
+    lu = hp.get_ilu_values()
+    assert row_scaled_error(mesh, lu, lu_ref) <= 1e-11
+    z_ref = oracle.ilu_apply(mesh, lu_ref, dp, x)
+    z = hp.ilu_apply(x)
+    assert np.max(np.abs(z - z_ref)) <= 1e-10 * np.max(np.abs(z_ref))
+    lo, up = hp.ilu_levels()
+    assert 1 <= lo <= mesh.ndof and 1 <= up <= mesh.ndof
+    hp.close()
+
+
+def test_ilu_diagonal_perturbation_and_zero_pivot(oracle):
+    from softx_2020_200_b200 import GlsnsError
+    mesh = oracle.BoxMesh(2, 3, 1, 1)
+    hp = hotpath_from_oracle_mesh(mesh)
+    a_ref, _ = oracle.assemble(mesh, random_state(mesh), oracle.scheme_params("steady", None, 1.0), True)
+    hp.set_matrix_values(a_ref)
+    for atol, rtol in ((1e-3, 1.0), (0.0, 1.5), (1e-12, 1.0)):
+        hp.setup_ilu(0, atol, rtol)
+        lu_ref, _ = oracle.ilu0(mesh, a_ref, atol, rtol)
+        assert row_scaled_error(mesh, hp.get_ilu_values(), lu_ref) <= 1e-11
+    hp.set_matrix_values(np.zeros_like(a_ref))
+    with pytest.raises(GlsnsError) as e:
+        hp.setup_ilu(0, 0.0, 1.0)
+    assert e.value.status == 4  # GLSNS_ERR_ZERO_PIVOT
+    with pytest.raises(GlsnsError) as e:
+        hp.setup_ilu(1, 1e-8, 1.0)
+    assert e.value.status == 6  # fill > 0 not built
+    hp.close()
+
+
+def _newton_gpu(hp, mesh, U0, scheme="steady", dts=None, tol=1e-6, max_it=10, lin=None, log=None):
+    """NewtonNonLinearSolver::solve (newton_non_linear_solver.h:76-139) over the C ABI with the
+    device-resident line search."""
+    lin = lin or {}
+    hp.set_vector("present_solution", U0)
+    hp.set_vector("evaluation_point", U0)
+    current_res = last_res = 1.0
+    it = 0
+    while current_res > tol and it < max_it:
+        hp.assemble(True, scheme, dts)
+        if it == 0:
+            current_res = last_res = hp.rhs_norm()
+        _, info = hp.solve_linear_system(download=False, **lin)
+        if log is not None:
+            log.append((info["iterations"], info["true_residual"]))
+        alpha = 1.0
+        while alpha > 1e-3:
+            hp.line_search_point(alpha)
+            hp.assemble(False, scheme, dts)
+            current_res = hp.rhs_norm()
+            if current_res < 0.9 * last_res or last_res < tol:
+                break
+            alpha *= 0.5
+        hp.accept_evaluation_point()
+        last_res = current_res
+        it += 1
+    return hp.get_vector("present_solution"), it, current_res
+
+
+def test_restart_01_golden_on_gpu(oracle):
+    """The reference's tests/solvers/restart_01.output reproduced by the CUDA path: GMRES iteration
+    counts 8/6/10 and true residuals per Newton step, velocity L2 error 0.0343628."""
+    mesh = oracle.BoxMesh(2, 16, 1, 1)
+    force = mesh.evaluate_force(mms.forcing_2d)
+    hp = hotpath_from_oracle_mesh(mesh, 1.0, force)
+    log = []
+    U, it, res = _newton_gpu(hp, mesh, np.zeros(mesh.ndof), log=log)
+    assert [k for k, _ in log] == [8, 6, 10]
+    for (_, r), g in zip(log, [0.00204885, 9.85227e-05, 3.32384e-08]):
+        assert abs(r - g) <= 2e-6 * g
+    err_u, _ = oracle.l2_error(mesh, U, mms.exact_2d)
+    assert float("%.6g" % err_u) == 0.0343628
+    hp.close()
+
+
+@pytest.mark.parametrize("dim,n,pu,pp,nu", [(3, 4, 1, 1, 1.0), (3, 3, 2, 2, 1.0), (2, 8, 2, 2, 0.1)])
+def test_newton_solution_matches_oracle(oracle, dim, n, pu, pp, nu):
+    mesh = oracle.BoxMesh(dim, n, pu, pp)
+    force = mesh.evaluate_force(mms.forcing_2d if dim == 2 else mms.forcing_3d)
+    lin = dict(rel=1e-4, abs_=1e-9, max_iters=5000, ilu_atol=1e-10)
+    log_ref, log = [], []
+    U_ref, it_ref, _ = oracle.newton_solve(mesh, np.zeros(mesh.ndof),
+                                           oracle.scheme_params("steady", None, nu), force,
+                                           tol=1e-8, lin=lin, log=log_ref)
+    hp = hotpath_from_oracle_mesh(mesh, nu, force)
+    U, it, res = _newton_gpu(hp, mesh, np.zeros(mesh.ndof), tol=1e-8, log=log,
+                             lin=dict(relative_residual=1e-4, minimum_residual=1e-9,
+                                      max_iterations=5000, ilu_atol=1e-10))
+    assert it == it_ref
+    for (k, _), (k_ref, _) in zip(log, log_ref):
+        assert abs(k - k_ref) <= 2
+    # the two runs stop GMRES at slightly different iterates; both are Newton-converged to 1e-8
+    assert np.linalg.norm(U - U_ref) <= 1e-7 * np.linalg.norm(U_ref)
+    hp.close()
+
+
+def test_gmres_no_convergence_and_state_errors(oracle):
+    from softx_2020_200_b200 import GlsnsError, NoConvergence
+    mesh = oracle.BoxMesh(2, 8, 1, 1)
+    force = mesh.evaluate_force(mms.forcing_2d)
+    hp = hotpath_from_oracle_mesh(mesh, 1.0, force)
+    with pytest.raises(GlsnsError) as e:        # solve before assemble
+        hp.solve_linear_system()
+    assert e.value.status == 5
+    hp.set_vector("evaluation_point", np.zeros(mesh.ndof))
+    hp.assemble(True)
+    with pytest.raises(NoConvergence) as e:     # SolverControl::NoConvergence
+        hp.solve_linear_system(relative_residual=1e-14, minimum_residual=1e-14, max_iterations=3)
+    assert e.value.info["iterations"] == 3
+    with pytest.raises(GlsnsError):             # umbrella scheme value
+        hp.assemble(True, "sdirk2", [0.1])
+    with pytest.raises(GlsnsError):             # transient without history
+        hp.assemble(True, "bdf1", [0.1])
+    hp.close()
