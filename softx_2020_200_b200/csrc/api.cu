@@ -240,9 +240,11 @@ glsns_destroy(glsns_context *ctx)
   for (auto &v : ctx->vec)
     v.release();
   DevBuf<int32_t> *i32[] = {&ctx->cell_dofs, &ctx->col, &ctx->color_cells, &ctx->order_l,
-                            &ctx->order_u, &ctx->counters, &ctx->row_done, &ctx->send_idx};
+                            &ctx->counters, &ctx->row_done, &ctx->send_idx};
   for (auto *b : i32)
     b->release();
+  ctx->desc_l.release();
+  ctx->desc_u.release();
   ctx->rowptr.release();
   ctx->diag_pos.release();
   ctx->constrained.release();

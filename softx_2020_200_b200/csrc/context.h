@@ -32,6 +32,19 @@ namespace glsns
     }
   };
 
+  // One group of consecutive rows with identical patterns, as the triangular-solve
+  // kernels consume it (one 32-byte record per ticket).
+  struct TrsvGroup
+  {
+    int64_t rs0;  // CSR offset of the group's first row
+    int32_t r0;   // first row
+    int32_t len;  // row length (same for every row of the group)
+    int32_t nlow; // entries left of the group = offset of the in-group block
+    int32_t cnt;  // entries outside the group this sweep reads (inside the diagonal block)
+    int32_t crit; // row index of the dependency on the highest level, -1 if none
+    int32_t m;    // rows in the group
+  };
+
   struct EventPair
   {
     cudaEvent_t a = nullptr, b = nullptr;
@@ -75,12 +88,13 @@ struct glsns_context
   bool    have_mesh = false;
   int64_t n_dofs = 0, n_owned = 0, n_cells = 0, nnz = 0;
   int32_t geometry_per_q = 0, n_colors = 0;
-  glsns::DevBuf<int32_t> cell_dofs, col, color_cells, order_l, order_u;
+  glsns::DevBuf<int32_t> cell_dofs, col, color_cells, order_l;
+  glsns::DevBuf<glsns::TrsvGroup> desc_l, desc_u;
   glsns::DevBuf<int64_t> rowptr, diag_pos;
   glsns::DevBuf<double>  inv_jac, det_jac, measure, q_points, force, cvalues;
   glsns::DevBuf<uint8_t> constrained;
   std::vector<int32_t>   color_ptr;
-  int32_t                levels_l = 0, levels_u = 0;
+  int32_t                levels_l = 0, levels_u = 0, levels_rows = 0, n_groups = 0;
   int32_t                max_row_len = 0;
   double                 avg_row_len = 0;
 
