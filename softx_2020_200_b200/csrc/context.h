@@ -38,11 +38,11 @@ namespace glsns
   {
     int64_t rs0;  // CSR offset of the group's first row
     int32_t r0;   // first row
-    int32_t len;  // row length (same for every row of the group)
+    int32_t len_m; // row length (same for every row of the group) | rows in the group << 28
     int32_t nlow; // entries left of the group = offset of the in-group block
-    int32_t cnt;  // entries outside the group this sweep reads (inside the diagonal block)
+    int32_t cnt;   // entries outside the group this sweep reads (inside the diagonal block)
     int32_t crit; // row index of the dependency on the highest level, -1 if none
-    int32_t m;    // rows in the group
+    int32_t crit2; // crit of crit's group: solved => this group is one level from the front
   };
 
   struct EventPair

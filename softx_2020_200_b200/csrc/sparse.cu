@@ -265,7 +265,7 @@ namespace glsns
             break;
           const TrsvGroup d   = desc[t];
           const int64_t   rs0 = d.rs0;
-          const int       len = d.len, m = d.m, r0 = d.r0;
+          const int       len = d.len_m & 0x0FFFFFFF, m = d.len_m >> 28, r0 = d.r0;
           const int       off = UPPER ? d.nlow + m : 0; // first entry outside the group
           const int       cnt = d.cnt;                  // entries outside the group (in block)
           // in-group triangle and right-hand side, fetched early by lane 0
@@ -281,6 +281,8 @@ namespace glsns
                     for (int b = 0; b < TRSV_G; ++b)
                       if (UPPER ? (b >= a && b < m) : (b < a))
                         tri[a][b] = __ldcs(lu + rs0 + (int64_t)a * len + d.nlow + b);
+                    if (UPPER) // Ifpack stores and applies the inverted diagonal as well
+                      tri[a][a] = 1.0 / tri[a][a];
                   }
             }
           double s[TRSV_G];
@@ -328,33 +330,16 @@ namespace glsns
                           if (a < m)
                             s[a] += v[u][a] * xv;
                       }
-                  if (first && !waited && d.crit >= 0 && !(flags & 1))
+                  if (first && !waited && d.crit2 >= 0 && !(flags & 1))
                     {
-                      if (flags & 4)
+                      // phase W: far from the front the whole warp parks behind one lane
+                      // polling one address (the critical dependency of our critical
+                      // dependency); once that is solved we are one level from the front
+                      // and every lane polls its own missing entries directly.
+                      if (lane == 0)
                         {
-                          // variant: every lane parks on its own highest-column pending entry
-                          if (pending)
-                            {
-                              const int       uu = 31 - __clz(pending);
-                              int32_t         cc = c[0];
-#pragma unroll
-                              for (int u = 1; u < TRSV_UNR; ++u)
-                                if (u == uu)
-                                  cc = c[u];
-                              long long w = 0;
-                              while (ld_volatile_u64(x + cc) == SENTINEL)
-                                if (++w > SPIN_LIMIT)
-                                  {
-                                    atomicExch(&counters[1], 2);
-                                    break;
-                                  }
-                            }
-                        }
-                      else if (lane == 0)
-                        {
-                          // phase W: the whole warp parks behind one polling lane
                           long long w = 0;
-                          while (ld_volatile_u64(x + d.crit) == SENTINEL)
+                          while (ld_volatile_u64(x + d.crit2) == SENTINEL)
                             if (++w > SPIN_LIMIT)
                               {
                                 atomicExch(&counters[1], 2);
@@ -391,7 +376,7 @@ namespace glsns
                         for (int b = TRSV_G - 1; b >= 0; --b)
                           if (b > a && b < m)
                             acc -= tri[a][b] * out[b];
-                        acc /= tri[a][a];
+                        acc *= tri[a][a];
                         out[a] = acc;
                         st_result(x + r0 + a, acc);
                       }
@@ -534,9 +519,10 @@ namespace glsns
         glev[g] = l;
         nl      = std::max(nl, l);
         TrsvGroup &d = desc[g];
-        d.rs0 = rowptr[i], d.r0 = (int32_t)i, d.len = (int32_t)(rowptr[i + 1] - rowptr[i]);
+        d.rs0 = rowptr[i], d.r0 = (int32_t)i;
+        d.len_m = (int32_t)(rowptr[i + 1] - rowptr[i]) | ((grp_ptr[g + 1] - grp_ptr[g]) << 28);
         d.nlow = (int32_t)(diag[i] - rowptr[i]), d.cnt = d.nlow, d.crit = crit;
-        d.m    = grp_ptr[g + 1] - grp_ptr[g];
+        d.crit2 = crit >= 0 ? desc[grp_of[crit]].crit : -1;
       }
     ctx->levels_l = ng ? nl + 1 : 0;
     GLSNS_TRY(upload_sorted(nl, ctx->desc_l));
@@ -559,6 +545,7 @@ namespace glsns
         glev[g] = l;
         nu      = std::max(nu, l);
         desc[g].cnt = cnt, desc[g].crit = crit;
+        desc[g].crit2 = crit >= 0 ? desc[grp_of[crit]].crit : -1;
       }
     ctx->levels_u = ng ? nu + 1 : 0;
     GLSNS_TRY(upload_sorted(nu, ctx->desc_u));
@@ -617,7 +604,7 @@ namespace glsns
     const int64_t n = ctx->n_owned;
     if (n == 0)
       return GLSNS_OK;
-    const int     block = 128;
+    static const int block = getenv("GLSNS_TRSV_BLOCK") ? atoi(getenv("GLSNS_TRSV_BLOCK")) : 128;
     const int32_t ng    = ctx->n_groups;
     const int64_t want  = ((int64_t)ng * 32 + block - 1) / block;
     static const int      ctas_per_sm = getenv("GLSNS_TRSV_CTAS") ? atoi(getenv("GLSNS_TRSV_CTAS")) : 2;

@@ -1,0 +1,92 @@
+"""Python proxy of the C++ host-side mirror (include/glsns_solver.hpp, csrc/host_solver.cpp):
+glsns::GLSNavierStokesSolver driven by the mirrored NewtonNonLinearSolver /
+SkipNewtonNonLinearSolver through host buffers, exactly as the reference's Newton drivers move
+their vectors (include/core/newton_non_linear_solver.h:76-139)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .hotpath import GlsnsError, NoConvergence
+
+METHODS = _lib.SCHEMES  # Parameters::SimulationControl::TimeSteppingMethod, same order
+
+
+def _bind(L):
+    if getattr(L, "_glsnsh_solver_bound", False):
+        return
+    L.glsnsh_solver_create.restype = C.c_void_p
+    L.glsnsh_solver_create.argtypes = [C.c_void_p, C.c_char_p, _lib.c_double_p, C.c_int]
+    L.glsnsh_solver_error.restype = C.c_char_p
+    L.glsnsh_solver_error.argtypes = [C.c_void_p]
+    L.glsnsh_solver_destroy.restype = None
+    L.glsnsh_solver_destroy.argtypes = [C.c_void_p]
+    L.glsnsh_solver_set_vector.restype = None
+    L.glsnsh_solver_set_vector.argtypes = [C.c_void_p, C.c_int, _lib.c_double_p, C.c_int64]
+    L.glsnsh_solver_get_present.restype = None
+    L.glsnsh_solver_get_present.argtypes = [C.c_void_p, _lib.c_double_p, C.c_int64]
+    L.glsnsh_solver_set_time_steps.restype = None
+    L.glsnsh_solver_set_time_steps.argtypes = [C.c_void_p, _lib.c_double_p, C.c_int]
+    L.glsnsh_solver_solve_non_linear_system.restype = C.c_int
+    L.glsnsh_solver_solve_non_linear_system.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.glsnsh_solver_log.restype = C.c_char_p
+    L.glsnsh_solver_log.argtypes = [C.c_void_p]
+    L._glsnsh_solver_bound = True
+
+
+class GLSNavierStokesSolver:
+    """mesh: softx_2020_200_b200.mesh.BoxMesh; prm: text of a reference .prm file (only the
+    subsections of the hot path are read); forcing_at_q: [n_cells, n_q, dim] or None."""
+
+    def __init__(self, mesh, prm="", forcing_at_q=None, device=0):
+        self._L = _lib.lib()
+        _bind(self._L)
+        self.mesh = mesh
+        f = None if forcing_at_q is None else np.ascontiguousarray(forcing_at_q, dtype=np.float64)
+        self._h = self._L.glsnsh_solver_create(
+            mesh._h, prm.encode(), None if f is None else f.ctypes.data_as(_lib.c_double_p), device)
+        err = self._L.glsnsh_solver_error(self._h).decode()
+        if err:
+            self._L.glsnsh_solver_destroy(self._h)
+            self._h = None
+            raise GlsnsError(_lib.ERR_CUDA, err)
+
+    def set_vector(self, which, values):
+        idx = {"present_solution": 0, "solution_m1": 1, "solution_m2": 2, "solution_m3": 3}[which]
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.size == self.mesh.n_dofs
+        self._L.glsnsh_solver_set_vector(self._h, idx, v.ctypes.data_as(_lib.c_double_p), v.size)
+
+    def set_time_steps(self, dts):
+        d = np.ascontiguousarray(dts, dtype=np.float64)
+        self._L.glsnsh_solver_set_time_steps(self._h, d.ctypes.data_as(_lib.c_double_p), d.size)
+
+    @property
+    def present_solution(self):
+        out = np.empty(self.mesh.n_dofs)
+        self._L.glsnsh_solver_get_present(self._h, out.ctypes.data_as(_lib.c_double_p), out.size)
+        return out
+
+    def solve_non_linear_system(self, time_stepping_method="steady", first_iteration=False,
+                                force_matrix_renewal=True):
+        rc = self._L.glsnsh_solver_solve_non_linear_system(
+            self._h, METHODS[time_stepping_method], int(first_iteration), int(force_matrix_renewal))
+        if rc == 3:
+            raise NoConvergence(self._L.glsnsh_solver_error(self._h).decode(), {})
+        if rc:
+            raise RuntimeError(self._L.glsnsh_solver_error(self._h).decode())
+
+    @property
+    def log(self):
+        return self._L.glsnsh_solver_log(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.glsnsh_solver_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -207,3 +207,73 @@ def test_gmres_no_convergence_and_state_errors(oracle):
     with pytest.raises(GlsnsError):             # transient without history
         hp.assemble(True, "bdf1", [0.1])
     hp.close()
+
+
+def test_restart_01_through_the_cpp_mirror(oracle):
+    """The reference's own solver-level test (tests/solvers/restart_01.cc) read through the mirrored
+    C++ interface: GLSNavierStokesSolver + NewtonNonLinearSolver with all .prm defaults, host
+    vectors in and out; the log lines of solve_system_GMRES carry the golden iteration counts."""
+    import re
+    from softx_2020_200_b200.mesh import BoxMesh
+    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.test_host_mirror import _match_numbering
+    mesh = BoxMesh(2, 16, 1, 1, with_q_points=True)
+    force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)
+    s = GLSNavierStokesSolver(mesh, "", force)          # every .prm default
+    s.set_vector("present_solution", np.zeros(mesh.n_dofs))
+    s.solve_non_linear_system("steady", False, True)
+    assert re.findall(r"-Iterative solver took : (\d+) steps", s.log) == ["8", "6", "10"]
+    assert len(re.findall(r"-Tolerance of iterative solver is : ", s.log)) == 3
+    assert len(re.findall(r"Newton iteration: \d+  - Residual:", s.log)) == 3
+    nat = BoxMesh(2, 16, 1, 1, renumber=False)
+    om = oracle.BoxMesh(2, 16, 1, 1, renumber=_match_numbering(nat, mesh, 2))
+    err_u, _ = oracle.l2_error(om, s.present_solution, mms.exact_2d)
+    assert float("%.6g" % err_u) == 0.0343628
+    s.close()
+
+
+def test_cpp_mirror_error_behaviour():
+    """std::runtime_error('This solver is not allowed') for methods that are not built;
+    SolverControl::NoConvergence when max iters is hit."""
+    from softx_2020_200_b200 import NoConvergence
+    from softx_2020_200_b200.mesh import BoxMesh
+    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    mesh = BoxMesh(2, 8, 1, 1, with_q_points=True)
+    force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)
+    s = GLSNavierStokesSolver(mesh, "subsection linear solver\n set method = amg\nend\n", force)
+    s.set_vector("present_solution", np.zeros(mesh.n_dofs))
+    with pytest.raises(RuntimeError, match="This solver is not allowed"):
+        s.solve_non_linear_system("steady")
+    s.close()
+    s = GLSNavierStokesSolver(mesh, "subsection linear solver\n set max iters = 2\n"
+                                    " set relative residual = 1e-14\nend\n", force)
+    s.set_vector("present_solution", np.zeros(mesh.n_dofs))
+    with pytest.raises(NoConvergence):
+        s.solve_non_linear_system("steady")
+    s.close()
+
+
+def test_skip_newton_and_transient_through_the_cpp_mirror(oracle):
+    """skip_newton reuses Jacobian + ILU (renewed_matrix=false path, gls_navier_stokes.cc:1270);
+    one bdf1 step of the MMS problem matches the oracle's Newton solve of the same step."""
+    from softx_2020_200_b200.mesh import BoxMesh
+    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.test_host_mirror import _match_numbering
+    mesh = BoxMesh(2, 8, 2, 1, with_q_points=True)
+    force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)
+    prm = ("subsection non-linear solver\n set solver = skip_newton\n set skip iterations = 2\n"
+           " set tolerance = 1e-9\n set max iterations = 30\nend\n"
+           "subsection linear solver\n set relative residual = 1e-6\n set minimum residual = 1e-12\nend\n")
+    s = GLSNavierStokesSolver(mesh, prm, force)
+    s.set_time_steps([0.1, 0.1, 0.1, 0.1])
+    z = np.zeros(mesh.n_dofs)
+    s.set_vector("present_solution", z)
+    s.set_vector("solution_m1", z)
+    s.solve_non_linear_system("bdf1", False, True)
+    nat = BoxMesh(2, 8, 2, 1, renumber=False)
+    om = oracle.BoxMesh(2, 8, 2, 1, renumber=_match_numbering(nat, mesh, 2))
+    pr = oracle.scheme_params("bdf1", [0.1], 1.0)
+    U_ref, _, _ = oracle.newton_solve(om, z, pr, om.evaluate_force(mms.forcing_2d), tol=1e-9,
+                                      max_it=30, lin=dict(rel=1e-6, abs_=1e-12), hist=(z, None, None))
+    assert np.linalg.norm(s.present_solution - U_ref) <= 1e-7 * np.linalg.norm(U_ref)
+    s.close()

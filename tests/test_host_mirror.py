@@ -1,0 +1,167 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
+the C++ mirror of the reference's Newton drivers reproduces the reference's fake-backend tests, the
+.prm reader honours the reference's option names and defaults, and the C++ box-mesh stand-in
+produces exactly the arrays of the oracle's deal.II restatement."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_of_the_header():
+    from softx_2020_200_b200 import _lib
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "glsns.h")).read()
+    declared = set(re.findall(r"\b(glsns_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert b"sm_100a" in L.glsns_version()
+
+
+def test_no_cpu_fallback_without_a_device():
+    """glsns_create fails loudly when there is no CUDA device (no CPU path exists)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from softx_2020_200_b200 import GLSHotPath, GlsnsError
+    with pytest.raises(GlsnsError):
+        GLSHotPath(0)
+
+
+@pytest.mark.parametrize("skip,skip_iterations", [(0, 1), (1, 1), (1, 3)])
+def test_newton_drivers_on_the_reference_fake_backend(skip, skip_iterations):
+    """tests/core/newton_non_linear_solver_01.output and skip_newton_non_linear_solver_01.output:
+    'The final solution is : 1.22474 -1.50000' for x0^2+x1=0, 2x1+3=0 from (1,0)."""
+    from softx_2020_200_b200 import _lib
+    L = _lib.lib()
+    x = (C.c_double * 2)()
+    n_matrix = L.glsnsh_newton_toy(skip, skip_iterations, x)
+    assert "%.5f %.5f" % (x[0], x[1]) == "1.22474 -1.50000"
+    # newton rebuilds the Jacobian every iteration, skip_newton once per call
+    assert n_matrix == (1 if skip else 4)
+
+
+def _parse(text):
+    from softx_2020_200_b200 import _lib
+    L = _lib.lib()
+    out = (C.c_double * 16)()
+    err = C.create_string_buffer(256)
+    rc = L.glsnsh_parse_prm(text.encode(), out, err, 256)
+    return rc, list(out), err.value.decode()
+
+
+def test_prm_defaults_match_the_reference():
+    """source/core/parameters.cc:373-447 (non-linear solver), :502-559 (linear solver)."""
+    rc, v, _ = _parse("")
+    assert rc == 0
+    assert v[:4] == [1e-6, 10, 1, 0]                      # tolerance, max it, skip it, newton
+    assert v[4:11] == [1e-3, 1e-8, 1000, 0, 1e-8, 1.0, 0]  # rel, abs, max iters, fill, atol, rtol, gmres
+    assert v[11:16] == [1.0, 1, 1, 0, 0.0]
+
+
+def test_prm_reads_the_shipped_cavity_file_syntax():
+    text = """
+# Listing of Parameters
+subsection physical properties
+    set kinematic viscosity            = 0.005
+end
+subsection FEM
+    set velocity order            = 2
+    set pressure order            = 2
+end
+subsection non-linear solver
+  set solver                  = skip_newton
+  set tolerance               = 1e-8
+  set max iterations          = 10
+  set skip iterations         = 3
+  set verbosity               = quiet
+end
+subsection linear solver
+  set method                                 = gmres
+  set max iters                              = 5000
+  set relative residual                      = 1e-4
+  set minimum residual                       = 1e-9
+  set ilu preconditioner fill                = 0
+  set ilu preconditioner absolute tolerance  = 1e-12
+  set ilu preconditioner relative tolerance  = 1.00
+  set verbosity               = quiet
+end
+subsection velocity source
+  set type = srf
+  set omega_z = -6.28318
+end
+"""
+    rc, v, _ = _parse(text)
+    assert rc == 0
+    assert v[:4] == [1e-8, 10, 3, 1]
+    assert v[4:11] == [1e-4, 1e-9, 5000, 0, 1e-12, 1.0, 0]
+    assert v[11:16] == [0.005, 2, 2, 1, -6.28318]
+    rc, _, err = _parse("subsection linear solver\n set method = direct\nend\n")
+    assert rc == 1 and "invalid iterative solver type" in err
+    rc, _, err = _parse("subsection non-linear solver\n set verbosity = loud\nend\n")
+    assert rc == 1 and "Invalid verbosity level" in err
+
+
+def _match_numbering(A, B, dim):
+    key = lambda m: np.lexsort(tuple(np.round(m.array("dof_coords").reshape(-1, dim)[:, d] * 1e6)
+                                     .astype(np.int64) for d in range(dim))
+                               + (m.array("dof_component"),))
+    new_of_old = np.empty(A.n_dofs, dtype=np.int64)
+    new_of_old[key(A)] = key(B)
+    return new_of_old
+
+
+@pytest.mark.parametrize("dim,n,pu,pp", [(2, 4, 1, 1), (2, 3, 2, 2), (2, 3, 2, 1), (3, 3, 1, 1),
+                                          (3, 2, 2, 2), (3, 2, 2, 1)])
+def test_box_mesh_equals_the_oracle_mesh(oracle, dim, n, pu, pp):
+    """The C++ stand-in for setup_dofs against the numpy restatement: dof tables, constraints,
+    sparsity (keep_constrained_dofs=false), FE tables, geometry; then the Cuthill–McKee numbering
+    (node-level CM == scipy's dof-level CM whenever the seed corner is the same)."""
+    from softx_2020_200_b200.mesh import BoxMesh
+    A = BoxMesh(dim, n, pu, pp, renumber=False, with_q_points=True)
+    O = oracle.BoxMesh(dim, n, pu, pp, renumber="none")
+    assert A.n_dofs == O.ndof and A.n_cells == O.ncell
+    for name, ref in [("cell_dofs", O.cell_dofs.ravel()), ("row_ptr", O.rowptr), ("col_idx", O.col),
+                      ("constrained", O.constrained), ("constraint_values", O.constraint_value),
+                      ("dof_component", O.dof_comp)]:
+        assert np.array_equal(A.array(name), ref), name
+    for name, ref in [("shape_u", O.fe.Nu), ("grad_u", O.fe.dNu), ("hess_u", O.fe.d2Nu),
+                      ("shape_p", O.fe.Np), ("grad_p", O.fe.dNp), ("weights", O.fe.wq),
+                      ("inv_jacobian", O.cell_invJ), ("det_jacobian", O.cell_detJ),
+                      ("q_points", O.qpoints), ("dof_coords", O.dof_coords)]:
+        assert np.allclose(A.array(name), ref.ravel(), rtol=0, atol=2e-14), name
+    B = BoxMesh(dim, n, pu, pp, renumber=True)
+    new_of_old = _match_numbering(A, B, dim)
+    O2 = oracle.BoxMesh(dim, n, pu, pp, renumber=new_of_old)
+    for name, ref in [("cell_dofs", O2.cell_dofs.ravel()), ("row_ptr", O2.rowptr),
+                      ("col_idx", O2.col), ("constrained", O2.constrained)]:
+        assert np.array_equal(B.array(name), ref), name
+    O3 = oracle.BoxMesh(dim, n, pu, pp, renumber="cm")
+    if int(np.argmin(O3.new_of_old)) == int(np.argmin(new_of_old)):      # same seed corner
+        assert np.array_equal(O3.new_of_old, new_of_old)
+    # colouring: cells of one colour share no dof
+    ptr, cells, cd = B.array("color_ptr"), B.array("color_cells"), B.array("cell_dofs").reshape(B.n_cells, -1)
+    for c in range(len(ptr) - 1):
+        d = cd[cells[ptr[c]:ptr[c + 1]]].ravel()
+        assert len(np.unique(d)) == d.size
+
+
+def test_cavity_boundary_conditions_first_listed_wins():
+    from softx_2020_200_b200.mesh import BoxMesh
+    bcs = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (4, "noslip"), (5, "noslip"),
+           (3, "function", (1.0, 0.0, 0.0))]
+    m = BoxMesh(3, 2, 2, 2, bcs=bcs)
+    xyz = m.array("dof_coords").reshape(-1, 3)
+    comp, con, val = m.array("dof_component"), m.array("constrained"), m.array("constraint_values")
+    lid_interior = (np.abs(xyz[:, 1] - 1) < 1e-12) & (np.abs(xyz[:, 0]) < 1 - 1e-12) & \
+        (np.abs(xyz[:, 2]) < 1 - 1e-12)
+    assert np.all(val[lid_interior & (comp == 0)] == 1.0) and np.all(con[lid_interior & (comp < 3)] == 1)
+    lid_edge = (np.abs(xyz[:, 1] - 1) < 1e-12) & (np.abs(np.abs(xyz[:, 0]) - 1) < 1e-12)
+    assert np.all(val[lid_edge] == 0.0)          # walls are listed before the lid
+    assert np.all(con[comp == 3] == 0)           # pressure is never constrained
