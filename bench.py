@@ -188,11 +188,13 @@ def newton_step_host(hp, U1, constrained, cvalues, pin):
     dx, info = hp.solve_linear_system(download=True, **LIN)
     d2h += dx.nbytes
     alpha = 1.0
+    no = dx.size
     while alpha > 1e-3:
-        np.multiply(dx, alpha, out=ev)
-        ev += U1
+        np.multiply(dx, alpha, out=ev[:no])
+        ev[:no] += U1[:no]
         ev[constrained] = cvalues[constrained]
         hp.set_vector("evaluation_point", ev)
+        hp.update_ghosts("evaluation_point")      # ghost import (no-op on one rank)
         h2d += ev.nbytes
         hp.assemble(False)
         d2h += 8

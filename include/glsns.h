@@ -239,6 +239,9 @@ glsns_status glsns_solve_linear_system(glsns_context *ctx,
    evaluation_point = present_solution + alpha * newton_update, then
    apply_constraints (constrained dofs take constraint_values), ghosts updated. */
 glsns_status glsns_line_search_point(glsns_context *ctx, double alpha);
+/* Ghost import of a ghosted input vector whose owned part was just set (what assigning to a
+   ghosted TrilinosWrappers::MPI::Vector does, newton_non_linear_solver.h:93,116). No-op on 1 rank. */
+glsns_status glsns_update_ghosts(glsns_context *ctx, glsns_vector which);
 /* present_solution = evaluation_point (newton_non_linear_solver.h:135). */
 glsns_status glsns_accept_evaluation_point(glsns_context *ctx);
 

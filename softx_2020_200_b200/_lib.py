@@ -87,6 +87,7 @@ SYMBOLS = {
     "glsns_solve_linear_system": (C.c_int, [ctx_p, C.POINTER(LinearSolverParams), C.c_int32,
                                             c_double_p, C.POINTER(SolveInfo)]),
     "glsns_line_search_point": (C.c_int, [ctx_p, C.c_double]),
+    "glsns_update_ghosts": (C.c_int, [ctx_p, C.c_int]),
     "glsns_accept_evaluation_point": (C.c_int, [ctx_p]),
     "glsns_get_matrix_values": (C.c_int, [ctx_p, c_double_p, C.c_int64]),
     "glsns_set_matrix_values": (C.c_int, [ctx_p, c_double_p, C.c_int64]),

@@ -575,6 +575,21 @@ glsns_line_search_point(glsns_context *ctx, double alpha)
 }
 
 glsns_status
+glsns_update_ghosts(glsns_context *ctx, glsns_vector which)
+{
+  CHECK_CTX(ctx);
+  if (!ctx->have_mesh)
+    return fail(ctx, GLSNS_ERR_STATE, "no mesh");
+  if ((int)which < 0 || (int)which > 6 || !is_ghosted_input(which))
+    return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "not a ghosted vector");
+  if (!ctx->vec_set[which])
+    return fail(ctx, GLSNS_ERR_STATE, "vector has not been set");
+  GLSNS_TRY(halo_exchange(ctx, ctx->vec[which].p));
+  GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GLSNS_OK;
+}
+
+glsns_status
 glsns_accept_evaluation_point(glsns_context *ctx)
 {
   CHECK_CTX(ctx);

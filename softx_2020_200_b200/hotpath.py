@@ -173,6 +173,9 @@ class GLSHotPath:
     def line_search_point(self, alpha):
         self._check(self._L.glsns_line_search_point(self._ctx, alpha))
 
+    def update_ghosts(self, which):
+        self._check(self._L.glsns_update_ghosts(self._ctx, _lib.VEC[which]))
+
     def accept_evaluation_point(self):
         self._check(self._L.glsns_accept_evaluation_point(self._ctx))
 

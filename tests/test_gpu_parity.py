@@ -277,3 +277,19 @@ def test_skip_newton_and_transient_through_the_cpp_mirror(oracle):
                                       max_it=30, lin=dict(rel=1e-6, abs_=1e-12), hist=(z, None, None))
     assert np.linalg.norm(s.present_solution - U_ref) <= 1e-7 * np.linalg.norm(U_ref)
     s.close()
+
+
+def test_two_gpu_newton_step_matches_block_jacobi_oracle():
+    """N = 2 ranks over NCCL (skipped on a 1-GPU box; run with `gpurun --gpus 2`)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29731", os.path.join(root, "tests", "multi_gpu_check.py"), "4"],
+                         capture_output=True, text=True, timeout=600)
+    assert "MULTI_GPU_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
