@@ -35,7 +35,9 @@ def main():
     hp.set_physics(0.005)
     l2g = m.array("local_to_global")
     # a non-trivial global state, same on every rank
-    Ug = 0.3 * np.random.default_rng(1234).uniform(-1, 1, g.n_dofs)
+    xyz = g.array("dof_coords").reshape(-1, 3)
+    Ug = 0.05 * np.sin(np.pi * xyz[:, 0] + 0.3 * g.array("dof_component")) * np.cos(np.pi * xyz[:, 1]) \
+        * np.cos(0.5 * np.pi * xyz[:, 2])
     con = g.array("constrained").astype(bool)
     Ug[con] = g.array("constraint_values")[con]
     hp.set_vector("present_solution", Ug[l2g])
