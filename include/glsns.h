@@ -253,6 +253,14 @@ glsns_status glsns_get_ilu_values(glsns_context *ctx, double *values, int64_t nn
 glsns_status glsns_spmv(glsns_context *ctx, const double *x, double *y);
 /* z = (LU)^-1 r, both [n_owned]. */
 glsns_status glsns_ilu_apply(glsns_context *ctx, const double *r, double *z);
+/* glsns_ilu_apply with a trace, for tuning the triangular solves: t_publish[0..n) /
+   [n..2n) = device time (ns) at which the lower / upper sweep published each row;
+   [2n..3n) / [3n..4n) = per group head (first row), lower / upper: extra polling rounds
+   << 32 | smallest row distance of an entry that was not there at the first look,
+   row_warp (may be NULL) = resident warp each row was scheduled on in the two
+   sweeps (bit 30: solved behind its predecessor on the same warp, -1: diagonal row). */
+glsns_status glsns_ilu_apply_trace(glsns_context *ctx, const double *r, double *z,
+                                   uint64_t *t_publish, int32_t *row_warp);
 /* number of dependency levels of the lower / upper triangular solves */
 glsns_status glsns_ilu_levels(glsns_context *ctx, int32_t *lower, int32_t *upper);
 glsns_status glsns_get_timers(glsns_context *ctx, glsns_timers *out);

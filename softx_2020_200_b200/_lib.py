@@ -95,6 +95,7 @@ SYMBOLS = {
     "glsns_spmv": (C.c_int, [ctx_p, c_double_p, c_double_p]),
     "glsns_ilu_apply": (C.c_int, [ctx_p, c_double_p, c_double_p]),
     "glsns_ilu_levels": (C.c_int, [ctx_p, c_i32_p, c_i32_p]),
+    "glsns_ilu_apply_trace": (C.c_int, [ctx_p, c_double_p, c_double_p, C.POINTER(C.c_uint64), c_i32_p]),
     "glsns_get_timers": (C.c_int, [ctx_p, C.POINTER(Timers)]),
     "glsns_reset_timers": (C.c_int, [ctx_p]),
     "glsns_time_kernel": (C.c_int, [ctx_p, C.c_int32, C.c_int32, C.c_int32, c_double_p]),

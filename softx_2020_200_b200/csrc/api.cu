@@ -678,8 +678,39 @@ glsns_ilu_apply(glsns_context *ctx, const double *r, double *z)
   GLSNS_TRY(launch_ilu_apply(ctx, ctx->tvec.p, ctx->zg.p));
   GLSNS_CUDA(ctx, cudaMemcpyAsync(z, ctx->zg.p, sizeof(double) * ctx->n_owned,
                                   cudaMemcpyDeviceToHost, ctx->stream));
-  GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return GLSNS_OK;
+  return check_counters(ctx, "ILU apply");
+}
+
+glsns_status
+glsns_ilu_apply_trace(glsns_context *ctx, const double *r, double *z, uint64_t *t_publish,
+                      int32_t *row_warp)
+{
+  CHECK_CTX(ctx);
+  if (!ctx->have_mesh || !ctx->have_ilu)
+    return fail(ctx, GLSNS_ERR_STATE, "no ILU factors");
+  if (!r || !z || !t_publish)
+    return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "null pointer");
+  const int64_t                 n = ctx->n_owned;
+  glsns::DevBuf<unsigned long long> tr;
+  GLSNS_TRY(dev_alloc(ctx, tr, (size_t)4 * n));
+  cudaMemsetAsync(tr.p, 0, sizeof(unsigned long long) * 4 * n, ctx->stream);
+  GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->tvec.p, r, sizeof(double) * n, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+  glsns_status s = launch_ilu_apply(ctx, ctx->tvec.p, ctx->zg.p, tr.p);
+  if (s == GLSNS_OK)
+    {
+      cudaMemcpyAsync(z, ctx->zg.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaMemcpyAsync(t_publish, tr.p, sizeof(uint64_t) * 4 * n, cudaMemcpyDeviceToHost,
+                      ctx->stream);
+      s = check_counters(ctx, "ILU apply");
+    }
+  tr.release();
+  if (row_warp && s == GLSNS_OK)
+    {
+      memcpy(row_warp, ctx->trsv_row_warp_l.data(), sizeof(int32_t) * n);
+      memcpy(row_warp + n, ctx->trsv_row_warp_u.data(), sizeof(int32_t) * n);
+    }
+  return s;
 }
 
 glsns_status

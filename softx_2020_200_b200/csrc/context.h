@@ -41,8 +41,20 @@ namespace glsns
     int32_t len_m; // row length (same for every row of the group) | rows in the group << 28
     int32_t nlow; // entries left of the group = offset of the in-group block
     int32_t cnt;   // entries outside the group this sweep reads (inside the diagonal block)
-    int32_t crit; // row index of the dependency on the highest level, -1 if none
-    int32_t crit2; // crit of crit's group: solved => this group is one level from the front
+    int32_t crit;  // column of the dependency on the highest level, -1 if none
+    int32_t crit2; // its position among the cnt entries
+  };
+
+  // One ring-slot load of the chain triangular solve: <= 128 entries of one group.
+  struct TrsvItem
+  {
+    int64_t rs0;   // CSR offset of the group's first row
+    int32_t r0;    // first row
+    int32_t len;   // row length (same for every row of the group)
+    int32_t e_off; // first entry of this item inside the row
+    int32_t flags; // rows in the group | IT_LAST | entries << 16
+    int32_t nlow;  // offset of the in-group block inside the row
+    int32_t fmask; // last item: bit d = couples to the chain row at distance d
   };
 
   struct EventPair
@@ -88,14 +100,18 @@ struct glsns_context
   bool    have_mesh = false;
   int64_t n_dofs = 0, n_owned = 0, n_cells = 0, nnz = 0;
   int32_t geometry_per_q = 0, n_colors = 0;
-  glsns::DevBuf<int32_t> cell_dofs, col, color_cells, order_l;
+  glsns::DevBuf<int32_t> cell_dofs, col, color_cells, order_l, diag_rows;
   glsns::DevBuf<glsns::TrsvGroup> desc_l, desc_u;
+  glsns::DevBuf<glsns::TrsvItem>  items_l, items_u;
+  glsns::DevBuf<int64_t>          wptr_l, wptr_u;
+  int32_t                         trsv_grid = 0;
+  std::vector<int32_t>            trsv_row_warp_l, trsv_row_warp_u; // schedule, for the trace
   glsns::DevBuf<int64_t> rowptr, diag_pos;
   glsns::DevBuf<double>  inv_jac, det_jac, measure, q_points, force, cvalues;
   glsns::DevBuf<uint8_t> constrained;
   std::vector<int32_t>   color_ptr;
   int32_t                levels_l = 0, levels_u = 0, levels_rows = 0, n_groups = 0;
-  int32_t                max_row_len = 0;
+  int32_t                max_row_len = 0, n_diag_rows = 0;
   double                 avg_row_len = 0;
 
   // ---- physics ----
@@ -105,7 +121,7 @@ struct glsns_context
   bool    have_force = false;
 
   // ---- matrix / factors / vectors ----
-  glsns::DevBuf<double> val, lu;
+  glsns::DevBuf<double> val, lu, dinv;
   bool                  have_matrix = false, have_ilu = false, have_rhs = false;
   glsns::DevBuf<double> vec[7];
   bool                  vec_set[7] = {false, false, false, false, false, false, false};
@@ -198,7 +214,14 @@ namespace glsns
   glsns_status launch_spmv(glsns_context *ctx, const double *x, double *y);
   glsns_status ilu_analyse(glsns_context *ctx, const int64_t *rowptr, const int32_t *col);
   glsns_status launch_ilu_factor(glsns_context *ctx, double atol, double rtol);
-  glsns_status launch_ilu_apply(glsns_context *ctx, const double *r, double *z);
+  glsns_status launch_ilu_apply(glsns_context *ctx, const double *r, double *z,
+                                unsigned long long *trace = nullptr);
+  // reads the device error flag (zero pivot / dependency wait timed out); synchronises
+  glsns_status check_counters(glsns_context *ctx, const char *what);
+  // trsv.cu
+  glsns_status trsv_analyse(glsns_context *ctx, const int64_t *rowptr, const int32_t *col,
+                            const int64_t *diag);
+  glsns_status trsv_prepare(glsns_context *ctx);
   // krylov.cu
   glsns_status ensure_workspace(glsns_context *ctx, int restart);
   glsns_status device_norm2(glsns_context *ctx, const double *x, double *out);

@@ -425,7 +425,7 @@ namespace glsns
     GLSNS_TRY(device_norm2(ctx, w, &tr));
     // zero_constraints.distribute(x), gls_navier_stokes.cc:1287
     GLSNS_TRY(launch_zero_constrained(ctx, x));
-    GLSNS_CUDA(ctx, cudaStreamSynchronize(st));
+    GLSNS_TRY(check_counters(ctx, "GMRES")); // synchronises; the solves' bug guard
     timers_drain(ctx);
     ctx->vec_set[GLSNS_VEC_NEWTON_UPDATE] = true;
     info->iterations                      = it;

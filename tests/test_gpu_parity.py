@@ -275,7 +275,11 @@ def test_skip_newton_and_transient_through_the_cpp_mirror(oracle):
     pr = oracle.scheme_params("bdf1", [0.1], 1.0)
     U_ref, _, _ = oracle.newton_solve(om, z, pr, om.evaluate_force(mms.forcing_2d), tol=1e-9,
                                       max_it=30, lin=dict(rel=1e-6, abs_=1e-12), hist=(z, None, None))
-    assert np.linalg.norm(s.present_solution - U_ref) <= 1e-7 * np.linalg.norm(U_ref)
+    # all-Dirichlet problem: the pressure is defined up to a constant that no solver pins (the
+    # reference compares it mean-free too, navier_stokes_base.cc:288-379), so shift it out
+    U, is_p = s.present_solution.copy(), mesh.array("dof_component") == 2
+    U[is_p] -= U[is_p].mean() - U_ref[is_p].mean()
+    assert np.linalg.norm(U - U_ref) <= 1e-7 * np.linalg.norm(U_ref)
     s.close()
 
 
