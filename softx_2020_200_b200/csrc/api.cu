@@ -243,8 +243,10 @@ glsns_destroy(glsns_context *ctx)
                             &ctx->counters, &ctx->row_done, &ctx->send_idx};
   for (auto *b : i32)
     b->release();
-  ctx->desc_l.release();
-  ctx->desc_u.release();
+  ctx->trsv_l.release();
+  ctx->trsv_u.release();
+  ctx->dinv.release();
+  ctx->diag_rows.release();
   ctx->rowptr.release();
   ctx->diag_pos.release();
   ctx->constrained.release();

@@ -32,20 +32,7 @@ namespace glsns
     }
   };
 
-  // One group of consecutive rows with identical patterns, as the triangular-solve
-  // kernels consume it (one 32-byte record per ticket).
-  struct TrsvGroup
-  {
-    int64_t rs0;  // CSR offset of the group's first row
-    int32_t r0;   // first row
-    int32_t len_m; // row length (same for every row of the group) | rows in the group << 28
-    int32_t nlow; // entries left of the group = offset of the in-group block
-    int32_t cnt;   // entries outside the group this sweep reads (inside the diagonal block)
-    int32_t crit;  // column of the dependency on the highest level, -1 if none
-    int32_t crit2; // its position among the cnt entries
-  };
-
-  // One ring-slot load of the chain triangular solve: <= 128 entries of one group.
+  // One item of the chain triangular solve: <= 128 entries of one group (trsv.cu).
   struct TrsvItem
   {
     int64_t rs0;   // CSR offset of the group's first row
@@ -55,6 +42,23 @@ namespace glsns
     int32_t flags; // rows in the group | IT_LAST | entries << 16
     int32_t nlow;  // offset of the in-group block inside the row
     int32_t fmask; // last item: bit d = couples to the chain row at distance d
+  };
+
+  // One sweep (lower or upper) of the ILU application in stream form (trsv.cu).
+  struct TrsvSweep
+  {
+    DevBuf<TrsvItem>      items;    // per-warp item lists, concatenated
+    DevBuf<int64_t>       blob_off; // byte offset of each item's blob in the stream
+    DevBuf<int32_t>       next16;   // bytes/16 of the blob NSLOT items ahead (same warp)
+    DevBuf<unsigned char> dir;      // per-warp directory
+    DevBuf<unsigned char> stream;   // headers, indices and factor values in consumption order
+    int64_t               n_items = 0, stream_bytes = 0;
+    void
+    release()
+    {
+      items.release(), blob_off.release(), next16.release(), dir.release(), stream.release();
+      n_items = stream_bytes = 0;
+    }
   };
 
   struct EventPair
@@ -101,9 +105,7 @@ struct glsns_context
   int64_t n_dofs = 0, n_owned = 0, n_cells = 0, nnz = 0;
   int32_t geometry_per_q = 0, n_colors = 0;
   glsns::DevBuf<int32_t> cell_dofs, col, color_cells, order_l, diag_rows;
-  glsns::DevBuf<glsns::TrsvGroup> desc_l, desc_u;
-  glsns::DevBuf<glsns::TrsvItem>  items_l, items_u;
-  glsns::DevBuf<int64_t>          wptr_l, wptr_u;
+  glsns::TrsvSweep                trsv_l, trsv_u;
   int32_t                         trsv_grid = 0;
   std::vector<int32_t>            trsv_row_warp_l, trsv_row_warp_u; // schedule, for the trace
   glsns::DevBuf<int64_t> rowptr, diag_pos;

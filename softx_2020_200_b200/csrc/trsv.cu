@@ -6,10 +6,10 @@
 // the GMRES iteration count, must be the reference's), so the parallelism is what
 // the dependency DAG of that ordering offers.  Under Cuthill-McKee that DAG is
 // deep and narrow (3D Q2-Q2, 32^3 cells: 2742 levels of ~100 mesh nodes each) and
-// ~88 % of its critical edges join a node to the node numbered just before it.  A
+// ~90 % of its critical edges join a node to the node numbered just before it.  A
 // level-synchronous or row-per-warp solve pays one L2 store->load hop (0.36 us on
 // B200, tools/hop_latency.cu) plus a warp reduction per level; this kernel is built
-// to take both HBM and that hop off the critical path:
+// to take HBM, the hop and most instructions off that critical path:
 //
 //   * GROUPS.  Up to 4 consecutive rows with identical column patterns (the dim+1
 //     dofs of a mesh node) are solved together: one index stream, a 4x4 triangle.
@@ -20,14 +20,19 @@
 //     (one per lane, a shift register over the row distance), so the entries that
 //     couple a group to its recent predecessors never wait for L2; only the
 //     dependencies on other chains travel through L2, and most of those have
-//     several levels of slack.  Every warp's list is sorted by level, which is what makes the
+//     several levels of slack.  Every warp's list is sorted by level, which makes the
 //     waiting deadlock free (the blocked group of lowest level would wait on a group
 //     of lower level that is some warp's current or earlier item) provided all warps
 //     are resident — hence the cooperative launch, which refuses instead of hanging.
-//   * RING.  Each warp streams the column indices and factor entries of its next
-//     items from HBM into a private shared-memory ring with cp.async, several items
-//     ahead of the one it is solving (~200 KB x 148 SMs in flight), and gathers the
-//     solution entries of item i+1 while it reduces item i and finishes item i-1.
+//   * STREAMS.  After every factorisation the factor entries are re-packed, per
+//     sweep, into one contiguous byte stream per warp in exactly the order that warp
+//     consumes them: per item (<= 128 entries of one group) a 16-byte header, the
+//     inverted diagonal, the in-group triangle, the window couplings, the column
+//     indices and the values.  The solve then reads HBM strictly sequentially, and
+//     one lane moves a whole item into the warp's shared-memory ring with a single
+//     bulk copy (cp.async.bulk, completion on an mbarrier) several items ahead of
+//     the one being solved: ~220 KB x 148 SMs of factor data in flight, ~5 issue
+//     slots per item instead of ~150 for per-entry copies.
 //   * The solution vector itself carries readiness: it is pre-filled with an
 //     all-ones NaN pattern and a consumer re-reads an entry until it has been
 //     overwritten (no flags, no fences).
@@ -48,25 +53,54 @@ namespace glsns
     constexpr long long          SPIN_LIMIT = 1ll << 21; // a bug guard (seconds), never reached in a correct run
 
     constexpr int TRSV_G = 4;          // rows per group
-    constexpr int TS_CH  = 128;        // entries per ring slot
-    constexpr int TS_U   = TS_CH / 32; // entries per lane and slot
+    constexpr int TS_CH  = 128;        // entries per item
+    constexpr int TS_U   = TS_CH / 32; // entries per lane and item
     constexpr int TS_WIN = 16;         // rows of the chain kept in registers
-    // slot layout (bytes): header 16 | rhs 32 | dinv 32 | tri 128 | fwd 8*G*WIN | col 4*CH | val 8*G*CH
-    constexpr int TS_OFF_RHS  = 16;
-    constexpr int TS_OFF_DINV = 48;
-    constexpr int TS_OFF_TRI  = 80;
-    constexpr int TS_OFF_FWD  = 208;
-    constexpr int TS_OFF_COL  = TS_OFF_FWD + 8 * TRSV_G * TS_WIN;
-    constexpr int TS_OFF_VAL  = TS_OFF_COL + 4 * TS_CH;
-    constexpr int TS_SLOT     = TS_OFF_VAL + 8 * TRSV_G * TS_CH; // 5328
-    constexpr int TS_REC      = 32; // item records staged per warp (1 KB)
-    constexpr int TS_SMEM_MAX = 227 * 1024;
+    // item blob (bytes, 16-byte aligned):
+    //   header 16: r0 | flags | fmask | bytes/16 of the blob NSLOT items ahead
+    //   last item of a group only: dinv 32 | tri 48 | fwd 8*G*WIN
+    //   col 4*pad4(entries) | val 8*m*pad4(entries)
+    constexpr int TS_OFF_DINV = 16;
+    constexpr int TS_OFF_TRI  = 48;
+    constexpr int TS_OFF_FWD  = 96;
+    constexpr int TS_OFF_COL1 = TS_OFF_FWD + 8 * TRSV_G * TS_WIN; // 608 (last item)
+    constexpr int TS_OFF_COL0 = 16;                                 // (other items)
+    constexpr int TS_SLOT     = TS_OFF_COL1 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 5216
+    constexpr int TS_MAX_SLOTS = 9;
+    constexpr int TS_SMEM_MAX  = 227 * 1024;
 
-    // item flags
-    constexpr int IT_LAST = 1 << 8; // last item of its group: finish and store
-    // bits 0-2: rows in the group (m); bits 4-7: diagonal-only rows between the chain
-    // predecessor and this group; bits 16..: entries.  TrsvItem::fmask, last item
-    // only: bit d = the group couples to the chain row at distance d (in registers)
+    // item flags: bits 0-2 rows in the group (m); bits 4-7 diagonal-only rows between
+    // the chain predecessor and this group; bit 8 last item of its group; bits 16..
+    // entries.  fmask (last item): bit d = couples to the chain row at distance d
+    constexpr int IT_LAST = 1 << 8;
+
+    __host__ __device__ inline int
+    pad4(int v)
+    {
+      return (v + 3) & ~3;
+    }
+    __host__ __device__ inline int
+    blob_bytes(int flags)
+    {
+      const int m = flags & 7, c = pad4(flags >> 16);
+      return ((flags & IT_LAST) ? TS_OFF_COL1 : TS_OFF_COL0) + 4 * c + 8 * m * c;
+    }
+    // in-group triangle, packed: lower (1,0)(2,0)(2,1)(3,0)(3,1)(3,2); upper (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
+    __host__ __device__ inline int
+    tri_index(bool upper, int a, int b)
+    {
+      return upper ? (a == 0 ? b - 1 : a == 1 ? b + 1 : 5) : a * (a - 1) / 2 + b;
+    }
+
+    // per-warp entry of the stream directory (64 bytes)
+    struct TrsvWarpDir
+    {
+      int64_t offset;  // byte offset of the warp's first blob in the stream
+      int32_t n_items;
+      int32_t first16[TS_MAX_SLOTS]; // bytes/16 of the first NSLOT blobs
+      int32_t pad[4];
+    };
+    static_assert(sizeof(TrsvWarpDir) == 64, "directory entry");
 
     __device__ __forceinline__ unsigned long long
     ld_relaxed_u64(const double *p)
@@ -84,33 +118,42 @@ namespace glsns
       asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(b) : "memory");
     }
     __device__ __forceinline__ void
-    cp_async4(void *smem_dst, const void *gsrc)
+    mbar_init(void *bar, int count)
+    {
+      const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    }
+    __device__ __forceinline__ void
+    mbar_expect_tx(void *bar, unsigned bytes)
+    {
+      const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes)
+                   : "memory");
+    }
+    __device__ __forceinline__ bool
+    mbar_try_wait(void *bar, unsigned parity)
+    {
+      const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+      unsigned       ok;
+      asm volatile("{\n\t.reg .pred p;\n\t"
+                   "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                   "selp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok)
+                   : "r"(a), "r"(parity)
+                   : "memory");
+      return ok != 0;
+    }
+    // one whole item: global -> shared, completion counted in bytes on the mbarrier;
+    // the stream is read once per sweep, so it is marked evict-first in L2
+    __device__ __forceinline__ void
+    bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, void *bar, unsigned long long policy)
     {
       const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-    }
-    __device__ __forceinline__ void
-    cp_async8(void *smem_dst, const void *gsrc)
-    {
-      const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-    }
-    __device__ __forceinline__ void
-    cp_async16(void *smem_dst, const void *gsrc)
-    {
-      const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-    }
-    __device__ __forceinline__ void
-    cp_async_commit()
-    {
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    template <int N>
-    __device__ __forceinline__ void
-    cp_async_wait()
-    {
-      asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+      const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+                   "[%0], [%1], %2, [%3], %4;" ::"r"(d),
+                   "l"(gsrc), "r"(bytes), "r"(b), "l"(policy)
+                   : "memory");
     }
 
     // rows whose pattern is the diagonal alone (constrained dofs) depend on nothing:
@@ -130,126 +173,152 @@ namespace glsns
         }
     }
 
-    // One warp = one list of items (TrsvItem, <= TS_CH entries of one group each), in
-    // the order the host scheduled them.  Three-stage software pipeline over the items:
-    //   G(i+3): column indices from the ring, solution entries requested from L2
+    // ---- stream packing: one warp per item -------------------------------------
+    // static part (once per sparsity pattern): header and column indices
+    __global__ void __launch_bounds__(256)
+    trsv_pack_static_kernel(const int64_t n_items, const TrsvItem *__restrict__ items,
+                            const int64_t *__restrict__ blob_off, const int32_t *__restrict__ next16,
+                            const int32_t *__restrict__ col, unsigned char *__restrict__ stream)
+    {
+      const int64_t it   = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+      const int     lane = threadIdx.x & 31;
+      if (it >= n_items)
+        return;
+      const TrsvItem d = items[it];
+      unsigned char *B = stream + blob_off[it];
+      if (lane == 0)
+        *reinterpret_cast<int4 *>(B) = make_int4(d.r0, d.flags, d.fmask, next16[it]);
+      const int cntc = d.flags >> 16, cp = pad4(cntc);
+      int32_t  *bc   = reinterpret_cast<int32_t *>(B + ((d.flags & IT_LAST) ? TS_OFF_COL1 : TS_OFF_COL0));
+      for (int k = lane; k < cp; k += 32)
+        bc[k] = k < cntc ? col[d.rs0 + d.e_off + k] : d.r0; // padding: any valid index
+    }
+
+    // values (after every factorisation)
+    template <bool UPPER>
+    __global__ void __launch_bounds__(256)
+    trsv_pack_values_kernel(const int64_t n_items, const TrsvItem *__restrict__ items,
+                            const int64_t *__restrict__ blob_off, const double *__restrict__ lu,
+                            unsigned char *__restrict__ stream)
+    {
+      const int64_t it   = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+      const int     lane = threadIdx.x & 31;
+      if (it >= n_items)
+        return;
+      const TrsvItem d = items[it];
+      unsigned char *B = stream + blob_off[it];
+      const int      m = d.flags & 7, cntc = d.flags >> 16, cp = pad4(cntc);
+      const bool     last = d.flags & IT_LAST;
+      double        *bv   = reinterpret_cast<double *>(B + (last ? TS_OFF_COL1 : TS_OFF_COL0) + 4 * cp);
+      for (int a = 0; a < m; ++a)
+        for (int k = lane; k < cp; k += 32)
+          bv[a * cp + k] = k < cntc ? __ldcs(lu + d.rs0 + (int64_t)a * d.len + d.e_off + k) : 0.0;
+      if (last)
+        {
+          double *di = reinterpret_cast<double *>(B + TS_OFF_DINV);
+          double *tr = reinterpret_cast<double *>(B + TS_OFF_TRI);
+          double *fw = reinterpret_cast<double *>(B + TS_OFF_FWD);
+          if (lane < TRSV_G) // Ifpack stores and applies the inverted diagonal
+            di[lane] = lane < m ? 1.0 / lu[d.rs0 + (int64_t)lane * d.len + d.nlow + lane] : 0.0;
+          if (lane < 16)
+            {
+              const int a = lane >> 2, b = lane & 3;
+              if (UPPER ? b > a : b < a)
+                tr[tri_index(UPPER, a, b)] =
+                  (a < m && b < m) ? lu[d.rs0 + (int64_t)a * d.len + d.nlow + b] : 0.0;
+            }
+          // coupling to the chain rows held in registers: entry of row a at distance dd
+          const unsigned fmask = (unsigned)d.fmask;
+          for (int q = lane; q < TRSV_G * TS_WIN; q += 32)
+            {
+              const int a = q / TS_WIN, dd = q % TS_WIN;
+              double    v = 0;
+              if (a < m && (fmask & (1u << dd)))
+                {
+                  const int before = __popc(fmask & ((1u << dd) - 1u));
+                  const int pos    = UPPER ? d.nlow + m + before : d.nlow - 1 - before;
+                  v                = lu[d.rs0 + (int64_t)a * d.len + pos];
+                }
+              fw[q] = v;
+            }
+        }
+    }
+
+    // ---- the solve ---------------------------------------------------------------
+    // One warp = one list of items in the order the host scheduled them.  Software
+    // pipeline over the items (three rotating register sets, selected at compile time):
+    //   G(i+3): wait for the item's bulk copy, column indices from the ring, solution
+    //           entries and the right-hand side requested from L2
     //   B(i)  : last item of a group: solve the in-group triangle, publish the
-    //           solution, shift it into the register window
+    //           solution, shift it into the register window, refill the ring slot
     //   R(i+1): entries that were not there yet are re-read until they are; multiply;
     //           last item of a group: add the coupling to the register window,
     //           warp-reduce
     template <bool UPPER, int NSLOT>
     __global__ void __launch_bounds__(256, 1)
-    trsv_chain_kernel(const int64_t *__restrict__ warp_ptr, const TrsvItem *__restrict__ items,
-                      const int32_t *__restrict__ col, const double *__restrict__ lu,
-                      const double *__restrict__ dinv, const double *__restrict__ rhs_vec,
-                      double *x, int *counters, unsigned long long *trace, const int64_t trace_n)
+    trsv_chain_kernel(const TrsvWarpDir *__restrict__ dir, const unsigned char *__restrict__ stream,
+                      const double *__restrict__ rhs_vec, double *x, int *counters,
+                      unsigned long long *trace, const int64_t trace_n)
     {
-      static_assert(NSLOT >= 5, "the pipeline holds four items besides the ones in flight");
-      extern __shared__ __align__(16) unsigned char ring_all[];
+      static_assert(NSLOT >= 5 && NSLOT <= TS_MAX_SLOTS, "ring depth");
+      extern __shared__ __align__(128) unsigned char ring_all[];
       const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-      const int64_t  w    = (int64_t)warp * gridDim.x + blockIdx.x; // consecutive lists on different SMs
-      unsigned char *ring = ring_all + (size_t)warp * NSLOT * TS_SLOT;
-      const int64_t  i0 = warp_ptr[w], n_items = warp_ptr[w + 1] - i0;
+      const int      nwarp = blockDim.x >> 5;
+      const int64_t  w     = (int64_t)warp * gridDim.x + blockIdx.x; // consecutive lists on different SMs
+      unsigned char *ring  = ring_all + (size_t)warp * NSLOT * TS_SLOT;
+      unsigned long long *bars =
+        reinterpret_cast<unsigned long long *>(ring_all + (size_t)nwarp * NSLOT * TS_SLOT) + warp * NSLOT;
+      const TrsvWarpDir *D       = dir + w;
+      const int64_t      n_items = D->n_items;
       if (n_items == 0)
         return;
-      const TrsvItem *my = items + i0;
+      unsigned long long policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
-      // ---- issue side ----
-      // The item records themselves are prefetched too: 32 of them live in shared
-      // memory, refilled by halves with cp.async 16 items before they are needed.
-      int64_t n_iss = 0;
-      int4   *recs  = reinterpret_cast<int4 *>(ring_all + (size_t)(blockDim.x >> 5) * NSLOT * TS_SLOT) +
-                    warp * (2 * TS_REC);
-      auto fetch_recs = [&](int64_t first) { // 16 records = 32 x 16 bytes, one per lane
-        const int64_t q = first * 2 + lane;  // index in int4 units
-        if (q < n_items * 2)
-          cp_async16(recs + (q & (2 * TS_REC - 1)), reinterpret_cast<const int4 *>(my) + q);
-      };
-      fetch_recs(0);
-      fetch_recs(TS_REC / 2);
-      cp_async_commit();
-      cp_async_wait<0>();
+      // ---- issue side (lane 0): running offset in the stream, sizes from the headers ----
+      const unsigned char *src   = stream + D->offset;
+      int64_t              n_iss = 0;
+      if (lane == 0)
+        {
+          for (int s = 0; s < NSLOT; ++s)
+            mbar_init(bars + s, 1);
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+          for (int s = 0; s < NSLOT; ++s)
+            if (s < n_items)
+              {
+                const unsigned bytes = 16u * (unsigned)D->first16[s];
+                mbar_expect_tx(bars + s, bytes);
+                bulk_load(ring + (size_t)s * TS_SLOT, src, bytes, bars + s, policy);
+                src += bytes;
+                ++n_iss;
+              }
+        }
       __syncwarp();
-      auto issue = [&](int slot) {
-        if (n_iss < n_items)
-          {
-            unsigned char *S     = ring + (size_t)slot * TS_SLOT;
-            const int4     ra = recs[(n_iss & (TS_REC - 1)) * 2], rb = recs[(n_iss & (TS_REC - 1)) * 2 + 1];
-            if ((n_iss & (TS_REC / 2 - 1)) == 0 && n_iss > 0)
-              fetch_recs(n_iss + TS_REC / 2); // the half just left; joins this item's group
-            const int64_t  rs0   = ((int64_t)(unsigned)ra.x) | ((int64_t)ra.y << 32);
-            const int      r0    = ra.z, len = ra.w;
-            const int      e_off = rb.x, flags = rb.y, nlow = rb.z;
-            const unsigned fmask = (unsigned)rb.w;
-            const int      m = flags & 7, cntc = flags >> 16;
-            const int64_t  e0   = rs0 + e_off;
-            int32_t       *scol = reinterpret_cast<int32_t *>(S + TS_OFF_COL);
-            double        *sval = reinterpret_cast<double *>(S + TS_OFF_VAL);
-#pragma unroll
-            for (int u = 0; u < TS_U; ++u)
-              {
-                const int k = lane + 32 * u;
-                if (k < cntc)
-                  {
-                    cp_async4(scol + k, col + e0 + k);
-#pragma unroll
-                    for (int a = 0; a < TRSV_G; ++a)
-                      if (a < m)
-                        cp_async8(sval + a * TS_CH + k, lu + e0 + (int64_t)a * len + k);
-                  }
-              }
-            if (flags & IT_LAST)
-              {
-                if (lane < 16)
-                  {
-                    const int a = lane >> 2, b = lane & 3;
-                    if (a < m && b < m && (UPPER ? b > a : b < a))
-                      cp_async8(S + TS_OFF_TRI + 8 * lane, lu + rs0 + (int64_t)a * len + nlow + b);
-                  }
-                else if (lane < 16 + m)
-                  cp_async8(S + TS_OFF_RHS + 8 * (lane - 16), rhs_vec + r0 + (lane - 16));
-                else if (UPPER && lane >= 24 && lane < 24 + m)
-                  cp_async8(S + TS_OFF_DINV + 8 * (lane - 24), dinv + r0 + (lane - 24));
-                // coupling to the chain rows held in registers: lane (h, d) copies rows
-                // a = h (mod 2) of the entry at distance d
-                const int d = lane & 15, hh = lane >> 4;
-                if (fmask & (1u << d))
-                  {
-                    const int before = __popc(fmask & ((1u << d) - 1u));
-                    const int pos    = UPPER ? nlow + m + before : nlow - 1 - before;
-#pragma unroll
-                    for (int a = 0; a < TRSV_G; ++a)
-                      if ((a & 1) == hh && a < m)
-                        cp_async8(S + TS_OFF_FWD + 8 * (a * TS_WIN + d),
-                                  lu + rs0 + (int64_t)a * len + pos);
-                  }
-              }
-            if (lane == 0)
-              {
-                int4 h;
-                h.x = r0, h.y = flags, h.z = rb.w /* fmask */, h.w = 0;
-                *reinterpret_cast<int4 *>(S) = h;
-              }
-            ++n_iss;
-          }
-        cp_async_commit();
-      };
-#pragma unroll
-      for (int s = 0; s < NSLOT; ++s)
-        issue(s);
 
       // ---- pipeline registers: three rotating sets (no copies: a copy would wait for
       //      the loads in flight), selected at compile time by the unrolled loop ----
       int32_t            cS[3][TS_U];
       unsigned long long bS[3][TS_U];
       unsigned           pS[3] = {0, 0, 0};
+      double             rS[3] = {0, 0, 0}; // right-hand side of row r0 + lane
       double             acc[TRSV_G], accB[TRSV_G];
       double             win = 0; // solution of the chain row at distance (lane & 15)
 #pragma unroll
       for (int a = 0; a < TRSV_G; ++a)
         acc[a] = accB[a] = 0;
-      int slotG = 0, slotR = 0, slotB = 0;
+      int      slotG = 0, slotR = 0, slotB = 0;
+      unsigned phaseG = 0;
+      long long tstage[6] = {0, 0, 0, 0, 0, 0}; // debugging aid (trace): cycles per stage
+#define TS_TICK(k)                              \
+  if (trace)                                    \
+    {                                           \
+      const long long now_ = clock64();         \
+      tstage[k] += now_ - tlast;                \
+      tlast = now_;                             \
+    }
+      long long tlast = clock64();
 
       // one pipeline step: G(it) into set KG, B(it-3), R(it-2) from set (KG+1)%3
       auto step = [&](auto KG, const int64_t it) {
@@ -260,182 +329,170 @@ namespace glsns
         int32_t(&cG)[TS_U]            = cS[kr];
         unsigned long long(&bG)[TS_U] = bS[kr];
         unsigned &pendG               = pS[kr];
-          // ================= G(it) =================
-          pendN = 0;
-          if (it < n_items)
-            {
-              cp_async_wait<NSLOT - 4>();
-              __syncwarp();
-              const unsigned char *S    = ring + (size_t)slotG * TS_SLOT;
-              const int            cntc = reinterpret_cast<const int4 *>(S)->y >> 16;
-              const int32_t       *scol = reinterpret_cast<const int32_t *>(S + TS_OFF_COL);
+        // ================= G(it) =================
+        pendN = 0;
+        if (it < n_items)
+          {
+            TS_TICK(5)
+            while (!mbar_try_wait(bars + slotG, phaseG))
+              ;
+            TS_TICK(0)
+            const unsigned char *S     = ring + (size_t)slotG * TS_SLOT;
+            const int4           h     = *reinterpret_cast<const int4 *>(S);
+            const int            flags = h.y, cntc = flags >> 16;
+            const int32_t       *scol =
+              reinterpret_cast<const int32_t *>(S + ((flags & IT_LAST) ? TS_OFF_COL1 : TS_OFF_COL0));
 #pragma unroll
-              for (int u = 0; u < TS_U; ++u)
-                {
-                  const int k = lane + 32 * u;
-                  if (k < cntc)
-                    {
-                      cN[u] = scol[k];
-                      pendN |= 1u << u;
-                    }
-                }
+            for (int u = 0; u < TS_U; ++u)
+              {
+                const int k = lane + 32 * u;
+                if (k < cntc)
+                  {
+                    cN[u] = scol[k];
+                    pendN |= 1u << u;
+                  }
+              }
 #pragma unroll
-              for (int u = 0; u < TS_U; ++u)
-                if (pendN & (1u << u))
-                  bN[u] = ld_relaxed_u64(x + cN[u]);
-              slotG = slotG + 1 == NSLOT ? 0 : slotG + 1;
-            }
-          // ================= B(it-3) =================
-          // (before R: the item R waits for may depend, through other warps, on the
-          //  group this stage publishes)
-          if (it >= 3)
-            {
-              const unsigned char *S     = ring + (size_t)slotB * TS_SLOT;
-              const int4           h     = *reinterpret_cast<const int4 *>(S);
-              const int            flags = h.y;
-              if (flags & IT_LAST)
+            for (int u = 0; u < TS_U; ++u)
+              if (pendN & (1u << u))
+                bN[u] = ld_relaxed_u64(x + cN[u]);
+            if ((flags & IT_LAST) && lane < (flags & 7))
+              rS[kg] = rhs_vec[h.x + lane];
+            slotG = slotG + 1 == NSLOT ? 0 : slotG + 1;
+            phaseG ^= slotG == 0;
+          }
+        TS_TICK(1)
+        // ================= B(it-3) =================
+        // (before R: the item R waits for may depend, through other warps, on the
+        //  group this stage publishes)
+        if (it >= 3)
+          {
+            const unsigned char *S     = ring + (size_t)slotB * TS_SLOT;
+            const int4           h     = *reinterpret_cast<const int4 *>(S);
+            const int            flags = h.y;
+            if (flags & IT_LAST)
+              {
+                const int     m = flags & 7, r0 = h.x;
+                const double *tri = reinterpret_cast<const double *>(S + TS_OFF_TRI);
+                const double *di  = reinterpret_cast<const double *>(S + TS_OFF_DINV);
+                double        out[TRSV_G];
+                // accB = (sum of couplings) - rhs, see the hand-over below
+#pragma unroll
+                for (int a = 0; a < TRSV_G; ++a)
+                  out[a] = -accB[a];
+                if (UPPER)
+                  {
+#pragma unroll
+                    for (int a = TRSV_G - 1; a >= 0; --a)
+                      {
+                        double v = out[a];
+#pragma unroll
+                        for (int b = TRSV_G - 1; b > a; --b)
+                          v -= tri[tri_index(true, a, b)] * out[b];
+                        out[a] = v * di[a]; // (rows >= m: zero coefficients, zero result)
+                      }
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int a = 0; a < TRSV_G; ++a)
+                      {
+                        double v = out[a];
+#pragma unroll
+                        for (int b = 0; b < a; ++b)
+                          v -= tri[tri_index(false, a, b)] * out[b];
+                        out[a] = v;
+                      }
+                  }
+                if (lane < m)
+                  {
+                    double v = out[0];
+#pragma unroll
+                    for (int a = 1; a < TRSV_G; ++a)
+                      if (lane == a)
+                        v = out[a];
+                    st_result(x + r0 + lane, v);
+                    if (trace) // debugging aid (glsns_ilu_apply_trace): when was the row published
+                      {
+                        unsigned long long tns;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+                        trace[r0 + lane] = tns;
+                      }
+                  }
+                // shift the solved rows into the register window: distance d of the
+                // next group of the chain is m-1-a (lower sweep) or a (upper sweep)
                 {
-                  const int     m = flags & 7, r0 = h.x;
-                  const double *rhs = reinterpret_cast<const double *>(S + TS_OFF_RHS);
-                  const double *tri = reinterpret_cast<const double *>(S + TS_OFF_TRI);
-                  const double *di  = reinterpret_cast<const double *>(S + TS_OFF_DINV);
-                  double        out[TRSV_G];
+                  const int    d  = lane & 15;
+                  const double up = __shfl_up_sync(0xffffffffu, win, m, 16);
+                  double       nv = up;
 #pragma unroll
                   for (int a = 0; a < TRSV_G; ++a)
-                    out[a] = a < m ? rhs[a] - accB[a] : 0.0;
-                  if (UPPER)
-                    {
+                    if (a < m && d == (UPPER ? a : m - 1 - a))
+                      nv = out[a];
+                  win = nv;
+                }
+              }
+            __syncwarp(); // every lane is done with the slot before it is refilled
+            TS_TICK(2)
+            if (lane == 0 && n_iss < n_items)
+              {
+                const unsigned bytes = 16u * (unsigned)h.w; // size of the item NSLOT ahead
+                mbar_expect_tx(bars + slotB, bytes);
+                bulk_load(ring + (size_t)slotB * TS_SLOT, src, bytes, bars + slotB, policy);
+                src += bytes;
+                ++n_iss;
+              }
+            slotB = slotB + 1 == NSLOT ? 0 : slotB + 1;
+          }
+        TS_TICK(3)
+        // ================= R(it-2) =================
+        if (it >= 2 && it <= n_items + 1)
+          {
+            const unsigned char *S     = ring + (size_t)slotR * TS_SLOT;
+            const int4           h     = *reinterpret_cast<const int4 *>(S);
+            const int            flags = h.y, m = flags & 7, cp = pad4(flags >> 16);
+            const bool           lastR = flags & IT_LAST;
+            const double        *sval  = reinterpret_cast<const double *>(
+              S + (lastR ? TS_OFF_COL1 : TS_OFF_COL0) + 4 * cp);
+            long long spins    = 0;
+            for (;;)
+              {
 #pragma unroll
-                      for (int a = TRSV_G - 1; a >= 0; --a)
-                        if (a < m)
-                          {
-                            double v = out[a];
-#pragma unroll
-                            for (int b = TRSV_G - 1; b >= 0; --b)
-                              if (b > a && b < m)
-                                v -= tri[a * 4 + b] * out[b];
-                            out[a] = v * di[a]; // Ifpack stores and applies the inverted diagonal
-                          }
-                    }
-                  else
+                for (int u = 0; u < TS_U; ++u)
+                  if ((pendG & (1u << u)) && bG[u] != SENTINEL)
                     {
+                      pendG &= ~(1u << u);
+                      const double xv = __longlong_as_double((long long)bG[u]);
+                      const int    k  = lane + 32 * u;
 #pragma unroll
                       for (int a = 0; a < TRSV_G; ++a)
                         if (a < m)
-                          {
-                            double v = out[a];
-#pragma unroll
-                            for (int b = 0; b < TRSV_G; ++b)
-                              if (b < a)
-                                v -= tri[a * 4 + b] * out[b];
-                            out[a] = v;
-                          }
+                          acc[a] += sval[a * cp + k] * xv;
                     }
-                  if (lane < m)
-                    {
-                      double v = out[0];
+                if (!__any_sync(0xffffffffu, pendG != 0))
+                  break;
 #pragma unroll
-                      for (int a = 1; a < TRSV_G; ++a)
-                        if (lane == a)
-                          v = out[a];
-                      st_result(x + r0 + lane, v);
-                      if (trace) // debugging aid (glsns_ilu_apply_trace): when was the row published
-                        {
-                          unsigned long long tns;
-                          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-                          trace[r0 + lane] = tns;
-                        }
-                    }
-                  // shift the solved rows into the register window: distance d of the
-                  // next group of the chain is m-1-a (lower sweep) or a (upper sweep)
+                for (int u = 0; u < TS_U; ++u)
+                  if (pendG & (1u << u))
+                    bG[u] = ld_relaxed_u64(x + cG[u]);
+                // bug guard: give up after seconds of waiting, or as soon as another
+                // warp has given up (the host reports GLSNS_ERR_CUDA)
+                if ((++spins & 1023) == 0 &&
+                    (spins > SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
                   {
-                    const int    d  = lane & 15;
-                    const double up = __shfl_up_sync(0xffffffffu, win, m, 16);
-                    double       nv = up;
-#pragma unroll
-                    for (int a = 0; a < TRSV_G; ++a)
-                      if (a < m && d == (UPPER ? a : m - 1 - a))
-                        nv = out[a];
-                    win = nv;
-                  }
-                }
-              __syncwarp(); // every lane is done with the slot before it is refilled
-              issue(slotB);
-              slotB = slotB + 1 == NSLOT ? 0 : slotB + 1;
-            }
-          // ================= R(it-2) =================
-          bool lastR = false;
-          if (it >= 2 && it <= n_items + 1)
-            {
-              const unsigned char *S     = ring + (size_t)slotR * TS_SLOT;
-              const int            flags = reinterpret_cast<const int4 *>(S)->y;
-              const int            m     = flags & 7;
-              const double        *sval  = reinterpret_cast<const double *>(S + TS_OFF_VAL);
-              lastR                      = flags & IT_LAST;
-              long long spins            = 0;
-              int       dbg_near         = 0x7fffffff;
-              for (;;)
-                {
-#pragma unroll
-                  for (int u = 0; u < TS_U; ++u)
-                    if ((pendG & (1u << u)) && bG[u] != SENTINEL)
-                      {
-                        pendG &= ~(1u << u);
-                        const double xv = __longlong_as_double((long long)bG[u]);
-                        const int    k  = lane + 32 * u;
-#pragma unroll
-                        for (int a = 0; a < TRSV_G; ++a)
-                          if (a < m)
-                            acc[a] += sval[a * TS_CH + k] * xv;
-                      }
-                  if (!__any_sync(0xffffffffu, pendG != 0))
+                    atomicExch(&counters[1], 2);
                     break;
-                  if (trace && spins == 0)
-                    { // debugging aid: which entries made this item wait (row distance)
-                      const int r0 = reinterpret_cast<const int4 *>(S)->x;
-#pragma unroll
-                      for (int u = 0; u < TS_U; ++u)
-                        if (pendG & (1u << u))
-                          dbg_near = min(dbg_near, abs(cG[u] - r0));
-                    }
-#pragma unroll
-                  for (int u = 0; u < TS_U; ++u)
-                    if (pendG & (1u << u))
-                      bG[u] = ld_relaxed_u64(x + cG[u]);
-                  // bug guard: give up after seconds of waiting, or as soon as another
-                  // warp has given up (the host reports GLSNS_ERR_CUDA)
-                  if ((++spins & 1023) == 0 &&
-                      (spins > SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
-                    {
-                      atomicExch(&counters[1], 2);
-                      break;
-                    }
-                }
-              if (trace)
-                {
-#pragma unroll
-                  for (int o = 16; o > 0; o >>= 1)
-                    dbg_near = min(dbg_near, __shfl_xor_sync(0xffffffffu, dbg_near, o));
-                  if (lane == 0 && lastR)
-                    {
-                      const int r0         = reinterpret_cast<const int4 *>(S)->x;
-                      trace[2 * trace_n + r0] = ((unsigned long long)spins << 32) | (unsigned)dbg_near;
-                    }
-                }
-              slotR = slotR + 1 == NSLOT ? 0 : slotR + 1;
-            }
-          // ---- hand-over R -> B: totals of a finished group in every lane ----
-          if (lastR)
-            {
-              // item it-2 closes its group: add the coupling to the chain rows in
-              // registers (all solved by now: their B stages ran at or before this
-              // iteration), then total over the warp
+                  }
+              }
+            TS_TICK(4)
+            if (lastR)
               {
-                const unsigned char *S  = ring + (size_t)(slotR == 0 ? NSLOT - 1 : slotR - 1) * TS_SLOT;
-                const int4           h  = *reinterpret_cast<const int4 *>(S);
-                const int            m  = h.y & 7, d = lane & 15, hh = lane >> 4;
-                const double        *fw = reinterpret_cast<const double *>(S + TS_OFF_FWD);
-                const int            gap = (h.y >> 4) & 15;
+                // the group is complete: add the coupling to the chain rows in registers
+                // (all solved by now: their B stages ran at or before this step), fold
+                // in the right-hand side, total over the warp
+                const int     d = lane & 15, hh = lane >> 4;
+                const double *fw = reinterpret_cast<const double *>(S + TS_OFF_FWD);
+                const int     gap = (flags >> 4) & 15;
                 if (gap) // diagonal-only rows between the predecessor and this group
                   win = __shfl_up_sync(0xffffffffu, win, gap, 16);
                 if ((unsigned)h.z & (1u << d))
@@ -445,19 +502,24 @@ namespace glsns
                       if ((a & 1) == hh && a < m)
                         acc[a] += fw[a * TS_WIN + d] * win;
                   }
-              }
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
                 for (int a = 0; a < TRSV_G; ++a)
-                  acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+                  if (lane == a && a < m)
+                    acc[a] -= rS[kr];
 #pragma unroll
-              for (int a = 0; a < TRSV_G; ++a)
-                {
-                  accB[a] = acc[a];
-                  acc[a]  = 0;
-                }
-            }
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                  for (int a = 0; a < TRSV_G; ++a)
+                    acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+#pragma unroll
+                for (int a = 0; a < TRSV_G; ++a)
+                  {
+                    accB[a] = acc[a];
+                    acc[a]  = 0;
+                  }
+              }
+            slotR = slotR + 1 == NSLOT ? 0 : slotR + 1;
+          }
       };
       for (int64_t it = 0; it < n_items + 3; it += 3)
         {
@@ -467,7 +529,13 @@ namespace glsns
           if (it + 2 < n_items + 3)
             step(std::integral_constant<int, 2>(), it + 2);
         }
-      cp_async_wait<0>();
+      if (trace && lane == 0 && (w + 1) * 8 <= trace_n)
+        { // cycles in: mbarrier wait, gather issue, B, ring refill, R, hand-over(+loop); items
+          for (int k = 0; k < 6; ++k)
+            trace[2 * trace_n + w * 8 + k] = (unsigned long long)tstage[k];
+          trace[2 * trace_n + w * 8 + 6] = (unsigned long long)n_items;
+        }
+#undef TS_TICK
     }
 
     __global__ void __launch_bounds__(256)
@@ -494,9 +562,9 @@ namespace glsns
         if (getenv("GLSNS_TRSV_NSLOT"))
           t.nslot = atoi(getenv("GLSNS_TRSV_NSLOT"));
         t.warps = std::max(1, std::min(8, t.warps));
-        if (t.nslot < 5 || t.nslot > 9)
+        if (t.nslot < 5 || t.nslot > TS_MAX_SLOTS)
           t.nslot = 7;
-        while ((size_t)t.warps * (t.nslot * TS_SLOT + TS_REC * 32) > (size_t)TS_SMEM_MAX)
+        while ((size_t)t.warps * (t.nslot * (TS_SLOT + 8)) > (size_t)TS_SMEM_MAX)
           --t.warps;
         return t;
       }();
@@ -505,14 +573,13 @@ namespace glsns
 
     template <bool UPPER>
     glsns_status
-    launch_chain(glsns_context *ctx, const int64_t *warp_ptr, const TrsvItem *items,
+    launch_chain(glsns_context *ctx, const TrsvWarpDir *dir, const unsigned char *stream,
                  const double *rhs, double *x, unsigned long long *trace)
     {
       const TrsvConfig cfg  = trsv_config();
-      const size_t     smem = (size_t)cfg.warps * (cfg.nslot * TS_SLOT + TS_REC * 32);
-      void (*kern)(const int64_t *, const TrsvItem *, const int32_t *, const double *,
-                   const double *, const double *, double *, int *, unsigned long long *,
-                   const int64_t) = nullptr;
+      const size_t     smem = (size_t)cfg.warps * cfg.nslot * (TS_SLOT + 8);
+      void (*kern)(const TrsvWarpDir *, const unsigned char *, const double *, double *, int *,
+                   unsigned long long *, const int64_t) = nullptr;
       switch (cfg.nslot)
         {
           case 5: kern = trsv_chain_kernel<UPPER, 5>; break;
@@ -523,12 +590,9 @@ namespace glsns
         }
       GLSNS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
-      const int32_t *col = ctx->col.p;
-      const double  *lu = ctx->lu.p, *dinv = ctx->dinv.p;
-      int           *counters = ctx->counters.p;
-      void *args[] = {(void *)&warp_ptr, (void *)&items, (void *)&col, (void *)&lu,
-                      (void *)&dinv,     (void *)&rhs,   (void *)&x,   (void *)&counters,
-                      (void *)&trace,    (void *)&ctx->n_owned};
+      int  *counters = ctx->counters.p;
+      void *args[]   = {(void *)&dir,      (void *)&stream, (void *)&rhs,         (void *)&x,
+                        (void *)&counters, (void *)&trace,  (void *)&ctx->n_owned};
       GLSNS_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kern, dim3(ctx->trsv_grid),
                                                   dim3(cfg.warps * 32), args, smem, ctx->stream));
       ctx->kernel_launches++;
@@ -586,8 +650,7 @@ namespace glsns
     std::vector<uint8_t> link(ng), has_succ(ng);
 
     // One sweep: levels, chain links, level-ordered schedule on NW warps, item lists.
-    auto schedule = [&](const bool upper, DevBuf<TrsvItem> &d_items, DevBuf<int64_t> &d_ptr,
-                        int32_t &n_levels) -> glsns_status {
+    auto schedule = [&](const bool upper, TrsvSweep &sw, int32_t &n_levels) -> glsns_status {
       // entries of group g this sweep reads, [kb, ke) in CSR offsets of its first row
       auto range = [&](int64_t g, int64_t &kb, int64_t &ke) {
         const int64_t i = grp_ptr[g];
@@ -761,17 +824,55 @@ namespace glsns
       for (int64_t g = 0; g < ng; ++g)
         for (int32_t a = 0; a < grp_m[g]; ++a)
           row_warp[grp_ptr[g] + a] = warp_of[g] | (fmask[g] ? 1 << 30 : 0);
-      GLSNS_TRY(dev_upload(ctx, d_items, items.data(), items.size()));
-      GLSNS_TRY(dev_upload(ctx, d_ptr, n_it.data(), n_it.size()));
+      // stream layout: the blobs of one warp back to back, warps one after another
+      const int64_t        nit = n_it[NW];
+      std::vector<int64_t> blob_off((size_t)nit);
+      std::vector<int32_t> next16((size_t)nit, 0);
+      std::vector<TrsvWarpDir> dirv((size_t)NW);
+      int64_t              off = 0;
+      for (int64_t w = 0; w < NW; ++w)
+        {
+          TrsvWarpDir &D = dirv[w];
+          memset(&D, 0, sizeof(D));
+          D.offset  = off;
+          D.n_items = (int32_t)(n_it[w + 1] - n_it[w]);
+          for (int64_t k = n_it[w]; k < n_it[w + 1]; ++k)
+            {
+              const int32_t b16 = blob_bytes(items[(size_t)k].flags) / 16;
+              blob_off[(size_t)k] = off;
+              off += 16 * (int64_t)b16;
+              const int64_t j = k - n_it[w];
+              if (j < cfg.nslot)
+                D.first16[j] = b16;
+              else
+                next16[(size_t)(k - cfg.nslot)] = b16;
+            }
+        }
+      sw.n_items      = nit;
+      sw.stream_bytes = off;
+      GLSNS_TRY(dev_upload(ctx, sw.items, items.data(), items.size()));
+      GLSNS_TRY(dev_upload(ctx, sw.blob_off, blob_off.data(), blob_off.size()));
+      GLSNS_TRY(dev_upload(ctx, sw.next16, next16.data(), next16.size()));
+      GLSNS_TRY(dev_upload(ctx, sw.dir, reinterpret_cast<const unsigned char *>(dirv.data()),
+                           dirv.size() * sizeof(TrsvWarpDir)));
+      GLSNS_TRY(dev_alloc(ctx, sw.stream, (size_t)std::max<int64_t>(off, 16)));
+      if (nit)
+        {
+          trsv_pack_static_kernel<<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            nit, sw.items.p, sw.blob_off.p, sw.next16.p, ctx->col.p, sw.stream.p);
+          ctx->kernel_launches++;
+          GLSNS_CUDA(ctx, cudaGetLastError());
+        }
       GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
       return GLSNS_OK;
     };
-    GLSNS_TRY(schedule(false, ctx->items_l, ctx->wptr_l, ctx->levels_l));
-    GLSNS_TRY(schedule(true, ctx->items_u, ctx->wptr_u, ctx->levels_u));
+    GLSNS_TRY(schedule(false, ctx->trsv_l, ctx->levels_l));
+    GLSNS_TRY(schedule(true, ctx->trsv_u, ctx->levels_u));
     return GLSNS_OK;
   }
 
-  // after every factorisation: the inverted diagonal of U (Ifpack keeps it too)
+  // after every factorisation: the inverted diagonal of U (Ifpack keeps it too) and
+  // the factor values in stream order
   glsns_status
   trsv_prepare(glsns_context *ctx)
   {
@@ -782,6 +883,20 @@ namespace glsns
         inv_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->diag_pos.p,
                                                                              ctx->lu.p,
                                                                              ctx->dinv.p);
+        ctx->kernel_launches++;
+      }
+    if (ctx->trsv_l.n_items)
+      {
+        const int64_t nit = ctx->trsv_l.n_items;
+        trsv_pack_values_kernel<false><<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+          nit, ctx->trsv_l.items.p, ctx->trsv_l.blob_off.p, ctx->lu.p, ctx->trsv_l.stream.p);
+        ctx->kernel_launches++;
+      }
+    if (ctx->trsv_u.n_items)
+      {
+        const int64_t nit = ctx->trsv_u.n_items;
+        trsv_pack_values_kernel<true><<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+          nit, ctx->trsv_u.items.p, ctx->trsv_u.blob_off.p, ctx->lu.p, ctx->trsv_u.stream.p);
         ctx->kernel_launches++;
       }
     GLSNS_CUDA(ctx, cudaGetLastError());
@@ -805,8 +920,10 @@ namespace glsns
       }
     if (ctx->n_groups)
       {
-        GLSNS_TRY(launch_chain<false>(ctx, ctx->wptr_l.p, ctx->items_l.p, r, ctx->ytmp.p, trace));
-        GLSNS_TRY(launch_chain<true>(ctx, ctx->wptr_u.p, ctx->items_u.p, ctx->ytmp.p, z,
+        GLSNS_TRY(launch_chain<false>(ctx, reinterpret_cast<const TrsvWarpDir *>(ctx->trsv_l.dir.p),
+                                      ctx->trsv_l.stream.p, r, ctx->ytmp.p, trace));
+        GLSNS_TRY(launch_chain<true>(ctx, reinterpret_cast<const TrsvWarpDir *>(ctx->trsv_u.dir.p),
+                                     ctx->trsv_u.stream.p, ctx->ytmp.p, z,
                                     trace ? trace + n : nullptr));
       }
     GLSNS_CUDA(ctx, cudaGetLastError());

@@ -72,10 +72,13 @@ for name, t, w, upper in (("lower", tl, wl, False), ("upper", tu, wu, True)):
     out[name]["critical_path"] = {"same_warp_hops": hops_same, "same_warp_us": time_same / 1e3,
                                   "other_warp_hops": hops_other, "other_warp_us": time_other / 1e3}
 for name, pl in zip(("lower", "upper"), hp.last_trace_polls):
-    pl = pl[pl != 0]
-    rounds, near = (pl >> np.uint64(32)).astype(np.int64), (pl & np.uint64(0xFFFFFFFF)).astype(np.int64)
-    near = near[near < 2**30]
-    out[name]["groups_that_polled"] = int(len(pl))
-    out[name]["poll_rounds_p50_p90"] = [float(np.percentile(rounds, p)) for p in (50, 90)] if len(pl) else None
-    out[name]["nearest_missing_row_distance_hist"] = {str(k): int(((near >= k) & (near < 2 * k)).sum()) for k in (1, 2, 4, 8, 16, 32, 64, 128, 256, 1024, 4096, 16384)}
+    nw = min(len(pl) // 8, 148 * 8)
+    st = pl[:nw * 8].reshape(nw, 8).astype(np.float64)
+    busy = st[st[:, 6] > 0]
+    tot = busy[:, :6].sum(axis=0)
+    out[name]["stage_cycles_per_item_[mbar_wait,gather,B,refill,R,handover+loop]"] = [float(v) for v in tot / busy[:, 6].sum()]
+    out[name]["stage_share"] = [float(v) for v in tot / tot.sum()]
+    # the busiest warp (most items): closest to a warp that is always on the critical path
+    k = int(np.argmax(st[:, 6]))
+    out[name]["busiest_warp_items_and_cycles_per_item"] = [float(st[k, 6])] + [float(v / st[k, 6]) for v in st[k, :6]]
 print(json.dumps(out, indent=1))
