@@ -65,14 +65,15 @@ namespace glsns
     constexpr int TS_OFF_FWD  = 96;
     constexpr int TS_OFF_COL1 = TS_OFF_FWD + 8 * TRSV_G * TS_WIN; // 608 (last item)
     constexpr int TS_OFF_COL0 = 16;                                 // (other items)
-    constexpr int TS_SLOT     = TS_OFF_COL1 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 5216
     constexpr int TS_MAX_SLOTS = 9;
     constexpr int TS_SMEM_MAX  = 227 * 1024;
 
-    // item flags: bits 0-2 rows in the group (m); bits 4-7 diagonal-only rows between
-    // the chain predecessor and this group; bit 8 last item of its group; bits 16..
-    // entries.  fmask (last item): bit d = couples to the chain row at distance d
-    constexpr int IT_LAST = 1 << 8;
+    // item flags: bits 0-2 rows in the group (m); bit 8 last helper item of its group;
+    // bit 9 solver item (one per group: inverted diagonal, in-group triangle, couplings
+    // to the chain window; fmask bit d = couples to the chain row at distance d);
+    // bits 16.. entries of a helper item
+    constexpr int IT_LAST   = 1 << 8;
+    constexpr int IT_SOLVER = 1 << 9;
 
     __host__ __device__ inline int
     pad4(int v)
@@ -83,7 +84,7 @@ namespace glsns
     blob_bytes(int flags)
     {
       const int m = flags & 7, c = pad4(flags >> 16);
-      return ((flags & IT_LAST) ? TS_OFF_COL1 : TS_OFF_COL0) + 4 * c + 8 * m * c;
+      return (flags & IT_SOLVER) ? TS_OFF_COL1 : TS_OFF_COL0 + 4 * c + 8 * m * c;
     }
     // in-group triangle, packed: lower (1,0)(2,0)(2,1)(3,0)(3,1)(3,2); upper (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
     __host__ __device__ inline int
@@ -188,8 +189,10 @@ namespace glsns
       unsigned char *B = stream + blob_off[it];
       if (lane == 0)
         *reinterpret_cast<int4 *>(B) = make_int4(d.r0, d.flags, d.fmask, next16[it]);
+      if (d.flags & IT_SOLVER)
+        return;
       const int cntc = d.flags >> 16, cp = pad4(cntc);
-      int32_t  *bc   = reinterpret_cast<int32_t *>(B + ((d.flags & IT_LAST) ? TS_OFF_COL1 : TS_OFF_COL0));
+      int32_t  *bc   = reinterpret_cast<int32_t *>(B + TS_OFF_COL0);
       for (int k = lane; k < cp; k += 32)
         bc[k] = k < cntc ? col[d.rs0 + d.e_off + k] : d.r0; // padding: any valid index
     }
@@ -208,109 +211,124 @@ namespace glsns
       const TrsvItem d = items[it];
       unsigned char *B = stream + blob_off[it];
       const int      m = d.flags & 7, cntc = d.flags >> 16, cp = pad4(cntc);
-      const bool     last = d.flags & IT_LAST;
-      double        *bv   = reinterpret_cast<double *>(B + (last ? TS_OFF_COL1 : TS_OFF_COL0) + 4 * cp);
-      for (int a = 0; a < m; ++a)
-        for (int k = lane; k < cp; k += 32)
-          bv[a * cp + k] = k < cntc ? __ldcs(lu + d.rs0 + (int64_t)a * d.len + d.e_off + k) : 0.0;
-      if (last)
+      if (!(d.flags & IT_SOLVER))
         {
-          double *di = reinterpret_cast<double *>(B + TS_OFF_DINV);
-          double *tr = reinterpret_cast<double *>(B + TS_OFF_TRI);
-          double *fw = reinterpret_cast<double *>(B + TS_OFF_FWD);
-          if (lane < TRSV_G) // Ifpack stores and applies the inverted diagonal
-            di[lane] = lane < m ? 1.0 / lu[d.rs0 + (int64_t)lane * d.len + d.nlow + lane] : 0.0;
-          if (lane < 16)
+          double *bv = reinterpret_cast<double *>(B + TS_OFF_COL0 + 4 * cp);
+          for (int a = 0; a < m; ++a)
+            for (int k = lane; k < cp; k += 32)
+              bv[a * cp + k] = k < cntc ? __ldcs(lu + d.rs0 + (int64_t)a * d.len + d.e_off + k) : 0.0;
+          return;
+        }
+      double *di = reinterpret_cast<double *>(B + TS_OFF_DINV);
+      double *tr = reinterpret_cast<double *>(B + TS_OFF_TRI);
+      double *fw = reinterpret_cast<double *>(B + TS_OFF_FWD);
+      if (lane < TRSV_G) // Ifpack stores and applies the inverted diagonal
+        di[lane] = lane < m ? 1.0 / lu[d.rs0 + (int64_t)lane * d.len + d.nlow + lane] : 0.0;
+      if (lane < 16)
+        {
+          const int a = lane >> 2, b = lane & 3;
+          if (UPPER ? b > a : b < a)
+            tr[tri_index(UPPER, a, b)] =
+              (a < m && b < m) ? lu[d.rs0 + (int64_t)a * d.len + d.nlow + b] : 0.0;
+        }
+      // coupling to the chain window: entry of row a for the chain row at distance dd
+      const unsigned fmask = (unsigned)d.fmask;
+      for (int q = lane; q < TRSV_G * TS_WIN; q += 32)
+        {
+          const int a = q / TS_WIN, dd = q % TS_WIN;
+          double    v = 0;
+          if (a < m && (fmask & (1u << dd)))
             {
-              const int a = lane >> 2, b = lane & 3;
-              if (UPPER ? b > a : b < a)
-                tr[tri_index(UPPER, a, b)] =
-                  (a < m && b < m) ? lu[d.rs0 + (int64_t)a * d.len + d.nlow + b] : 0.0;
+              const int before = __popc(fmask & ((1u << dd) - 1u));
+              const int pos    = UPPER ? d.nlow + m + before : d.nlow - 1 - before;
+              v                = lu[d.rs0 + (int64_t)a * d.len + pos];
             }
-          // coupling to the chain rows held in registers: entry of row a at distance dd
-          const unsigned fmask = (unsigned)d.fmask;
-          for (int q = lane; q < TRSV_G * TS_WIN; q += 32)
-            {
-              const int a = q / TS_WIN, dd = q % TS_WIN;
-              double    v = 0;
-              if (a < m && (fmask & (1u << dd)))
-                {
-                  const int before = __popc(fmask & ((1u << dd) - 1u));
-                  const int pos    = UPPER ? d.nlow + m + before : d.nlow - 1 - before;
-                  v                = lu[d.rs0 + (int64_t)a * d.len + pos];
-                }
-              fw[q] = v;
-            }
+          fw[q] = v;
         }
     }
 
     // ---- the solve ---------------------------------------------------------------
-    // One warp = one list of items in the order the host scheduled them.  Software
-    // pipeline over the items (three rotating register sets, selected at compile time):
-    //   G(i+3): wait for the item's bulk copy, column indices from the ring, solution
-    //           entries and the right-hand side requested from L2
-    //   B(i)  : last item of a group: solve the in-group triangle, publish the
-    //           solution, shift it into the register window, refill the ring slot
-    //   R(i+1): entries that were not there yet are re-read until they are; multiply;
-    //           last item of a group: add the coupling to the register window,
-    //           warp-reduce
-    template <bool UPPER, int NSLOT>
-    __global__ void __launch_bounds__(256, 1)
-    trsv_chain_kernel(const TrsvWarpDir *__restrict__ dir, const unsigned char *__restrict__ stream,
-                      const double *__restrict__ rhs_vec, double *x, int *counters,
-                      unsigned long long *trace, const int64_t trace_n)
+    // A TEAM of 1 + K warps owns one list of groups (chains, in the order the host
+    // scheduled them):
+    //   * K helper warps take the groups round-robin.  A helper streams the items of
+    //     its groups (column indices + factor entries) through its own ring, gathers
+    //     the solution entries they refer to (re-reading until they are there),
+    //     multiplies, folds in the right-hand side, reduces over the warp and posts
+    //     the four totals in the team's mailbox.  None of this depends on the chain,
+    //     so it runs ahead of it, on several groups at once.
+    //   * the solver warp is the chain's recurrence and nothing else: mailbox totals
+    //     minus the couplings to the last 16 rows of the chain (kept in a tiny
+    //     shared-memory window, coefficients from the solver's own stream), the 4x4
+    //     triangle, publish.  ~300 issue slots per group.
+    constexpr int TS_NSH  = 5;  // helper ring slots
+    constexpr int TS_NSS  = 8;  // solver ring slots
+    constexpr int TS_MBOX = 8;  // mailbox entries per team
+    constexpr int TS_HSLOT = TS_OFF_COL0 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 4624
+    constexpr int TS_SSLOT = TS_OFF_COL1;                                   // 608
+    constexpr int TS_TEAM_AREA = 1024; // window 128 | mailbox 256 | (48 spare) | barriers
+    static_assert(TS_MBOX == 8 && 128 + 32 * TS_MBOX + 4 * TS_MBOX + 16 + 8 * (4 * TS_NSH + TS_NSS) <= TS_TEAM_AREA,
+                  "team area");
+
+    template <bool UPPER>
+    __global__ void __launch_bounds__(512, 1)
+    trsv_team_kernel(const TrsvWarpDir *__restrict__ dir, const unsigned char *__restrict__ stream,
+                     const double *__restrict__ rhs_vec, double *x, int *counters,
+                     unsigned long long *trace, const int64_t trace_n, const int K)
     {
-      static_assert(NSLOT >= 5 && NSLOT <= TS_MAX_SLOTS, "ring depth");
-      extern __shared__ __align__(128) unsigned char ring_all[];
-      const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-      const int      nwarp = blockDim.x >> 5;
-      const int64_t  w     = (int64_t)warp * gridDim.x + blockIdx.x; // consecutive lists on different SMs
-      unsigned char *ring  = ring_all + (size_t)warp * NSLOT * TS_SLOT;
-      unsigned long long *bars =
-        reinterpret_cast<unsigned long long *>(ring_all + (size_t)nwarp * NSLOT * TS_SLOT) + warp * NSLOT;
-      const TrsvWarpDir *D       = dir + w;
-      const int64_t      n_items = D->n_items;
+      extern __shared__ __align__(128) unsigned char smem_all[];
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int team_in_cta = warp / (K + 1), role = warp - team_in_cta * (K + 1);
+      const int n_teams_cta = (blockDim.x >> 5) / (K + 1);
+      if (team_in_cta >= n_teams_cta)
+        return;
+      const int64_t team      = (int64_t)team_in_cta * gridDim.x + blockIdx.x; // consecutive lists on different SMs
+      const size_t  team_smem = (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SSLOT + TS_TEAM_AREA;
+      unsigned char *T0   = smem_all + (size_t)team_in_cta * team_smem;
+      unsigned char *area = T0 + (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SSLOT;
+      double        *wsm  = reinterpret_cast<double *>(area);            // [16] chain window by row & 15
+      double        *mbox = reinterpret_cast<double *>(area + 128);      // [TS_MBOX][4], all-ones = empty
+      unsigned long long *bars_all = reinterpret_cast<unsigned long long *>(area + 128 + 36 * TS_MBOX + 16);
+      const TrsvWarpDir  *D        = dir + team * (K + 1) + role;
+      const int64_t       n_items  = D->n_items;
+      unsigned long long  policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      // team-wide initialisation by the solver warp (window zero, mailbox empty), made
+      // visible to the helpers by the one CTA barrier of the kernel
+      if (role == 0)
+        {
+          if (lane < 16)
+            wsm[lane] = 0.0;
+          reinterpret_cast<unsigned long long *>(mbox)[lane] = SENTINEL; // TS_MBOX * 4 = 32 entries, all empty
+        }
+      __syncthreads();
       if (n_items == 0)
         return;
-      unsigned long long policy;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      const unsigned char *src = stream + D->offset;
 
-      // ---- issue side (lane 0): running offset in the stream, sizes from the headers ----
-      const unsigned char *src   = stream + D->offset;
-      int64_t              n_iss = 0;
-      if (lane == 0)
+      if (role == 0)
         {
-          for (int s = 0; s < NSLOT; ++s)
-            mbar_init(bars + s, 1);
-          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-          for (int s = 0; s < NSLOT; ++s)
-            if (s < n_items)
-              {
-                const unsigned bytes = 16u * (unsigned)D->first16[s];
-                mbar_expect_tx(bars + s, bytes);
-                bulk_load(ring + (size_t)s * TS_SLOT, src, bytes, bars + s, policy);
-                src += bytes;
-                ++n_iss;
-              }
-        }
-      __syncwarp();
-
-      // ---- pipeline registers: three rotating sets (no copies: a copy would wait for
-      //      the loads in flight), selected at compile time by the unrolled loop ----
-      int32_t            cS[3][TS_U];
-      unsigned long long bS[3][TS_U];
-      unsigned           pS[3] = {0, 0, 0};
-      double             rS[3] = {0, 0, 0}; // right-hand side of row r0 + lane
-      double             acc[TRSV_G], accB[TRSV_G];
-      double             win = 0; // solution of the chain row at distance (lane & 15)
-#pragma unroll
-      for (int a = 0; a < TRSV_G; ++a)
-        acc[a] = accB[a] = 0;
-      int      slotG = 0, slotR = 0, slotB = 0;
-      unsigned phaseG = 0;
-      long long tstage[6] = {0, 0, 0, 0, 0, 0}; // debugging aid (trace): cycles per stage
+          // =============================== solver ===============================
+          unsigned char      *ring = T0 + (size_t)K * TS_NSH * TS_HSLOT;
+          unsigned long long *bars = bars_all + K * TS_NSH;
+          int64_t             n_iss = 0;
+          if (lane == 0)
+            {
+              for (int s = 0; s < TS_NSS; ++s)
+                mbar_init(bars + s, 1);
+              asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              for (int s = 0; s < TS_NSS && s < n_items; ++s)
+                {
+                  mbar_expect_tx(bars + s, TS_SSLOT);
+                  bulk_load(ring + (size_t)s * TS_SSLOT, src, TS_SSLOT, bars + s, policy);
+                  src += TS_SSLOT;
+                  ++n_iss;
+                }
+            }
+          __syncwarp();
+          int      slot = 0;
+          unsigned phase = 0;
+          long long tstage[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64(); // debugging aid (trace)
 #define TS_TICK(k)                              \
   if (trace)                                    \
     {                                           \
@@ -318,9 +336,158 @@ namespace glsns
       tstage[k] += now_ - tlast;                \
       tlast = now_;                             \
     }
-      long long tlast = clock64();
+          for (int64_t g = 0; g < n_items; ++g)
+            {
+              while (!mbar_try_wait(bars + slot, phase))
+                ;
+              TS_TICK(0)
+              const unsigned char *S  = ring + (size_t)slot * TS_SSLOT;
+              const int4           h  = *reinterpret_cast<const int4 *>(S);
+              const int            r0 = h.x, m = h.y & 7;
+              const double        *di = reinterpret_cast<const double *>(S + TS_OFF_DINV);
+              const double        *tri = reinterpret_cast<const double *>(S + TS_OFF_TRI);
+              const double2       *fw  = reinterpret_cast<const double2 *>(S + TS_OFF_FWD);
+              // couplings to the chain window: rows r0-1-d (lower) / r0+m+d (upper);
+              // coefficients of absent entries are zero (and the window holds finite
+              // numbers), so no masking: all loads first, then four short chains per row
+              double wv[TS_WIN];
+#pragma unroll
+              for (int d = 0; d < TS_WIN; ++d)
+                wv[d] = wsm[(UPPER ? r0 + m + d : r0 - 1 - d) & 15];
+              double s4[TRSV_G][4];
+#pragma unroll
+              for (int a = 0; a < TRSV_G; ++a)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  {
+                    const double2 c0 = fw[a * (TS_WIN / 2) + j], c1 = fw[a * (TS_WIN / 2) + 4 + j];
+                    s4[a][j] = c0.x * wv[2 * j] + c0.y * wv[2 * j + 1];
+                    s4[a][j] += c1.x * wv[8 + 2 * j];
+                    s4[a][j] += c1.y * wv[8 + 2 * j + 1];
+                  }
+              TS_TICK(1)
+              // totals of everything else (minus the right-hand side), from a helper: the
+              // mailbox entry carries its own readiness (all-ones pattern = empty)
+              const int mb = (int)(g & (TS_MBOX - 1));
+              {
+                volatile unsigned long long *mv =
+                  reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4);
+                long long spins = 0;
+                while (!__all_sync(0xffffffffu, mv[lane & 3] != SENTINEL))
+                  if ((++spins & 4095) == 0 &&
+                      (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
+                    {
+                      atomicExch(&counters[1], 2);
+                      break;
+                    }
+              }
+              TS_TICK(2)
+              double out[TRSV_G];
+#pragma unroll
+              for (int a = 0; a < TRSV_G; ++a)
+                out[a] = -(reinterpret_cast<volatile double *>(mbox)[mb * 4 + a] +
+                           ((s4[a][0] + s4[a][1]) + (s4[a][2] + s4[a][3])));
+              __syncwarp();
+              if (lane < TRSV_G) // hand the entry back
+                reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4)[lane] = SENTINEL;
+              if (UPPER)
+                {
+#pragma unroll
+                  for (int a = TRSV_G - 1; a >= 0; --a)
+                    {
+                      double v = out[a];
+#pragma unroll
+                      for (int b = TRSV_G - 1; b > a; --b)
+                        v -= tri[tri_index(true, a, b)] * out[b];
+                      out[a] = v * di[a]; // Ifpack stores and applies the inverted diagonal
+                    }
+                }
+              else
+                {
+#pragma unroll
+                  for (int a = 0; a < TRSV_G; ++a)
+                    {
+                      double v = out[a];
+#pragma unroll
+                      for (int b = 0; b < a; ++b)
+                        v -= tri[tri_index(false, a, b)] * out[b];
+                      out[a] = v;
+                    }
+                }
+              if (lane < m)
+                {
+                  double v = out[0];
+#pragma unroll
+                  for (int a = 1; a < TRSV_G; ++a)
+                    if (lane == a)
+                      v = out[a];
+                  st_result(x + r0 + lane, v);
+                  wsm[(r0 + lane) & 15] = v;
+                  if (trace) // debugging aid (glsns_ilu_apply_trace): when was the row published
+                    {
+                      unsigned long long tns;
+                      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+                      trace[r0 + lane] = tns;
+                    }
+                }
+              __syncwarp();
+              TS_TICK(3)
+              if (lane == 0 && n_iss < n_items)
+                {
+                  mbar_expect_tx(bars + slot, TS_SSLOT);
+                  bulk_load(ring + (size_t)slot * TS_SSLOT, src, TS_SSLOT, bars + slot, policy);
+                  src += TS_SSLOT;
+                  ++n_iss;
+                }
+              slot = slot + 1 == TS_NSS ? 0 : slot + 1;
+              phase ^= slot == 0;
+              TS_TICK(4)
+            }
+          if (trace && lane == 0 && (team + 1) * 8 <= trace_n)
+            { // cycles in: ring wait, window product, mailbox wait, triangle+publish, release+refill
+              for (int k = 0; k < 6; ++k)
+                trace[2 * trace_n + team * 8 + k] = (unsigned long long)tstage[k];
+              trace[2 * trace_n + team * 8 + 6] = (unsigned long long)n_items;
+            }
+#undef TS_TICK
+          return;
+        }
 
-      // one pipeline step: G(it) into set KG, B(it-3), R(it-2) from set (KG+1)%3
+      // =============================== helper ===============================
+      const int           hid  = role - 1;
+      unsigned char      *ring = T0 + (size_t)hid * TS_NSH * TS_HSLOT;
+      unsigned long long *bars = bars_all + hid * TS_NSH;
+      int64_t             n_iss = 0;
+      if (lane == 0)
+        {
+          for (int s = 0; s < TS_NSH; ++s)
+            mbar_init(bars + s, 1);
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          for (int s = 0; s < TS_NSH && s < n_items; ++s)
+            {
+              const unsigned bytes = 16u * (unsigned)D->first16[s];
+              mbar_expect_tx(bars + s, bytes);
+              bulk_load(ring + (size_t)s * TS_HSLOT, src, bytes, bars + s, policy);
+              src += bytes;
+              ++n_iss;
+            }
+        }
+      __syncwarp();
+      // pipeline registers: three rotating sets (no copies: a copy would wait for the
+      // loads in flight), selected at compile time by the unrolled loop
+      int32_t            cS[3][TS_U];
+      unsigned long long bS[3][TS_U];
+      unsigned           pS[3] = {0, 0, 0};
+      double             rS[3] = {0, 0, 0}; // right-hand side of row r0 + lane
+      double             acc[TRSV_G];
+#pragma unroll
+      for (int a = 0; a < TRSV_G; ++a)
+        acc[a] = 0;
+      int      slotG = 0, slotR = 0;
+      unsigned phaseG = 0;
+      int64_t  seq    = hid; // position of the helper's current group in the team's list
+      // one pipeline step: G(it) into set KG, R(it-2) from set (KG+1)%3
       auto step = [&](auto KG, const int64_t it) {
         constexpr int      kg = decltype(KG)::value, kr = (kg + 1) % 3;
         int32_t(&cN)[TS_U]            = cS[kg];
@@ -329,19 +496,16 @@ namespace glsns
         int32_t(&cG)[TS_U]            = cS[kr];
         unsigned long long(&bG)[TS_U] = bS[kr];
         unsigned &pendG               = pS[kr];
-        // ================= G(it) =================
+        // ---- G(it): wait for the item, request the solution entries it refers to ----
         pendN = 0;
         if (it < n_items)
           {
-            TS_TICK(5)
             while (!mbar_try_wait(bars + slotG, phaseG))
               ;
-            TS_TICK(0)
-            const unsigned char *S     = ring + (size_t)slotG * TS_SLOT;
+            const unsigned char *S     = ring + (size_t)slotG * TS_HSLOT;
             const int4           h     = *reinterpret_cast<const int4 *>(S);
             const int            flags = h.y, cntc = flags >> 16;
-            const int32_t       *scol =
-              reinterpret_cast<const int32_t *>(S + ((flags & IT_LAST) ? TS_OFF_COL1 : TS_OFF_COL0));
+            const int32_t       *scol  = reinterpret_cast<const int32_t *>(S + TS_OFF_COL0);
 #pragma unroll
             for (int u = 0; u < TS_U; ++u)
               {
@@ -358,103 +522,17 @@ namespace glsns
                 bN[u] = ld_relaxed_u64(x + cN[u]);
             if ((flags & IT_LAST) && lane < (flags & 7))
               rS[kg] = rhs_vec[h.x + lane];
-            slotG = slotG + 1 == NSLOT ? 0 : slotG + 1;
+            slotG = slotG + 1 == TS_NSH ? 0 : slotG + 1;
             phaseG ^= slotG == 0;
           }
-        TS_TICK(1)
-        // ================= B(it-3) =================
-        // (before R: the item R waits for may depend, through other warps, on the
-        //  group this stage publishes)
-        if (it >= 3)
+        // ---- R(it-2): entries not there yet are re-read until they are; multiply ----
+        if (it >= 2)
           {
-            const unsigned char *S     = ring + (size_t)slotB * TS_SLOT;
-            const int4           h     = *reinterpret_cast<const int4 *>(S);
-            const int            flags = h.y;
-            if (flags & IT_LAST)
-              {
-                const int     m = flags & 7, r0 = h.x;
-                const double *tri = reinterpret_cast<const double *>(S + TS_OFF_TRI);
-                const double *di  = reinterpret_cast<const double *>(S + TS_OFF_DINV);
-                double        out[TRSV_G];
-                // accB = (sum of couplings) - rhs, see the hand-over below
-#pragma unroll
-                for (int a = 0; a < TRSV_G; ++a)
-                  out[a] = -accB[a];
-                if (UPPER)
-                  {
-#pragma unroll
-                    for (int a = TRSV_G - 1; a >= 0; --a)
-                      {
-                        double v = out[a];
-#pragma unroll
-                        for (int b = TRSV_G - 1; b > a; --b)
-                          v -= tri[tri_index(true, a, b)] * out[b];
-                        out[a] = v * di[a]; // (rows >= m: zero coefficients, zero result)
-                      }
-                  }
-                else
-                  {
-#pragma unroll
-                    for (int a = 0; a < TRSV_G; ++a)
-                      {
-                        double v = out[a];
-#pragma unroll
-                        for (int b = 0; b < a; ++b)
-                          v -= tri[tri_index(false, a, b)] * out[b];
-                        out[a] = v;
-                      }
-                  }
-                if (lane < m)
-                  {
-                    double v = out[0];
-#pragma unroll
-                    for (int a = 1; a < TRSV_G; ++a)
-                      if (lane == a)
-                        v = out[a];
-                    st_result(x + r0 + lane, v);
-                    if (trace) // debugging aid (glsns_ilu_apply_trace): when was the row published
-                      {
-                        unsigned long long tns;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-                        trace[r0 + lane] = tns;
-                      }
-                  }
-                // shift the solved rows into the register window: distance d of the
-                // next group of the chain is m-1-a (lower sweep) or a (upper sweep)
-                {
-                  const int    d  = lane & 15;
-                  const double up = __shfl_up_sync(0xffffffffu, win, m, 16);
-                  double       nv = up;
-#pragma unroll
-                  for (int a = 0; a < TRSV_G; ++a)
-                    if (a < m && d == (UPPER ? a : m - 1 - a))
-                      nv = out[a];
-                  win = nv;
-                }
-              }
-            __syncwarp(); // every lane is done with the slot before it is refilled
-            TS_TICK(2)
-            if (lane == 0 && n_iss < n_items)
-              {
-                const unsigned bytes = 16u * (unsigned)h.w; // size of the item NSLOT ahead
-                mbar_expect_tx(bars + slotB, bytes);
-                bulk_load(ring + (size_t)slotB * TS_SLOT, src, bytes, bars + slotB, policy);
-                src += bytes;
-                ++n_iss;
-              }
-            slotB = slotB + 1 == NSLOT ? 0 : slotB + 1;
-          }
-        TS_TICK(3)
-        // ================= R(it-2) =================
-        if (it >= 2 && it <= n_items + 1)
-          {
-            const unsigned char *S     = ring + (size_t)slotR * TS_SLOT;
+            const unsigned char *S     = ring + (size_t)slotR * TS_HSLOT;
             const int4           h     = *reinterpret_cast<const int4 *>(S);
             const int            flags = h.y, m = flags & 7, cp = pad4(flags >> 16);
-            const bool           lastR = flags & IT_LAST;
-            const double        *sval  = reinterpret_cast<const double *>(
-              S + (lastR ? TS_OFF_COL1 : TS_OFF_COL0) + 4 * cp);
-            long long spins    = 0;
+            const double        *sval  = reinterpret_cast<const double *>(S + TS_OFF_COL0 + 4 * cp);
+            long long            spins = 0;
             for (;;)
               {
 #pragma unroll
@@ -484,24 +562,10 @@ namespace glsns
                     break;
                   }
               }
-            TS_TICK(4)
-            if (lastR)
+            if (flags & IT_LAST)
               {
-                // the group is complete: add the coupling to the chain rows in registers
-                // (all solved by now: their B stages ran at or before this step), fold
-                // in the right-hand side, total over the warp
-                const int     d = lane & 15, hh = lane >> 4;
-                const double *fw = reinterpret_cast<const double *>(S + TS_OFF_FWD);
-                const int     gap = (flags >> 4) & 15;
-                if (gap) // diagonal-only rows between the predecessor and this group
-                  win = __shfl_up_sync(0xffffffffu, win, gap, 16);
-                if ((unsigned)h.z & (1u << d))
-                  {
-#pragma unroll
-                    for (int a = 0; a < TRSV_G; ++a)
-                      if ((a & 1) == hh && a < m)
-                        acc[a] += fw[a * TS_WIN + d] * win;
-                  }
+                // the group is complete: fold in the right-hand side, total over the
+                // warp, post in the mailbox once the solver has freed the entry
 #pragma unroll
                 for (int a = 0; a < TRSV_G; ++a)
                   if (lane == a && a < m)
@@ -511,31 +575,54 @@ namespace glsns
 #pragma unroll
                   for (int a = 0; a < TRSV_G; ++a)
                     acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+                const int mb = (int)(seq & (TS_MBOX - 1));
+                volatile unsigned long long *mv =
+                  reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4);
+                spins = 0;
+                while (!__all_sync(0xffffffffu, mv[lane & 3] == SENTINEL)) // until the solver has emptied it
+                  if ((++spins & 4095) == 0 &&
+                      (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
+                    {
+                      atomicExch(&counters[1], 2);
+                      break;
+                    }
+                if (lane < TRSV_G)
+                  {
+                    double v = acc[0];
+#pragma unroll
+                    for (int a = 1; a < TRSV_G; ++a)
+                      if (lane == a)
+                        v = acc[a];
+                    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+                    if (b == SENTINEL)
+                      b = 0x7FF8000000000000ull;
+                    mv[lane] = b;
+                  }
 #pragma unroll
                 for (int a = 0; a < TRSV_G; ++a)
-                  {
-                    accB[a] = acc[a];
-                    acc[a]  = 0;
-                  }
+                  acc[a] = 0;
+                seq += K;
               }
-            slotR = slotR + 1 == NSLOT ? 0 : slotR + 1;
+            __syncwarp(); // every lane is done with the slot before it is refilled
+            if (lane == 0 && n_iss < n_items)
+              {
+                const unsigned bytes = 16u * (unsigned)h.w; // size of the item TS_NSH ahead
+                mbar_expect_tx(bars + slotR, bytes);
+                bulk_load(ring + (size_t)slotR * TS_HSLOT, src, bytes, bars + slotR, policy);
+                src += bytes;
+                ++n_iss;
+              }
+            slotR = slotR + 1 == TS_NSH ? 0 : slotR + 1;
           }
       };
-      for (int64_t it = 0; it < n_items + 3; it += 3)
+      for (int64_t it = 0; it < n_items + 2; it += 3)
         {
           step(std::integral_constant<int, 0>(), it);
-          if (it + 1 < n_items + 3)
+          if (it + 1 < n_items + 2)
             step(std::integral_constant<int, 1>(), it + 1);
-          if (it + 2 < n_items + 3)
+          if (it + 2 < n_items + 2)
             step(std::integral_constant<int, 2>(), it + 2);
         }
-      if (trace && lane == 0 && (w + 1) * 8 <= trace_n)
-        { // cycles in: mbarrier wait, gather issue, B, ring refill, R, hand-over(+loop); items
-          for (int k = 0; k < 6; ++k)
-            trace[2 * trace_n + w * 8 + k] = (unsigned long long)tstage[k];
-          trace[2 * trace_n + w * 8 + 6] = (unsigned long long)n_items;
-        }
-#undef TS_TICK
     }
 
     __global__ void __launch_bounds__(256)
@@ -549,23 +636,28 @@ namespace glsns
 
     struct TrsvConfig
     {
-      int warps = 6, nslot = 7;
+      int teams = 3, helpers = 3; // per SM
     };
+
+    size_t
+    team_smem_bytes(int helpers)
+    {
+      return (size_t)helpers * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SSLOT + TS_TEAM_AREA;
+    }
 
     TrsvConfig
     trsv_config()
     {
       static TrsvConfig c = [] {
         TrsvConfig t;
-        if (getenv("GLSNS_TRSV_WARPS"))
-          t.warps = atoi(getenv("GLSNS_TRSV_WARPS"));
-        if (getenv("GLSNS_TRSV_NSLOT"))
-          t.nslot = atoi(getenv("GLSNS_TRSV_NSLOT"));
-        t.warps = std::max(1, std::min(8, t.warps));
-        if (t.nslot < 5 || t.nslot > TS_MAX_SLOTS)
-          t.nslot = 7;
-        while ((size_t)t.warps * (t.nslot * (TS_SLOT + 8)) > (size_t)TS_SMEM_MAX)
-          --t.warps;
+        if (getenv("GLSNS_TRSV_TEAMS"))
+          t.teams = atoi(getenv("GLSNS_TRSV_TEAMS"));
+        if (getenv("GLSNS_TRSV_HELPERS"))
+          t.helpers = atoi(getenv("GLSNS_TRSV_HELPERS"));
+        t.helpers = std::max(1, std::min(4, t.helpers));
+        t.teams   = std::max(1, std::min(16 / (t.helpers + 1), t.teams));
+        while (t.teams > 1 && t.teams * team_smem_bytes(t.helpers) > (size_t)TS_SMEM_MAX)
+          --t.teams;
         return t;
       }();
       return c;
@@ -573,28 +665,21 @@ namespace glsns
 
     template <bool UPPER>
     glsns_status
-    launch_chain(glsns_context *ctx, const TrsvWarpDir *dir, const unsigned char *stream,
-                 const double *rhs, double *x, unsigned long long *trace)
+    launch_team(glsns_context *ctx, const TrsvWarpDir *dir, const unsigned char *stream,
+                const double *rhs, double *x, unsigned long long *trace)
     {
       const TrsvConfig cfg  = trsv_config();
-      const size_t     smem = (size_t)cfg.warps * cfg.nslot * (TS_SLOT + 8);
-      void (*kern)(const TrsvWarpDir *, const unsigned char *, const double *, double *, int *,
-                   unsigned long long *, const int64_t) = nullptr;
-      switch (cfg.nslot)
-        {
-          case 5: kern = trsv_chain_kernel<UPPER, 5>; break;
-          case 6: kern = trsv_chain_kernel<UPPER, 6>; break;
-          case 7: kern = trsv_chain_kernel<UPPER, 7>; break;
-          case 8: kern = trsv_chain_kernel<UPPER, 8>; break;
-          default: kern = trsv_chain_kernel<UPPER, 9>; break;
-        }
+      const size_t     smem = cfg.teams * team_smem_bytes(cfg.helpers);
+      auto             kern = trsv_team_kernel<UPPER>;
       GLSNS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
       int  *counters = ctx->counters.p;
-      void *args[]   = {(void *)&dir,      (void *)&stream, (void *)&rhs,         (void *)&x,
-                        (void *)&counters, (void *)&trace,  (void *)&ctx->n_owned};
+      int   K        = cfg.helpers;
+      void *args[]   = {(void *)&dir,      (void *)&stream, (void *)&rhs,          (void *)&x,
+                        (void *)&counters, (void *)&trace,  (void *)&ctx->n_owned, (void *)&K};
       GLSNS_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kern, dim3(ctx->trsv_grid),
-                                                  dim3(cfg.warps * 32), args, smem, ctx->stream));
+                                                  dim3(cfg.teams * (cfg.helpers + 1) * 32), args,
+                                                  smem, ctx->stream));
       ctx->kernel_launches++;
       return GLSNS_OK;
     }
@@ -644,7 +729,8 @@ namespace glsns
 
     const TrsvConfig cfg = trsv_config();
     ctx->trsv_grid       = ctx->n_sm;
-    const int64_t NW     = (int64_t)ctx->trsv_grid * cfg.warps;
+    const int64_t NW     = (int64_t)ctx->trsv_grid * cfg.teams; // teams: one chain list each
+    const int     K      = cfg.helpers;
 
     std::vector<int32_t> glev(ng), fmask(ng), gapv(ng), cnt(ng), e_off(ng), order(ng), warp_of(ng);
     std::vector<uint8_t> link(ng), has_succ(ng);
@@ -723,7 +809,6 @@ namespace glsns
       // a chain head takes the warp that has been free the longest
       std::vector<int32_t> last_of(NW, -1), chain_edge(NW, 0);
       std::vector<uint8_t> live(NW, 0), pooled(NW, 1);
-      std::vector<int64_t> n_it(NW + 1, 0);
       std::deque<int32_t>  pool;
       for (int64_t w = 0; w < NW; ++w)
         pool.push_back((int32_t)w);
@@ -788,35 +873,56 @@ namespace glsns
           warp_of[g] = w;
           last_of[w] = g;
           live[w]    = has_succ[g];
-          n_it[w + 1] += std::max<int64_t>(1, (cnt[g] + TS_CH - 1) / TS_CH);
           if (!live[w] && !pooled[w])
             {
               pool.push_back(w);
               pooled[w] = 1;
             }
         }
-      for (int64_t w = 0; w < NW; ++w)
+      // item lists: per team one solver list (one item per group) and K helper lists
+      // (the groups round-robin, <= TS_CH entries per item)
+      const int64_t        NWARP = NW * (K + 1);
+      std::vector<int64_t> n_it(NWARP + 1, 0), team_cnt(NW, 0);
+      std::vector<int32_t> seq_in_team(ng);
+      for (int64_t t = 0; t < ng; ++t)
+        {
+          const int32_t g  = order[t];
+          const int64_t tm = warp_of[g];
+          const int64_t j  = team_cnt[tm]++;
+          seq_in_team[g]   = (int32_t)j;
+          n_it[tm * (K + 1) + 0 + 1] += 1;
+          n_it[tm * (K + 1) + 1 + (j % K) + 1] += std::max<int64_t>(1, (cnt[g] + TS_CH - 1) / TS_CH);
+        }
+      for (int64_t w = 0; w < NWARP; ++w)
         n_it[w + 1] += n_it[w];
-      std::vector<TrsvItem> items((size_t)n_it[NW]);
+      std::vector<TrsvItem> items((size_t)n_it[NWARP]);
       std::vector<int64_t>  fill(n_it.begin(), n_it.end() - 1);
       for (int64_t t = 0; t < ng; ++t)
         {
           const int32_t g = order[t];
           const int64_t i = grp_ptr[g];
           const int32_t m = grp_m[g], len = (int32_t)(rowptr[i + 1] - rowptr[i]);
+          const int64_t tm = warp_of[g], j = seq_in_team[g];
+          {
+            TrsvItem &it = items[(size_t)fill[tm * (K + 1)]++];
+            it.rs0 = rowptr[i], it.r0 = (int32_t)i, it.len = len, it.e_off = 0;
+            it.flags = m | IT_SOLVER;
+            it.nlow  = (int32_t)(diag[i] - rowptr[i]);
+            it.fmask = fmask[g];
+          }
           const int32_t nchunk = std::max(1, (cnt[g] + TS_CH - 1) / TS_CH);
           for (int32_t c = 0; c < nchunk; ++c)
             {
-              TrsvItem  &it   = items[(size_t)fill[warp_of[g]]++];
+              TrsvItem  &it   = items[(size_t)fill[tm * (K + 1) + 1 + (j % K)]++];
               const int  cntc = std::max(0, std::min(TS_CH, cnt[g] - c * TS_CH));
               const bool last = c == nchunk - 1;
               it.rs0   = rowptr[i];
               it.r0    = (int32_t)i;
               it.len   = len;
               it.e_off = e_off[g] + c * TS_CH;
-              it.flags = m | (last ? IT_LAST | (gapv[g] << 4) : 0) | (cntc << 16);
+              it.flags = m | (last ? IT_LAST : 0) | (cntc << 16);
               it.nlow  = (int32_t)(diag[i] - rowptr[i]);
-              it.fmask = last ? fmask[g] : 0;
+              it.fmask = 0;
             }
         }
       std::vector<int32_t> &row_warp = upper ? ctx->trsv_row_warp_u : ctx->trsv_row_warp_l;
@@ -825,12 +931,12 @@ namespace glsns
         for (int32_t a = 0; a < grp_m[g]; ++a)
           row_warp[grp_ptr[g] + a] = warp_of[g] | (fmask[g] ? 1 << 30 : 0);
       // stream layout: the blobs of one warp back to back, warps one after another
-      const int64_t        nit = n_it[NW];
+      const int64_t        nit = n_it[NWARP];
       std::vector<int64_t> blob_off((size_t)nit);
       std::vector<int32_t> next16((size_t)nit, 0);
-      std::vector<TrsvWarpDir> dirv((size_t)NW);
+      std::vector<TrsvWarpDir> dirv((size_t)NWARP);
       int64_t              off = 0;
-      for (int64_t w = 0; w < NW; ++w)
+      for (int64_t w = 0; w < NWARP; ++w)
         {
           TrsvWarpDir &D = dirv[w];
           memset(&D, 0, sizeof(D));
@@ -842,10 +948,10 @@ namespace glsns
               blob_off[(size_t)k] = off;
               off += 16 * (int64_t)b16;
               const int64_t j = k - n_it[w];
-              if (j < cfg.nslot)
+              if (j < TS_NSH)
                 D.first16[j] = b16;
               else
-                next16[(size_t)(k - cfg.nslot)] = b16;
+                next16[(size_t)(k - TS_NSH)] = b16; // (helper lists; the solver's blobs have one size)
             }
         }
       sw.n_items      = nit;
@@ -920,9 +1026,9 @@ namespace glsns
       }
     if (ctx->n_groups)
       {
-        GLSNS_TRY(launch_chain<false>(ctx, reinterpret_cast<const TrsvWarpDir *>(ctx->trsv_l.dir.p),
+        GLSNS_TRY(launch_team<false>(ctx, reinterpret_cast<const TrsvWarpDir *>(ctx->trsv_l.dir.p),
                                       ctx->trsv_l.stream.p, r, ctx->ytmp.p, trace));
-        GLSNS_TRY(launch_chain<true>(ctx, reinterpret_cast<const TrsvWarpDir *>(ctx->trsv_u.dir.p),
+        GLSNS_TRY(launch_team<true>(ctx, reinterpret_cast<const TrsvWarpDir *>(ctx->trsv_u.dir.p),
                                      ctx->trsv_u.stream.p, ctx->ytmp.p, z,
                                     trace ? trace + n : nullptr));
       }

@@ -72,13 +72,11 @@ for name, t, w, upper in (("lower", tl, wl, False), ("upper", tu, wu, True)):
     out[name]["critical_path"] = {"same_warp_hops": hops_same, "same_warp_us": time_same / 1e3,
                                   "other_warp_hops": hops_other, "other_warp_us": time_other / 1e3}
 for name, pl in zip(("lower", "upper"), hp.last_trace_polls):
-    nw = min(len(pl) // 8, 148 * 8)
+    nw = min(len(pl) // 8, 148 * 4)
     st = pl[:nw * 8].reshape(nw, 8).astype(np.float64)
     busy = st[st[:, 6] > 0]
-    tot = busy[:, :6].sum(axis=0)
-    out[name]["stage_cycles_per_item_[mbar_wait,gather,B,refill,R,handover+loop]"] = [float(v) for v in tot / busy[:, 6].sum()]
-    out[name]["stage_share"] = [float(v) for v in tot / tot.sum()]
-    # the busiest warp (most items): closest to a warp that is always on the critical path
+    tot = busy[:, :5].sum(axis=0)
+    out[name]["solver_cycles_per_group_[ring_wait,window,mailbox_wait,triangle_publish,release_refill]"] = [float(v) for v in tot / busy[:, 6].sum()]
     k = int(np.argmax(st[:, 6]))
-    out[name]["busiest_warp_items_and_cycles_per_item"] = [float(st[k, 6])] + [float(v / st[k, 6]) for v in st[k, :6]]
+    out[name]["busiest_solver_groups_and_cycles_per_group"] = [float(st[k, 6])] + [float(v / st[k, 6]) for v in st[k, :5]]
 print(json.dumps(out, indent=1))
