@@ -36,6 +36,7 @@
 //   * The solution vector itself carries readiness: it is pre-filled with an
 //     all-ones NaN pattern and a consumer re-reads an entry until it has been
 //     overwritten (no flags, no fences).
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -74,6 +75,9 @@ namespace glsns
     // bits 16.. entries of a helper item
     constexpr int IT_LAST   = 1 << 8;
     constexpr int IT_SOLVER = 1 << 9;
+    constexpr int IT_GUEST  = 1 << 10; // solver item of a group that runs through no window
+    // bits 12-13 of a solver item: which of the team's windows its chain runs through
+    constexpr int TS_NWIN   = 4;
 
     __host__ __device__ inline int
     pad4(int v)
@@ -265,8 +269,8 @@ namespace glsns
     constexpr int TS_MBOX = 8;  // mailbox entries per team
     constexpr int TS_HSLOT = TS_OFF_COL0 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 4624
     constexpr int TS_SSLOT = TS_OFF_COL1;                                   // 608
-    constexpr int TS_TEAM_AREA = 1024; // window 128 | mailbox 256 | (48 spare) | barriers
-    static_assert(TS_MBOX == 8 && 128 + 32 * TS_MBOX + 4 * TS_MBOX + 16 + 8 * (4 * TS_NSH + TS_NSS) <= TS_TEAM_AREA,
+    constexpr int TS_TEAM_AREA = 1024; // windows 4 x 128 | mailbox 256 | solved counter 16 | barriers
+    static_assert(TS_MBOX == 8 && TS_NWIN == 4 && 128 * TS_NWIN + 32 * TS_MBOX + 16 + 8 * (4 * TS_NSH + TS_NSS) <= TS_TEAM_AREA,
                   "team area");
 
     template <bool UPPER>
@@ -285,9 +289,11 @@ namespace glsns
       const size_t  team_smem = (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SSLOT + TS_TEAM_AREA;
       unsigned char *T0   = smem_all + (size_t)team_in_cta * team_smem;
       unsigned char *area = T0 + (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SSLOT;
-      double        *wsm  = reinterpret_cast<double *>(area);            // [16] chain window by row & 15
-      double        *mbox = reinterpret_cast<double *>(area + 128);      // [TS_MBOX][4], all-ones = empty
-      unsigned long long *bars_all = reinterpret_cast<unsigned long long *>(area + 128 + 36 * TS_MBOX + 16);
+      double        *wsm_all = reinterpret_cast<double *>(area);         // [TS_NWIN][16] chain windows by row & 15
+      double        *mbox = reinterpret_cast<double *>(area + 128 * TS_NWIN); // [TS_MBOX][4], all-ones = empty
+      volatile int  *done = reinterpret_cast<volatile int *>(area + 128 * TS_NWIN + 32 * TS_MBOX); // groups solved
+      unsigned long long *bars_all =
+        reinterpret_cast<unsigned long long *>(area + 128 * TS_NWIN + 32 * TS_MBOX + 16);
       const TrsvWarpDir  *D        = dir + team * (K + 1) + role;
       const int64_t       n_items  = D->n_items;
       unsigned long long  policy;
@@ -296,9 +302,10 @@ namespace glsns
       // visible to the helpers by the one CTA barrier of the kernel
       if (role == 0)
         {
-          if (lane < 16)
-            wsm[lane] = 0.0;
+          wsm_all[lane] = wsm_all[lane + 32] = 0.0; // TS_NWIN * 16 = 64 entries
           reinterpret_cast<unsigned long long *>(mbox)[lane] = SENTINEL; // TS_MBOX * 4 = 32 entries, all empty
+          if (lane == 0)
+            *done = 0;
         }
       __syncthreads();
       if (n_items == 0)
@@ -344,6 +351,7 @@ namespace glsns
               const unsigned char *S  = ring + (size_t)slot * TS_SSLOT;
               const int4           h  = *reinterpret_cast<const int4 *>(S);
               const int            r0 = h.x, m = h.y & 7;
+              double              *wsm = wsm_all + 16 * ((h.y >> 12) & (TS_NWIN - 1));
               const double        *di = reinterpret_cast<const double *>(S + TS_OFF_DINV);
               const double        *tri = reinterpret_cast<const double *>(S + TS_OFF_TRI);
               const double2       *fw  = reinterpret_cast<const double2 *>(S + TS_OFF_FWD);
@@ -388,8 +396,10 @@ namespace glsns
                 out[a] = -(reinterpret_cast<volatile double *>(mbox)[mb * 4 + a] +
                            ((s4[a][0] + s4[a][1]) + (s4[a][2] + s4[a][3])));
               __syncwarp();
-              if (lane < TRSV_G) // hand the entry back
+              if (lane < TRSV_G) // hand the entry back: empty it, then let group g + TS_MBOX in
                 reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4)[lane] = SENTINEL;
+              if (lane == 0)
+                *done = (int)g + 1;
               if (UPPER)
                 {
 #pragma unroll
@@ -422,7 +432,8 @@ namespace glsns
                     if (lane == a)
                       v = out[a];
                   st_result(x + r0 + lane, v);
-                  wsm[(r0 + lane) & 15] = v;
+                  if (!(h.y & IT_GUEST))
+                    wsm[(r0 + lane) & 15] = v;
                   if (trace) // debugging aid (glsns_ilu_apply_trace): when was the row published
                     {
                       unsigned long long tns;
@@ -579,7 +590,8 @@ namespace glsns
                 volatile unsigned long long *mv =
                   reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4);
                 spins = 0;
-                while (!__all_sync(0xffffffffu, mv[lane & 3] == SENTINEL)) // until the solver has emptied it
+                // the entry is this group's once the solver is within TS_MBOX groups of it
+                while ((int64_t)*done + TS_MBOX <= seq)
                   if ((++spins & 4095) == 0 &&
                       (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
                     {
@@ -730,10 +742,12 @@ namespace glsns
     const TrsvConfig cfg = trsv_config();
     ctx->trsv_grid       = ctx->n_sm;
     const int64_t NW     = (int64_t)ctx->trsv_grid * cfg.teams; // teams: one chain list each
+    const int32_t max_level_gap = getenv("GLSNS_TRSV_GAP") ? atoi(getenv("GLSNS_TRSV_GAP")) : 2;
     const int     K      = cfg.helpers;
 
-    std::vector<int32_t> glev(ng), fmask(ng), gapv(ng), cnt(ng), e_off(ng), order(ng), warp_of(ng);
-    std::vector<uint8_t> link(ng), has_succ(ng);
+    std::vector<int32_t> glev(ng), fmask(ng), gapv(ng), cnt(ng), e_off(ng), order(ng), warp_of(ng),
+      slot_of(ng);
+    std::vector<uint8_t> link(ng), has_succ(ng), is_primary(ng);
 
     // One sweep: levels, chain links, level-ordered schedule on NW warps, item lists.
     auto schedule = [&](const bool upper, TrsvSweep &sw, int32_t &n_levels) -> glsns_status {
@@ -788,6 +802,10 @@ namespace glsns
                         }
                 }
             }
+          // a predecessor solved long before this group needs it is no link: its rows
+          // reach the group through L2 in time, and the team is free for another chain
+          if (link[g] && l - glev[p] > max_level_gap)
+            link[g] = 0;
           if (link[g])
             has_succ[p] = 1;
         }
@@ -807,34 +825,62 @@ namespace glsns
       }
       // list scheduling: a chained group follows its predecessor on the same warp;
       // a chain head takes the warp that has been free the longest
-      std::vector<int32_t> last_of(NW, -1), chain_edge(NW, 0);
-      std::vector<uint8_t> live(NW, 0), pooled(NW, 1);
-      std::deque<int32_t>  pool;
+      // Every team has TS_NWIN chain slots (one window each).  A chain head takes a slot
+      // of the least loaded team: `bucket[k]` lists teams believed to run k chains
+      // (entries are validated when popped).
+      std::vector<int32_t> last_of(NW * TS_NWIN, -1), chain_edge(NW * TS_NWIN, 0);
+      std::vector<uint8_t> n_live(NW, 0);
+      std::deque<int32_t>  bucket[TS_NWIN];
       for (int64_t w = 0; w < NW; ++w)
-        pool.push_back((int32_t)w);
-      int64_t rr = 0;
+        bucket[0].push_back((int32_t)w);
+      auto take_slot = [&]() -> int32_t { // team * TS_NWIN + slot, or -1
+        for (int k = 0; k < TS_NWIN; ++k)
+          while (!bucket[k].empty())
+            {
+              const int32_t w = bucket[k].front();
+              bucket[k].pop_front();
+              if (n_live[w] != k)
+                continue; // stale entry
+              for (int sl = 0; sl < TS_NWIN; ++sl)
+                if (last_of[(int64_t)w * TS_NWIN + sl] == -1)
+                  {
+                    ++n_live[w];
+                    if (n_live[w] < TS_NWIN)
+                      bucket[n_live[w]].push_back(w);
+                    return w * TS_NWIN + sl;
+                  }
+            }
+        return -1;
+      };
+      int64_t rr = 0, n_heads = 0, n_steals = 0, n_interrupted = 0;
       for (int64_t t = 0; t < ng; ++t)
         {
           const int32_t g = order[t];
           const int64_t p = upper ? (int64_t)g + 1 : (int64_t)g - 1;
           const int32_t r0 = grp_ptr[g], m = grp_m[g];
-          int32_t       w;
-          bool          chained = false;
-          if (link[g])
+          // A chain runs through one window of its team.  When every window of every
+          // team is taken, a group is placed on a busy team as a GUEST: solved in list
+          // order without touching any window, so the chains there keep their forwarding.
+          int32_t ws; // team * TS_NWIN + slot
+          bool    chained = false, primary = true;
+          if (link[g] && is_primary[p] && last_of[slot_of[p]] == p)
             {
-              w       = warp_of[p];
-              chained = last_of[w] == p; // else: interrupted (more chains than warps)
+              ws      = slot_of[p];
+              chained = true;
             }
-          else if (!pool.empty())
-            {
-              w = pool.front();
-              pool.pop_front();
-              pooled[w] = 0;
-            }
+          else if ((ws = take_slot()) >= 0)
+            n_interrupted += link[g]; // chain head, or the successor of a guest: a fresh window
           else
-            w = (int32_t)(rr++ % NW);
-          if (!chained) // a new chain starts here: first row (lower) / end row (upper)
-            chain_edge[w] = upper ? r0 + m : r0;
+            {
+              ws      = (link[g] ? warp_of[p] : (int32_t)(rr++ % NW)) * TS_NWIN;
+              primary = false;
+              ++n_steals;
+            }
+          const int32_t w = ws / TS_NWIN;
+          n_heads += !link[g];
+          is_primary[g] = primary;
+          if (!chained && primary) // a new chain starts here: first row (lower) / end row (upper)
+            chain_edge[ws] = upper ? r0 + m : r0;
           // entries that couple to the rows of this chain still held in registers: the
           // run next to the in-group block, at most TS_WIN rows away
           int64_t kb, ke;
@@ -847,7 +893,7 @@ namespace glsns
                 for (int64_t k = ke - 1; k >= kb; --k)
                   {
                     const int32_t d = r0 - 1 - col[k];
-                    if (d >= TS_WIN || col[k] < chain_edge[w] || grp_of[col[k]] < 0)
+                    if (d >= TS_WIN || col[k] < chain_edge[ws] || grp_of[col[k]] < 0)
                       break;
                     fm |= 1u << d;
                     ++nf;
@@ -856,7 +902,7 @@ namespace glsns
                 for (int64_t k = kb; k < ke; ++k)
                   {
                     const int32_t d = col[k] - (r0 + m);
-                    if (d >= TS_WIN || col[k] >= chain_edge[w] || grp_of[col[k]] < 0)
+                    if (d >= TS_WIN || col[k] >= chain_edge[ws] || grp_of[col[k]] < 0)
                       break;
                     fm |= 1u << d;
                     ++nf;
@@ -871,14 +917,25 @@ namespace glsns
           e_off[g] = (int32_t)((upper ? kb + nf : kb) - rowptr[grp_ptr[g]]);
           cnt[g]   = (int32_t)(ke - kb - nf);
           warp_of[g] = w;
-          last_of[w] = g;
-          live[w]    = has_succ[g];
-          if (!live[w] && !pooled[w])
+          slot_of[g] = ws;
+          if (primary)
             {
-              pool.push_back(w);
-              pooled[w] = 1;
+              if (has_succ[g])
+                last_of[ws] = g; // (last group of the chain in this window so far)
+              else
+                { // the chain ends here: the window is free again
+                  last_of[ws] = -1;
+                  --n_live[w];
+                  bucket[n_live[w]].push_back(w);
+                }
             }
         }
+      if (getenv("GLSNS_TRSV_DEBUG"))
+        fprintf(stderr,
+                "trsv_analyse %s: %lld groups, %d levels, %lld teams, %lld chain heads, %lld taken "
+                "as guests on busy teams, %lld chains restarted\n",
+                upper ? "upper" : "lower", (long long)ng, nlev + 1, (long long)NW, (long long)n_heads,
+                (long long)n_steals, (long long)n_interrupted);
       // item lists: per team one solver list (one item per group) and K helper lists
       // (the groups round-robin, <= TS_CH entries per item)
       const int64_t        NWARP = NW * (K + 1);
@@ -906,7 +963,7 @@ namespace glsns
           {
             TrsvItem &it = items[(size_t)fill[tm * (K + 1)]++];
             it.rs0 = rowptr[i], it.r0 = (int32_t)i, it.len = len, it.e_off = 0;
-            it.flags = m | IT_SOLVER;
+            it.flags = m | IT_SOLVER | (is_primary[g] ? 0 : IT_GUEST) | ((slot_of[g] % TS_NWIN) << 12);
             it.nlow  = (int32_t)(diag[i] - rowptr[i]);
             it.fmask = fmask[g];
           }
