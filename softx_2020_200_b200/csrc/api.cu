@@ -247,6 +247,7 @@ glsns_destroy(glsns_context *ctx)
   ctx->trsv_u.release();
   ctx->dinv.release();
   ctx->diag_rows.release();
+  ctx->fgroups.release();
   ctx->rowptr.release();
   ctx->diag_pos.release();
   ctx->constrained.release();

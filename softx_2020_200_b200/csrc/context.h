@@ -111,6 +111,7 @@ struct glsns_context
   glsns::DevBuf<int64_t> rowptr, diag_pos;
   glsns::DevBuf<double>  inv_jac, det_jac, measure, q_points, force, cvalues;
   glsns::DevBuf<uint8_t> constrained;
+  glsns::DevBuf<int2>    fgroups; // (first row, rows) of the row groups, by lower-sweep level
   std::vector<int32_t>   color_ptr;
   int32_t                levels_l = 0, levels_u = 0, levels_rows = 0, n_groups = 0;
   int32_t                max_row_len = 0, n_diag_rows = 0;

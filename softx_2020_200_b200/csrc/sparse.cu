@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "context.h"
 
@@ -212,6 +213,261 @@ namespace glsns
         }
     }
 
+
+    // IKJ ILU(0) for a GROUP of up to 4 consecutive rows with identical column
+    // patterns (the dim+1 dofs of a mesh node; same groups as the triangular solves,
+    // trsv.cu).  The arithmetic per row is exactly the scalar IKJ elimination (pivots
+    // ascending, l = a_ik / u_kk, a_ij -= l u_kj on the pattern) — the grouping only
+    // shares the work around it: one warp stages the group's rows in shared memory,
+    // waits once per pivot row instead of once per (row, pivot), reads each pivot row
+    // once for all rows of the group and locates each of its entries in the common
+    // pattern with ONE hash look-up (column -> position, built in shared memory when
+    // the group is staged).  Four pivot rows are in flight: the first 128 entries of
+    // row kk+3 are requested while row kk is applied.  Rows of the same group eliminate
+    // each other from shared memory at the end.  Measured (B200, 3D Q2-Q2, 64^3 cells):
+    // 0.9 s -> the kernel is bound by the ~410 GB of pivot-row reads it issues as
+    // 1.5 KB pieces (each group re-reads the ~128 pivot rows its neighbours also
+    // read); sharing pivot rows between the consecutive groups of a chain is the
+    // next step.
+    constexpr int FG_PRE   = 4; // 32-entry chunks of the next pivot row requested early
+
+    __global__ void __launch_bounds__(512, 1)
+    ilu_factor_groups_kernel(const int32_t n_groups, const int2 *__restrict__ groups,
+                             const int64_t n, const int64_t *__restrict__ rowptr,
+                             const int32_t *__restrict__ col, const int64_t *__restrict__ diag_pos,
+                             double *lu, int *row_done, const int epoch, int *counters,
+                             const int maxlen, const int hbits)
+    {
+      extern __shared__ __align__(16) unsigned char fg_smem[];
+      const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int      hsize = 1 << hbits, hmask = hsize - 1;
+      const size_t   per_warp = (size_t)maxlen * 36 + 64 + (size_t)hsize * 6;
+      unsigned char *W  = fg_smem + warp * per_warp;
+      double        *sv = reinterpret_cast<double *>(W);                    // [4][maxlen]
+      double        *l4 = reinterpret_cast<double *>(W + (size_t)maxlen * 32); // [4]
+      int32_t       *sc = reinterpret_cast<int32_t *>(W + (size_t)maxlen * 32 + 64); // [maxlen]
+      // column -> position in the group's rows: open addressing, linear probing
+      int32_t       *hkey = sc + maxlen;                                    // [hsize], -1 = empty
+      int16_t       *hpos = reinterpret_cast<int16_t *>(hkey + hsize);      // [hsize]
+      auto hash = [&](int32_t j) { return (int)(((unsigned)j * 2654435761u) >> (32 - hbits)); };
+      for (;;)
+        {
+          int t = 0;
+          if (lane == 0)
+            t = atomicAdd(&counters[0], 1);
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if (t >= n_groups)
+            break;
+          const int2    g  = groups[t];
+          const int     r0 = g.x, m = g.y;
+          const int64_t rs = rowptr[r0];
+          const int     len = (int)(rowptr[r0 + 1] - rs), nl = (int)(diag_pos[r0] - rs);
+          for (int k = lane; k < hsize; k += 32)
+            hkey[k] = -1;
+          __syncwarp();
+          for (int k = lane; k < len; k += 32)
+            {
+              const int32_t j = col[rs + k];
+              sc[k]           = j;
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                if (a < m)
+                  sv[a * maxlen + k] = lu[rs + (int64_t)a * len + k];
+              int s = hash(j);
+              while (atomicCAS(hkey + s, -1, j) != -1)
+                s = (s + 1) & hmask;
+              hpos[s] = (int16_t)k;
+            }
+          __syncwarp();
+          // ---- pivot rows outside the group ----
+          // CSR extents of the pivot rows: 32 at a time, one per lane, a batch ahead
+          int64_t bkd = 0, bke = 0, nkd = 0, nke = 0; // pivots [b0, b0+32) and [b0+32, b0+64)
+          int     b0  = 0;
+          auto load_extents = [&](int first, int64_t &kd_, int64_t &ke_) {
+            if (first + lane < nl)
+              {
+                const int32_t k = sc[first + lane];
+                kd_             = diag_pos[k];
+                ke_             = rowptr[k + 1];
+              }
+          };
+          load_extents(0, bkd, bke);
+          load_extents(32, nkd, nke);
+          auto extents = [&](int kk, int64_t &kd_, int64_t &ke_) { // kk in [b0, b0+64)
+            const int64_t a = __shfl_sync(0xffffffffu, bkd, kk & 31), b = __shfl_sync(0xffffffffu, bke, kk & 31);
+            const int64_t c = __shfl_sync(0xffffffffu, nkd, kk & 31), d = __shfl_sync(0xffffffffu, nke, kk & 31);
+            kd_             = kk < b0 + 32 ? a : c;
+            ke_             = kk < b0 + 32 ? b : d;
+          };
+          // Pivot rows that are final already (nearly all of them: everything but the
+          // last few levels) are covered by ONE acquire fence; whenever a pivot row had
+          // to be waited for, the next fence covers every row found final before it.
+          int  first_unready = 0;
+          auto scan_ready    = [&]() { // advance first_unready over rows that are final; then fence
+            while (first_unready < nl)
+              {
+                const int  kk   = first_unready + lane;
+                const bool nope = kk >= nl ? false : *(volatile int *)(row_done + sc[kk]) != epoch;
+                const unsigned bal = __ballot_sync(0xffffffffu, nope);
+                if (bal)
+                  {
+                    first_unready += __ffs(bal) - 1;
+                    break;
+                  }
+                first_unready = min(nl, first_unready + 32);
+              }
+            __threadfence();
+          };
+          scan_ready();
+          // four pivot rows in flight: row kk+3 is requested while row kk is applied
+          int64_t kdS[4], keS[4];
+          double  ukkS[4];
+          int32_t cjS[4][FG_PRE];
+          double  uvS[4][FG_PRE];
+          auto fetch = [&](auto SET, int kk) {
+            constexpr int st = decltype(SET)::value;
+            if (kk >= nl)
+              return;
+            if (kk >= first_unready)
+              { // not final when last looked: wait for it
+                const int32_t k = sc[kk];
+                if (lane == 0)
+                  {
+                    long long spins = 0;
+                    while (*(volatile int *)(row_done + k) != epoch)
+                      if (++spins > SPIN_LIMIT)
+                        {
+                          atomicExch(&counters[1], 2);
+                          break;
+                        }
+                  }
+                __syncwarp();
+                first_unready = kk + 1;
+                scan_ready();
+              }
+            extents(kk, kdS[st], keS[st]);
+            ukkS[st] = __ldcg(lu + kdS[st]);
+#pragma unroll
+            for (int u = 0; u < FG_PRE; ++u)
+              {
+                const int64_t q = kdS[st] + 1 + lane + 32 * u;
+                cjS[st][u]      = q < keS[st] ? __ldg(col + q) : 0x7fffffff;
+                uvS[st][u]      = q < keS[st] ? __ldcg(lu + q) : 0.0;
+              }
+          };
+          auto apply_row = [&](auto SET, int kk) {
+            constexpr int st = decltype(SET)::value;
+            if (kk >= nl)
+              return;
+            // multipliers of the group's rows
+            if (lane < m)
+              {
+                const double l         = sv[lane * maxlen + kk] / ukkS[st];
+                sv[lane * maxlen + kk] = l;
+                l4[lane]               = l;
+              }
+            __syncwarp();
+            double lm[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              lm[a] = a < m ? l4[a] : 0.0;
+            auto apply = [&](const int32_t j, const double u) {
+              if (j >= n)
+                return; // ghost column (or past the end): outside the diagonal block
+              int s = hash(j);
+              for (;;)
+                {
+                  const int32_t key = hkey[s];
+                  if (key == j)
+                    {
+                      const int p = hpos[s];
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        if (a < m)
+                          sv[a * maxlen + p] -= lm[a] * u;
+                      return;
+                    }
+                  if (key == -1)
+                    return; // not in the pattern: ILU(0) drops the fill
+                  s = (s + 1) & hmask;
+                }
+            };
+#pragma unroll
+            for (int u = 0; u < FG_PRE; ++u)
+              apply(cjS[st][u], uvS[st][u]);
+            for (int64_t q = kdS[st] + 1 + lane + 32 * FG_PRE; q < keS[st]; q += 32)
+              apply(__ldg(col + q), __ldcg(lu + q));
+            __syncwarp();
+          };
+          auto shift_extents = [&](int kk_next_fetch) {
+            if (kk_next_fetch >= b0 + 64 - 1)
+              { // the first batch of extents is used up: shift, load the one after next
+                bkd = nkd, bke = nke;
+                b0 += 32;
+                load_extents(b0 + 32, nkd, nke);
+              }
+          };
+          fetch(std::integral_constant<int, 0>(), 0);
+          fetch(std::integral_constant<int, 1>(), 1);
+          fetch(std::integral_constant<int, 2>(), 2);
+          for (int kk = 0; kk < nl; kk += 4)
+            {
+              shift_extents(kk + 6);
+              fetch(std::integral_constant<int, 3>(), kk + 3);
+              apply_row(std::integral_constant<int, 0>(), kk);
+              fetch(std::integral_constant<int, 0>(), kk + 4);
+              apply_row(std::integral_constant<int, 1>(), kk + 1);
+              fetch(std::integral_constant<int, 1>(), kk + 5);
+              apply_row(std::integral_constant<int, 2>(), kk + 2);
+              fetch(std::integral_constant<int, 2>(), kk + 6);
+              apply_row(std::integral_constant<int, 3>(), kk + 3);
+            }
+          // ---- rows of the group eliminate each other ----
+          for (int b = 0; b + 1 < m; ++b)
+            {
+              const int pb = nl + b;
+              if (lane > b && lane < m)
+                {
+                  const double l      = sv[lane * maxlen + pb] / sv[b * maxlen + pb];
+                  sv[lane * maxlen + pb] = l;
+                  l4[lane]            = l;
+                }
+              __syncwarp();
+              for (int p = pb + 1 + lane; p < len; p += 32)
+                if (sc[p] < n)
+                  {
+                    const double ub = sv[b * maxlen + p];
+#pragma unroll
+                    for (int a = 1; a < 4; ++a)
+                      if (a > b && a < m)
+                        sv[a * maxlen + p] -= l4[a] * ub;
+                  }
+              __syncwarp();
+            }
+          for (int k = lane; k < len; k += 32)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (a < m)
+                lu[rs + (int64_t)a * len + k] = sv[a * maxlen + k];
+          if (lane < m && sv[lane * maxlen + nl + lane] == 0.0)
+            atomicExch(&counters[1], 1);
+          __syncwarp();
+          __threadfence(); // the rows, then (one fence for all of them) their flags
+          if (lane < m)
+            *(volatile int *)(row_done + r0 + lane) = epoch;
+          __syncwarp();
+        }
+    }
+
+    // flags of the rows no group covers (diagonal-only rows): final from the start
+    __global__ void __launch_bounds__(256)
+    ilu_mark_rows_kernel(const int32_t n_rows, const int32_t *__restrict__ rows, int *row_done,
+                         const int epoch)
+    {
+      const int i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i < n_rows)
+        row_done[rows[i]] = epoch;
+    }
   } // namespace
 
   glsns_status
@@ -319,15 +575,42 @@ namespace glsns
       {
         ilu_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
           n, ctx->diag_pos.p, atol, rtol, ctx->lu.p);
-        int per_sm = 0;
-        GLSNS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                          &per_sm, ilu_factor_kernel, FACTOR_WARPS * 32, 0));
-        const int grid = (int)std::min<int64_t>((n + FACTOR_WARPS - 1) / FACTOR_WARPS,
-                                                (int64_t)ctx->n_sm * std::max(per_sm, 1));
-        ilu_factor_kernel<<<grid, FACTOR_WARPS * 32, 0, ctx->stream>>>(
-          n, ctx->order_l.p, ctx->rowptr.p, ctx->col.p, ctx->diag_pos.p, ctx->lu.p,
-          ctx->row_done.p, ctx->epoch, ctx->counters.p);
-        ctx->kernel_launches += 2;
+        const int    maxlen   = (ctx->max_row_len + 3) & ~3;
+        int          hbits    = 4;
+        while ((1 << hbits) < 2 * maxlen)
+          ++hbits;
+        const size_t per_warp = (size_t)maxlen * 36 + 64 + ((size_t)6 << hbits);
+        const int    warps    = (int)std::min<size_t>(16, (size_t)(227 * 1024) / per_warp);
+        static const bool by_rows = getenv("GLSNS_ILU_BY_ROWS") != nullptr;
+        if (warps >= 2 && ctx->n_groups > 0 && !by_rows)
+          {
+            // rows of a group share one warp (the general case)
+            if (ctx->n_diag_rows)
+              ilu_mark_rows_kernel<<<(ctx->n_diag_rows + 255) / 256, 256, 0, ctx->stream>>>(
+                ctx->n_diag_rows, ctx->diag_rows.p, ctx->row_done.p, ctx->epoch);
+            const size_t smem = warps * per_warp;
+            GLSNS_CUDA(ctx, cudaFuncSetAttribute(ilu_factor_groups_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem));
+            const int grid = (int)std::min<int64_t>((ctx->n_groups + warps - 1) / warps, ctx->n_sm);
+            ilu_factor_groups_kernel<<<grid, warps * 32, smem, ctx->stream>>>(
+              ctx->n_groups, ctx->fgroups.p, n, ctx->rowptr.p, ctx->col.p, ctx->diag_pos.p,
+              ctx->lu.p, ctx->row_done.p, ctx->epoch, ctx->counters.p, maxlen, hbits);
+            ctx->kernel_launches += 3;
+          }
+        else
+          {
+            // rows too long to stage a group in shared memory: one row per warp
+            int per_sm = 0;
+            GLSNS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                              &per_sm, ilu_factor_kernel, FACTOR_WARPS * 32, 0));
+            const int grid = (int)std::min<int64_t>((n + FACTOR_WARPS - 1) / FACTOR_WARPS,
+                                                    (int64_t)ctx->n_sm * std::max(per_sm, 1));
+            ilu_factor_kernel<<<grid, FACTOR_WARPS * 32, 0, ctx->stream>>>(
+              n, ctx->order_l.p, ctx->rowptr.p, ctx->col.p, ctx->diag_pos.p, ctx->lu.p,
+              ctx->row_done.p, ctx->epoch, ctx->counters.p);
+            ctx->kernel_launches += 2;
+          }
       }
     GLSNS_CUDA(ctx, cudaGetLastError());
     GLSNS_TRY(trsv_prepare(ctx));

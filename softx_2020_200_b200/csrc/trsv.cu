@@ -823,6 +823,14 @@ namespace glsns
             order[start[glev[g]]++] = (int32_t)g;
           }
       }
+      if (!upper)
+        { // the factorisation takes the groups in the same order (sparse.cu)
+          std::vector<int2> fg((size_t)ng);
+          for (int64_t t = 0; t < ng; ++t)
+            fg[(size_t)t] = make_int2(grp_ptr[order[t]], grp_m[order[t]]);
+          GLSNS_TRY(dev_upload(ctx, ctx->fgroups, fg.data(), fg.size()));
+          GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
       // list scheduling: a chained group follows its predecessor on the same warp;
       // a chain head takes the warp that has been free the longest
       // Every team has TS_NWIN chain slots (one window each).  A chain head takes a slot

@@ -15,3 +15,4 @@ ms = hp.time_kernel("ilu_apply", reps=5)
 by = 12 * m.nnz + 40 * m.n_dofs
 print(json.dumps(dict(n=n, ndof=m.n_dofs, t_mesh=t_mesh, t_attach=t_attach, t_setup_ilu=t_ilu, levels=hp.ilu_levels(),
                       ilu_apply_ms=ms, frac=by / ms / 1e6 / 6546.2, spmv_ms=hp.time_kernel("spmv", reps=5))))
+print(json.dumps(dict(ilu_factor_ms=hp.time_kernel("ilu_factor", reps=2))))
