@@ -319,8 +319,19 @@ def run_ours(args):
               ("setup_ilu", "setup_ilu_ms"))}
     dom = "ilu_apply" if tm["trsv_ms"] >= tm["spmv_ms"] else "spmv"
     achieved = algo[dom] / (per[dom] * 1e-3) / 1e9
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    # (profiles/), only when it was taken on this very workload
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            cap = json.load(f)
+        key = "%s@n%d" % (dom, n)
+        if world == 1 and key in cap:
+            traffic = cap[key]["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                "frac": achieved / hbm, "traffic": traffic, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": algo[dom], "avg_launch_ms": per[dom],
                 "share_of_step": share[dom],
                 "spmv": {"achieved": algo["spmv"] / (per["spmv"] * 1e-3) / 1e9,

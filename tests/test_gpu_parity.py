@@ -283,6 +283,37 @@ def test_skip_newton_and_transient_through_the_cpp_mirror(oracle):
     s.close()
 
 
+@pytest.mark.parametrize("name", ["case_2d_q2q1_bdf2", "case_3d_q1q1_steady", "case_3d_q2q2_steady"])
+def test_against_committed_golden_fixtures(oracle, name):
+    """The CUDA path against tests/golden/case_*.npz (oracle outputs frozen by make_fixtures.py): the
+    oracle only rebuilds the mesh arrays here, no oracle arithmetic runs."""
+    import os
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    mesh = oracle.BoxMesh(int(fx["dim"]), int(fx["n"]), int(fx["pu"]), int(fx["pp"]))
+    assert np.array_equal(mesh.col, fx["col_idx"])
+    nu, scheme = float(fx["viscosity"]), str(fx["scheme"])
+    dts = list(fx["dts"]) or None
+    hp = hotpath_from_oracle_mesh(mesh, nu, None)
+    hp.set_vector("evaluation_point", fx["U"])
+    if fx["U1"].size:
+        hp.set_vector("solution_m1", fx["U1"])
+        hp.set_vector("solution_m2", fx["U2"])
+    hp.assemble(True, scheme, dts)
+    assert row_scaled_error(mesh, hp.get_matrix_values(), fx["matrix"]) <= TOL_ENTRY
+    b = hp.get_vector("system_rhs")
+    assert np.max(np.abs(b - fx["rhs"])) <= TOL_ENTRY * np.max(np.abs(fx["rhs"]))
+    assert np.max(np.abs(hp.spmv(fx["x"]) - fx["spmv"])) <= 1e-13 * np.max(np.abs(fx["spmv"]))
+    hp.setup_ilu(0, 1e-8, 1.0)
+    assert row_scaled_error(mesh, hp.get_ilu_values(), fx["ilu"]) <= 1e-11
+    z = hp.ilu_apply(fx["x"])
+    assert np.max(np.abs(z - fx["ilu_apply"])) <= 1e-10 * np.max(np.abs(fx["ilu_apply"]))
+    dx, info = hp.solve_linear_system(relative_residual=1e-6, minimum_residual=1e-12,
+                                      max_iterations=2000, ilu_atol=1e-8)
+    assert abs(info["iterations"] - int(fx["gmres_iterations"])) <= 2
+    assert info["true_residual"] <= info["tolerance"] * 1.0000001
+    hp.close()
+
+
 def test_two_gpu_newton_step_matches_block_jacobi_oracle():
     """N = 2 ranks over NCCL (skipped on a 1-GPU box; run with `gpurun --gpus 2`)."""
     import subprocess

@@ -2,10 +2,17 @@
 
 The expected numbers below are copied from the reference's checked-in test outputs; the inputs
 (mesh, forcing, solver settings) are those of the corresponding reference test."""
+import json
+import os
+
 import numpy as np
 import pytest
 
 from tests import mms
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+with open(os.path.join(GOLDEN_DIR, "reference_golden.json")) as _f:
+    REF = json.load(_f)      # the reference's own numbers, file:line in each entry's "source"
 
 
 def test_bdf_coefficients_bdf_01_output(oracle):
@@ -27,12 +34,12 @@ def test_restart_01_output(oracle):
     pr = oracle.scheme_params("steady", [1.0], 1.0)
     log = []
     U, it, res = oracle.newton_solve(m, np.zeros(m.ndof), pr, f, log=log)
-    assert [k for k, _ in log] == [8, 6, 10]
-    golden = [0.00204885, 9.85227e-05, 3.32384e-08]
+    assert [k for k, _ in log] == REF["restart_01"]["gmres_iterations"] == [8, 6, 10]
+    golden = REF["restart_01"]["true_residuals"]
     for (_, r), g in zip(log, golden):
         assert float("%.6g" % r) == g          # every printed digit
     err_u, _ = oracle.l2_error(m, U, mms.exact_2d)
-    assert float("%.6g" % err_u) == 0.0343628
+    assert float("%.6g" % err_u) == REF["restart_01"]["l2_error_velocity"] == 0.0343628
     # "Error after zeroing the solution: 0.612372" = ||u_exact||
     assert float("%.6g" % oracle.l2_error(m, np.zeros(m.ndof), mms.exact_2d)[0]) == 0.612372
 
@@ -70,3 +77,22 @@ def test_mms2d_gls_output(oracle, n, ndof, eu, ep):
     err_u, err_p = oracle.l2_error(m, U, mms.exact_mms2d)
     assert float("%.5g" % err_u) == eu
     assert float("%.5g" % err_p) == ep
+
+
+@pytest.mark.parametrize("name", ["case_2d_q2q1_bdf2", "case_3d_q1q1_steady", "case_3d_q2q2_steady"])
+def test_oracle_reproduces_committed_fixtures(oracle, name):
+    """tests/golden/case_*.npz (made by tests/golden/make_fixtures.py) are what the GPU parity tests
+    meet; the oracle must still produce them bit for bit (same compiler flags: no FMA contraction)."""
+    fx = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    mesh = oracle.BoxMesh(int(fx["dim"]), int(fx["n"]), int(fx["pu"]), int(fx["pp"]))
+    assert np.array_equal(mesh.rowptr, fx["row_ptr"]) and np.array_equal(mesh.col, fx["col_idx"])
+    dts = list(fx["dts"]) or None
+    pr = oracle.scheme_params(str(fx["scheme"]), dts, float(fx["viscosity"]))
+    U1 = fx["U1"] if fx["U1"].size else None
+    U2 = fx["U2"] if fx["U2"].size else None
+    val, rhs = oracle.assemble(mesh, fx["U"], pr, True, None, U1, U2, None)
+    assert np.array_equal(val, fx["matrix"]) and np.array_equal(rhs, fx["rhs"])
+    lu, dp = oracle.ilu0(mesh, val, 1e-8, 1.0)
+    assert np.array_equal(lu, fx["ilu"])
+    assert np.array_equal(oracle.ilu_apply(mesh, lu, dp, fx["x"]), fx["ilu_apply"])
+    assert np.array_equal(oracle.spmv(mesh, val, fx["x"]), fx["spmv"])
