@@ -248,6 +248,7 @@ glsns_destroy(glsns_context *ctx)
   ctx->dinv.release();
   ctx->diag_rows.release();
   ctx->fgroups.release();
+  ctx->sgroups.release();
   ctx->rowptr.release();
   ctx->diag_pos.release();
   ctx->constrained.release();

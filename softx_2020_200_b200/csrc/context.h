@@ -112,6 +112,8 @@ struct glsns_context
   glsns::DevBuf<double>  inv_jac, det_jac, measure, q_points, force, cvalues;
   glsns::DevBuf<uint8_t> constrained;
   glsns::DevBuf<int2>    fgroups; // (first row, rows) of the row groups, by lower-sweep level
+  glsns::DevBuf<int2>    sgroups; // every row in a group (diagonal-only rows too), by row: SpMV
+  int64_t                n_sgroups = 0;
   std::vector<int32_t>   color_ptr;
   int32_t                levels_l = 0, levels_u = 0, levels_rows = 0, n_groups = 0;
   int32_t                max_row_len = 0, n_diag_rows = 0;

@@ -737,6 +737,22 @@ namespace glsns
       }
     ctx->n_groups    = (int32_t)ng;
     ctx->n_diag_rows = (int32_t)diag_rows.size();
+    { // the SpMV takes every row, group by group, in row order (sparse.cu)
+      std::vector<int2> sg;
+      sg.reserve((size_t)ng + diag_rows.size());
+      size_t dr = 0;
+      for (int64_t g = 0; g < ng; ++g)
+        {
+          while (dr < diag_rows.size() && diag_rows[dr] < grp_ptr[g])
+            sg.push_back(make_int2(diag_rows[dr++], 1));
+          sg.push_back(make_int2(grp_ptr[g], grp_m[g]));
+        }
+      while (dr < diag_rows.size())
+        sg.push_back(make_int2(diag_rows[dr++], 1));
+      ctx->n_sgroups = (int64_t)sg.size();
+      GLSNS_TRY(dev_upload(ctx, ctx->sgroups, sg.data(), sg.size()));
+      GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     GLSNS_TRY(dev_upload(ctx, ctx->diag_rows, diag_rows.data(), diag_rows.size()));
 
     const TrsvConfig cfg = trsv_config();
