@@ -551,14 +551,7 @@ namespace glsns
       {
         const int64_t ng   = ctx->n_sgroups;
         const int64_t want = (ng * tpr + block - 1) / block;
-        // one resident wave: every block streams groups until the matrix is done
-        static int per_sm = 0;
-        if (!per_sm)
-          {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_groups_kernel<32>, block, 0);
-            per_sm = std::max(per_sm, 1);
-          }
-        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->n_sm * per_sm);
+        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->n_sm * 8 * 4);
         if (tpr == 32)
           spmv_groups_kernel<32><<<grid, block, 0, ctx->stream>>>(
             (int32_t)ng, ctx->sgroups.p, ctx->rowptr.p, ctx->col.p, ctx->val.p, x, y);

@@ -265,11 +265,12 @@ namespace glsns
     //     shared-memory window, coefficients from the solver's own stream), the 4x4
     //     triangle, publish.  ~300 issue slots per group.
     constexpr int TS_NSH  = 5;  // helper ring slots
-    constexpr int TS_NSS  = 8;  // solver ring slots
+    constexpr int TS_NSS  = 3;  // solver ring slots
+    constexpr int TS_SCH  = 3;  // groups per solver ring slot (one bulk copy, one barrier wait)
     constexpr int TS_MBOX = 8;  // mailbox entries per team
     constexpr int TS_HSLOT = TS_OFF_COL0 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 4624
     constexpr int TS_SSLOT = TS_OFF_COL1;                                   // 608
-    constexpr int TS_TEAM_AREA = 1024; // windows 4 x 128 | mailbox 256 | solved counter 16 | barriers
+    constexpr int TS_TEAM_AREA = 976; // windows 4 x 128 | mailbox 256 | solved counter 16 | barriers
     static_assert(TS_MBOX == 8 && TS_NWIN == 4 && 128 * TS_NWIN + 32 * TS_MBOX + 16 + 8 * (4 * TS_NSH + TS_NSS) <= TS_TEAM_AREA,
                   "team area");
 
@@ -286,9 +287,9 @@ namespace glsns
       if (team_in_cta >= n_teams_cta)
         return;
       const int64_t team      = (int64_t)team_in_cta * gridDim.x + blockIdx.x; // consecutive lists on different SMs
-      const size_t  team_smem = (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SSLOT + TS_TEAM_AREA;
+      const size_t  team_smem = (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SCH * TS_SSLOT + TS_TEAM_AREA;
       unsigned char *T0   = smem_all + (size_t)team_in_cta * team_smem;
-      unsigned char *area = T0 + (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SSLOT;
+      unsigned char *area = T0 + (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SCH * TS_SSLOT;
       double        *wsm_all = reinterpret_cast<double *>(area);         // [TS_NWIN][16] chain windows by row & 15
       double        *mbox = reinterpret_cast<double *>(area + 128 * TS_NWIN); // [TS_MBOX][4], all-ones = empty
       volatile int  *done = reinterpret_cast<volatile int *>(area + 128 * TS_NWIN + 32 * TS_MBOX); // groups solved
@@ -324,12 +325,13 @@ namespace glsns
                 mbar_init(bars + s, 1);
               asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              for (int s = 0; s < TS_NSS && s < n_items; ++s)
+              for (int s = 0; s < TS_NSS && n_iss < n_items; ++s)
                 {
-                  mbar_expect_tx(bars + s, TS_SSLOT);
-                  bulk_load(ring + (size_t)s * TS_SSLOT, src, TS_SSLOT, bars + s, policy);
-                  src += TS_SSLOT;
-                  ++n_iss;
+                  const unsigned bytes = (unsigned)min((int64_t)TS_SCH, n_items - n_iss) * TS_SSLOT;
+                  mbar_expect_tx(bars + s, bytes);
+                  bulk_load(ring + (size_t)s * TS_SCH * TS_SSLOT, src, bytes, bars + s, policy);
+                  src += bytes;
+                  n_iss += TS_SCH;
                 }
             }
           __syncwarp();
@@ -343,12 +345,14 @@ namespace glsns
       tstage[k] += now_ - tlast;                \
       tlast = now_;                             \
     }
+          int sub = 0; // group inside the slot
           for (int64_t g = 0; g < n_items; ++g)
             {
-              while (!mbar_try_wait(bars + slot, phase))
-                ;
+              if (sub == 0)
+                while (!mbar_try_wait(bars + slot, phase))
+                  ;
               TS_TICK(0)
-              const unsigned char *S  = ring + (size_t)slot * TS_SSLOT;
+              const unsigned char *S  = ring + ((size_t)slot * TS_SCH + sub) * TS_SSLOT;
               const int4           h  = *reinterpret_cast<const int4 *>(S);
               const int            r0 = h.x, m = h.y & 7;
               double              *wsm = wsm_all + 16 * ((h.y >> 12) & (TS_NWIN - 1));
@@ -443,15 +447,20 @@ namespace glsns
                 }
               __syncwarp();
               TS_TICK(3)
-              if (lane == 0 && n_iss < n_items)
-                {
-                  mbar_expect_tx(bars + slot, TS_SSLOT);
-                  bulk_load(ring + (size_t)slot * TS_SSLOT, src, TS_SSLOT, bars + slot, policy);
-                  src += TS_SSLOT;
-                  ++n_iss;
+              if (++sub == TS_SCH)
+                { // the slot is used up: refill it with the groups TS_NSS slots ahead
+                  sub = 0;
+                  if (lane == 0 && n_iss < n_items)
+                    {
+                      const unsigned bytes = (unsigned)min((int64_t)TS_SCH, n_items - n_iss) * TS_SSLOT;
+                      mbar_expect_tx(bars + slot, bytes);
+                      bulk_load(ring + (size_t)slot * TS_SCH * TS_SSLOT, src, bytes, bars + slot, policy);
+                      src += bytes;
+                      n_iss += TS_SCH;
+                    }
+                  slot = slot + 1 == TS_NSS ? 0 : slot + 1;
+                  phase ^= slot == 0;
                 }
-              slot = slot + 1 == TS_NSS ? 0 : slot + 1;
-              phase ^= slot == 0;
               TS_TICK(4)
             }
           if (trace && lane == 0 && (team + 1) * 8 <= trace_n)
@@ -654,7 +663,7 @@ namespace glsns
     size_t
     team_smem_bytes(int helpers)
     {
-      return (size_t)helpers * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SSLOT + TS_TEAM_AREA;
+      return (size_t)helpers * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SCH * TS_SSLOT + TS_TEAM_AREA;
     }
 
     TrsvConfig
