@@ -61,10 +61,9 @@ namespace glsns
     //   header 16: r0 | flags | fmask | bytes/16 of the blob NSLOT items ahead
     //   last item of a group only: dinv 32 | tri 48 | fwd 8*G*WIN
     //   col 4*pad4(entries) | val 8*m*pad4(entries)
-    constexpr int TS_OFF_DINV = 16;
-    constexpr int TS_OFF_TRI  = 48;
-    constexpr int TS_OFF_FWD  = 96;
-    constexpr int TS_OFF_COL1 = TS_OFF_FWD + 8 * TRSV_G * TS_WIN; // 608 (last item)
+    constexpr int TS_OFF_M    = 16;                                  // solver blob: T^-1, [4][4]
+    constexpr int TS_OFF_G    = TS_OFF_M + 8 * TRSV_G * TRSV_G;      // solver blob: T^-1 F, [4][WIN]
+    constexpr int TS_OFF_COL1 = TS_OFF_G + 8 * TRSV_G * TS_WIN;      // 656 = size of a solver blob
     constexpr int TS_OFF_COL0 = 16;                                 // (other items)
     constexpr int TS_MAX_SLOTS = 9;
     constexpr int TS_SMEM_MAX  = 227 * 1024;
@@ -90,13 +89,6 @@ namespace glsns
       const int m = flags & 7, c = pad4(flags >> 16);
       return (flags & IT_SOLVER) ? TS_OFF_COL1 : TS_OFF_COL0 + 4 * c + 8 * m * c;
     }
-    // in-group triangle, packed: lower (1,0)(2,0)(2,1)(3,0)(3,1)(3,2); upper (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
-    __host__ __device__ inline int
-    tri_index(bool upper, int a, int b)
-    {
-      return upper ? (a == 0 ? b - 1 : a == 1 ? b + 1 : 5) : a * (a - 1) / 2 + b;
-    }
-
     // per-warp entry of the stream directory (64 bytes)
     struct TrsvWarpDir
     {
@@ -223,31 +215,77 @@ namespace glsns
               bv[a * cp + k] = k < cntc ? __ldcs(lu + d.rs0 + (int64_t)a * d.len + d.e_off + k) : 0.0;
           return;
         }
-      double *di = reinterpret_cast<double *>(B + TS_OFF_DINV);
-      double *tr = reinterpret_cast<double *>(B + TS_OFF_TRI);
-      double *fw = reinterpret_cast<double *>(B + TS_OFF_FWD);
-      if (lane < TRSV_G) // Ifpack stores and applies the inverted diagonal
-        di[lane] = lane < m ? 1.0 / lu[d.rs0 + (int64_t)lane * d.len + d.nlow + lane] : 0.0;
-      if (lane < 16)
-        {
-          const int a = lane >> 2, b = lane & 3;
-          if (UPPER ? b > a : b < a)
-            tr[tri_index(UPPER, a, b)] =
-              (a < m && b < m) ? lu[d.rs0 + (int64_t)a * d.len + d.nlow + b] : 0.0;
-        }
-      // coupling to the chain window: entry of row a for the chain row at distance dd
+      // Solver blob.  With T the group's own 4x4 triangle (unit lower / upper with the
+      // diagonal) and F its couplings to the 16 chain rows of the window, the recurrence
+      //     T out = -(totals + F w)
+      // is stored solved for out:  M = T^-1 and G = T^-1 F, so that the solver warp does
+      // one 4 x 20 product per group and no substitution (the explicit inverse of a 4x4
+      // block costs a few ulps times its condition number; Ifpack substitutes).
+      // Lanes 0..3 solve for the columns of M, lanes 4..19 for those of G.
+      double T[TRSV_G][TRSV_G];
+#pragma unroll
+      for (int a = 0; a < TRSV_G; ++a)
+#pragma unroll
+        for (int b = 0; b < TRSV_G; ++b)
+          {
+            const bool in = a < m && b < m && (UPPER ? b >= a : b < a);
+            T[a][b]       = in ? lu[d.rs0 + (int64_t)a * d.len + d.nlow + b] : (a == b ? 1.0 : 0.0);
+          }
+      if (!UPPER)
+#pragma unroll
+        for (int a = 0; a < TRSV_G; ++a)
+          T[a][a] = 1.0;
       const unsigned fmask = (unsigned)d.fmask;
-      for (int q = lane; q < TRSV_G * TS_WIN; q += 32)
+      double         rhs[TRSV_G];
+      const int      dd = lane - TRSV_G; // window distance of this lane's G column
+#pragma unroll
+      for (int a = 0; a < TRSV_G; ++a)
         {
-          const int a = q / TS_WIN, dd = q % TS_WIN;
-          double    v = 0;
-          if (a < m && (fmask & (1u << dd)))
+          double v = 0;
+          if (lane < TRSV_G)
+            v = lane == a ? 1.0 : 0.0;
+          else if (dd < TS_WIN && a < m && (fmask & (1u << dd)))
             {
               const int before = __popc(fmask & ((1u << dd) - 1u));
               const int pos    = UPPER ? d.nlow + m + before : d.nlow - 1 - before;
               v                = lu[d.rs0 + (int64_t)a * d.len + pos];
             }
-          fw[q] = v;
+          rhs[a] = v;
+        }
+      double sol[TRSV_G];
+      if (UPPER)
+        {
+#pragma unroll
+          for (int a = TRSV_G - 1; a >= 0; --a)
+            {
+              double v = rhs[a];
+#pragma unroll
+              for (int b = TRSV_G - 1; b > a; --b)
+                v -= T[a][b] * sol[b];
+              sol[a] = v / T[a][a];
+            }
+        }
+      else
+        {
+#pragma unroll
+          for (int a = 0; a < TRSV_G; ++a)
+            {
+              double v = rhs[a];
+#pragma unroll
+              for (int b = 0; b < a; ++b)
+                v -= T[a][b] * sol[b];
+              sol[a] = v;
+            }
+        }
+      double *M = reinterpret_cast<double *>(B + TS_OFF_M);
+      double *G = reinterpret_cast<double *>(B + TS_OFF_G);
+#pragma unroll
+      for (int a = 0; a < TRSV_G; ++a)
+        {
+          if (lane < TRSV_G)
+            M[a * TRSV_G + lane] = sol[a];
+          else if (dd < TS_WIN)
+            G[a * TS_WIN + dd] = sol[a];
         }
     }
 
@@ -356,36 +394,26 @@ namespace glsns
               const int4           h  = *reinterpret_cast<const int4 *>(S);
               const int            r0 = h.x, m = h.y & 7;
               double              *wsm = wsm_all + 16 * ((h.y >> 12) & (TS_NWIN - 1));
-              const double        *di = reinterpret_cast<const double *>(S + TS_OFF_DINV);
-              const double        *tri = reinterpret_cast<const double *>(S + TS_OFF_TRI);
-              const double2       *fw  = reinterpret_cast<const double2 *>(S + TS_OFF_FWD);
-              // couplings to the chain window: rows r0-1-d (lower) / r0+m+d (upper);
-              // coefficients of absent entries are zero (and the window holds finite
-              // numbers), so no masking: all loads first, then four short chains per row
-              double wv[TS_WIN];
-#pragma unroll
-              for (int d = 0; d < TS_WIN; ++d)
-                wv[d] = wsm[(UPPER ? r0 + m + d : r0 - 1 - d) & 15];
-              double s4[TRSV_G][4];
-#pragma unroll
-              for (int a = 0; a < TRSV_G; ++a)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  {
-                    const double2 c0 = fw[a * (TS_WIN / 2) + j], c1 = fw[a * (TS_WIN / 2) + 4 + j];
-                    s4[a][j] = c0.x * wv[2 * j] + c0.y * wv[2 * j + 1];
-                    s4[a][j] += c1.x * wv[8 + 2 * j];
-                    s4[a][j] += c1.y * wv[8 + 2 * j + 1];
-                  }
+              // out = -(M totals + G w): lane (a, j) = (lane >> 3, lane & 7) takes columns j
+              // and j+8 of G (window rows r0-1-d / r0+m+d at distances d = j, j+8) and, for
+              // j < 4, column j of M.  Coefficients of absent couplings are exactly zero
+              // and the window only ever holds finite numbers: no masking.
+              const int     a = lane >> 3, j = lane & 7;
+              const double *G = reinterpret_cast<const double *>(S + TS_OFF_G) + a * TS_WIN;
+              const double  mm = reinterpret_cast<const double *>(S + TS_OFF_M)[a * TRSV_G + (j & 3)];
+              const double  w0 = wsm[(UPPER ? r0 + m + j : r0 - 1 - j) & 15];
+              const double  w1 = wsm[(UPPER ? r0 + m + j + 8 : r0 - 9 - j) & 15];
+              double        p  = G[j] * w0 + G[j + 8] * w1;
               TS_TICK(1)
               // totals of everything else (minus the right-hand side), from a helper: the
               // mailbox entry carries its own readiness (all-ones pattern = empty)
               const int mb = (int)(g & (TS_MBOX - 1));
+              volatile unsigned long long *mv =
+                reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4);
+              unsigned long long tv;
               {
-                volatile unsigned long long *mv =
-                  reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4);
                 long long spins = 0;
-                while (!__all_sync(0xffffffffu, mv[lane & 3] != SENTINEL))
+                while (!__all_sync(0xffffffffu, (tv = mv[lane & 3]) != SENTINEL))
                   if ((++spins & 4095) == 0 &&
                       (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
                     {
@@ -394,55 +422,27 @@ namespace glsns
                     }
               }
               TS_TICK(2)
-              double out[TRSV_G];
-#pragma unroll
-              for (int a = 0; a < TRSV_G; ++a)
-                out[a] = -(reinterpret_cast<volatile double *>(mbox)[mb * 4 + a] +
-                           ((s4[a][0] + s4[a][1]) + (s4[a][2] + s4[a][3])));
+              if (j < 4)
+                p += mm * __longlong_as_double((long long)tv);
               __syncwarp();
               if (lane < TRSV_G) // hand the entry back: empty it, then let group g + TS_MBOX in
-                reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4)[lane] = SENTINEL;
+                mv[lane] = SENTINEL;
               if (lane == 0)
                 *done = (int)g + 1;
-              if (UPPER)
+              p += __shfl_xor_sync(0xffffffffu, p, 4);
+              p += __shfl_xor_sync(0xffffffffu, p, 2);
+              p += __shfl_xor_sync(0xffffffffu, p, 1);
+              if (j == 0 && a < m)
                 {
-#pragma unroll
-                  for (int a = TRSV_G - 1; a >= 0; --a)
-                    {
-                      double v = out[a];
-#pragma unroll
-                      for (int b = TRSV_G - 1; b > a; --b)
-                        v -= tri[tri_index(true, a, b)] * out[b];
-                      out[a] = v * di[a]; // Ifpack stores and applies the inverted diagonal
-                    }
-                }
-              else
-                {
-#pragma unroll
-                  for (int a = 0; a < TRSV_G; ++a)
-                    {
-                      double v = out[a];
-#pragma unroll
-                      for (int b = 0; b < a; ++b)
-                        v -= tri[tri_index(false, a, b)] * out[b];
-                      out[a] = v;
-                    }
-                }
-              if (lane < m)
-                {
-                  double v = out[0];
-#pragma unroll
-                  for (int a = 1; a < TRSV_G; ++a)
-                    if (lane == a)
-                      v = out[a];
-                  st_result(x + r0 + lane, v);
+                  const double v = -p;
+                  st_result(x + r0 + a, v);
                   if (!(h.y & IT_GUEST))
-                    wsm[(r0 + lane) & 15] = v;
+                    wsm[(r0 + a) & 15] = v;
                   if (trace) // debugging aid (glsns_ilu_apply_trace): when was the row published
                     {
                       unsigned long long tns;
                       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-                      trace[r0 + lane] = tns;
+                      trace[r0 + a] = tns;
                     }
                 }
               __syncwarp();
