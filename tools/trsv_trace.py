@@ -27,6 +27,7 @@ for name, t, w, upper in (("lower", tl, wl, False), ("upper", tu, wu, True)):
     rows = np.nonzero(ok)[0]
     # per row: last-arriving dependency
     dt_same, dt_other, crit_is_same = [], [], []
+    other_chained, other_head, other_dist = [], [], []
     pure = {1000: [], 3000: [], 10000: []}  # chain step when every other-warp input is older than .. ns
     step = max(1, len(rows) // 60000)
     for i in rows[::step]:
@@ -41,6 +42,9 @@ for name, t, w, upper in (("lower", tl, wl, False), ("upper", tu, wu, True)):
         d = t[i] - t[j]
         same = warp[j] == warp[i]
         (dt_same if same else dt_other).append(d)
+        if not same:
+            (other_chained if chained[i] else other_head).append(d)
+            other_dist.append(abs(int(j) - int(i)))
         if same:
             oth = c[warp[c] != warp[i]]
             age = t[j] - (t[oth].max() if len(oth) else -10**9)   # how long before the same-warp input
@@ -54,6 +58,11 @@ for name, t, w, upper in (("lower", tl, wl, False), ("upper", tu, wu, True)):
                  "wait_after_last_input_same_warp_ns": [float(np.percentile(ds, p)) for p in (10, 50, 90)] if len(ds) else None,
                  "pure_chain_step_ns_p10_p50_p90_by_min_age_of_other_inputs":
                      {k: [float(np.percentile(v, p)) for p in (10, 50, 90)] + [len(v)] for k, v in pure.items() if len(v)},
+                 "other_team_last_input:_chained_rows_(n,p50_ns)_vs_chain_heads_(n,p50_ns)":
+                     [len(other_chained), float(np.median(other_chained)) if other_chained else None,
+                      len(other_head), float(np.median(other_head)) if other_head else None],
+                 "other_team_last_input_row_distance_p10_p50_p90":
+                     [float(np.percentile(other_dist, p)) for p in (10, 50, 90)] if other_dist else None,
                  "wait_after_last_input_other_warp_ns": [float(np.percentile(do, p)) for p in (10, 50, 90)] if len(do) else None}
     # critical path by time: walk back from the last published row through last-arriving inputs
     i = int(np.argmax(np.where(ok, t, -1))); hops_same = hops_other = 0; time_same = time_other = 0
