@@ -39,15 +39,17 @@ namespace glsns
     int32_t r0;    // first row
     int32_t len;   // row length (same for every row of the group)
     int32_t e_off; // first entry of this item inside the row
-    int32_t flags; // rows in the group | IT_LAST | entries << 16
+    int32_t flags; // rows in the group (block) | IT_LAST / IT_SOLVER ... | entries << 16
     int32_t nlow;  // offset of the in-group block inside the row
-    int32_t fmask; // last item: bit d = couples to the chain row at distance d
+    int32_t fmask; // group descriptor: bit d = couples to the chain row at distance d;
+                   // helper item: where the totals go (block position << 4 | row offset)
   };
 
   // One sweep (lower or upper) of the ILU application in stream form (trsv.cu).
   struct TrsvSweep
   {
     DevBuf<TrsvItem>      items;    // per-warp item lists, concatenated
+    DevBuf<TrsvItem>      gdesc;    // the groups of every block (a solver item's rs0 / len index it)
     DevBuf<int64_t>       blob_off; // byte offset of each item's blob in the stream
     DevBuf<int32_t>       next16;   // bytes/16 of the blob NSLOT items ahead (same warp)
     DevBuf<unsigned char> dir;      // per-warp directory
@@ -56,7 +58,7 @@ namespace glsns
     void
     release()
     {
-      items.release(), blob_off.release(), next16.release(), dir.release(), stream.release();
+      items.release(), gdesc.release(), blob_off.release(), next16.release(), dir.release(), stream.release();
       n_items = stream_bytes = 0;
     }
   };

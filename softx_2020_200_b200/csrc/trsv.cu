@@ -56,26 +56,29 @@ namespace glsns
     constexpr int TRSV_G = 4;          // rows per group
     constexpr int TS_CH  = 128;        // entries per item
     constexpr int TS_U   = TS_CH / 32; // entries per lane and item
-    constexpr int TS_WIN = 16;         // rows of the chain kept in registers
-    // item blob (bytes, 16-byte aligned):
-    //   header 16: r0 | flags | fmask | bytes/16 of the blob NSLOT items ahead
-    //   last item of a group only: dinv 32 | tri 48 | fwd 8*G*WIN
-    //   col 4*pad4(entries) | val 8*m*pad4(entries)
-    constexpr int TS_OFF_M    = 16;                                  // solver blob: T^-1, [4][4]
-    constexpr int TS_OFF_G    = TS_OFF_M + 8 * TRSV_G * TRSV_G;      // solver blob: T^-1 F, [4][WIN]
-    constexpr int TS_OFF_COL1 = TS_OFF_G + 8 * TRSV_G * TS_WIN;      // 656 = size of a solver blob
-    constexpr int TS_OFF_COL0 = 16;                                 // (other items)
+    constexpr int TS_WIN = 16;         // rows of the chain kept in the window
+    constexpr int TS_BG  = 4;          // groups per block (the solver's unit)
+    constexpr int TS_BR  = 16;         // rows per block
+    static_assert(TS_BR == TRSV_G * TS_BG && TS_BR == TS_WIN, "block = window = 16 rows");
+    // item blob (bytes, 16-byte aligned), first 16 bytes = header
+    //   helper item: r0 | flags | block position in the team's list << 4 | row offset in the
+    //                block | bytes/16 of the blob NSLOT items ahead;
+    //                then col 4*pad4(entries) | val 8*m*pad4(entries)
+    //   solver item (one per block): r0 | flags | - | bytes/16 of the blob NSLOT items ahead;
+    //                then the block's solved recurrence, 16 x 2R doubles (R = rows padded to 4)
+    constexpr int TS_OFF_COL0 = 16;
+    constexpr int TS_OFF_C    = 16;
+    constexpr int TS_NSLOT     = 4; // ring slots of every warp (helper and solver)
     constexpr int TS_MAX_SLOTS = 9;
     constexpr int TS_SMEM_MAX  = 227 * 1024;
 
-    // item flags: bits 0-2 rows in the group (m); bit 8 last helper item of its group;
-    // bit 9 solver item (one per group: inverted diagonal, in-group triangle, couplings
-    // to the chain window; fmask bit d = couples to the chain row at distance d);
-    // bits 16.. entries of a helper item
+    // item flags: bits 0-4 rows (m: of the group, <= 4, in a helper item; of the block, <= 16,
+    // in a solver item); bit 8 last helper item of its group; bit 9 solver item; bit 10 solver
+    // item of a block that runs through no window; bits 12-13 of a solver item: which of the
+    // team's windows its chain runs through; bits 16.. entries of a helper item
     constexpr int IT_LAST   = 1 << 8;
     constexpr int IT_SOLVER = 1 << 9;
-    constexpr int IT_GUEST  = 1 << 10; // solver item of a group that runs through no window
-    // bits 12-13 of a solver item: which of the team's windows its chain runs through
+    constexpr int IT_GUEST  = 1 << 10;
     constexpr int TS_NWIN   = 4;
 
     __host__ __device__ inline int
@@ -86,8 +89,8 @@ namespace glsns
     __host__ __device__ inline int
     blob_bytes(int flags)
     {
-      const int m = flags & 7, c = pad4(flags >> 16);
-      return (flags & IT_SOLVER) ? TS_OFF_COL1 : TS_OFF_COL0 + 4 * c + 8 * m * c;
+      const int m = flags & 31, c = pad4(flags >> 16);
+      return (flags & IT_SOLVER) ? TS_OFF_C + 256 * pad4(m) : TS_OFF_COL0 + 4 * c + 8 * m * c;
     }
     // per-warp entry of the stream directory (64 bytes)
     struct TrsvWarpDir
@@ -197,16 +200,18 @@ namespace glsns
     template <bool UPPER>
     __global__ void __launch_bounds__(256)
     trsv_pack_values_kernel(const int64_t n_items, const TrsvItem *__restrict__ items,
+                            const TrsvItem *__restrict__ gdesc,
                             const int64_t *__restrict__ blob_off, const double *__restrict__ lu,
                             unsigned char *__restrict__ stream)
     {
+      __shared__ double TF[8][2 * TS_BR * TS_BR]; // per warp: T [16][16], F [16][16]
       const int64_t it   = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       const int     lane = threadIdx.x & 31;
       if (it >= n_items)
         return;
       const TrsvItem d = items[it];
       unsigned char *B = stream + blob_off[it];
-      const int      m = d.flags & 7, cntc = d.flags >> 16, cp = pad4(cntc);
+      const int      m = d.flags & 31, cntc = d.flags >> 16, cp = pad4(cntc);
       if (!(d.flags & IT_SOLVER))
         {
           double *bv = reinterpret_cast<double *>(B + TS_OFF_COL0 + 4 * cp);
@@ -215,101 +220,102 @@ namespace glsns
               bv[a * cp + k] = k < cntc ? __ldcs(lu + d.rs0 + (int64_t)a * d.len + d.e_off + k) : 0.0;
           return;
         }
-      // Solver blob.  With T the group's own 4x4 triangle (unit lower / upper with the
-      // diagonal) and F its couplings to the 16 chain rows of the window, the recurrence
+      // Solver blob of a BLOCK (<= 4 consecutive groups of one chain, rows [r0, r0 + m)).
+      // With T the block's own triangle (unit lower / upper with the diagonal: the
+      // in-group triangles and the couplings between the groups of the block) and F its
+      // couplings to the 16 chain rows next to it (the window), the recurrence
       //     T out = -(totals + F w)
       // is stored solved for out:  M = T^-1 and G = T^-1 F, so that the solver warp does
-      // one 4 x 20 product per group and no substitution (the explicit inverse of a 4x4
-      // block costs a few ulps times its condition number; Ifpack substitutes).
-      // Lanes 0..3 solve for the columns of M, lanes 4..19 for those of G.
-      double T[TRSV_G][TRSV_G];
-#pragma unroll
-      for (int a = 0; a < TRSV_G; ++a)
-#pragma unroll
-        for (int b = 0; b < TRSV_G; ++b)
-          {
-            const bool in = a < m && b < m && (UPPER ? b >= a : b < a);
-            T[a][b]       = in ? lu[d.rs0 + (int64_t)a * d.len + d.nlow + b] : (a == b ? 1.0 : 0.0);
-          }
-      if (!UPPER)
-#pragma unroll
-        for (int a = 0; a < TRSV_G; ++a)
-          T[a][a] = 1.0;
-      const unsigned fmask = (unsigned)d.fmask;
-      double         rhs[TRSV_G];
-      const int      dd = lane - TRSV_G; // window distance of this lane's G column
-#pragma unroll
-      for (int a = 0; a < TRSV_G; ++a)
+      // one 16 x 32 product per block and no substitution (the explicit inverse of a
+      // 16 x 16 triangle costs a few ulps times its condition number; Ifpack substitutes).
+      double *T = TF[(threadIdx.x >> 5)], *F = T + TS_BR * TS_BR;
+      for (int k = lane; k < TS_BR * TS_BR; k += 32)
         {
-          double v = 0;
-          if (lane < TRSV_G)
-            v = lane == a ? 1.0 : 0.0;
-          else if (dd < TS_WIN && a < m && (fmask & (1u << dd)))
-            {
-              const int before = __popc(fmask & ((1u << dd) - 1u));
-              const int pos    = UPPER ? d.nlow + m + before : d.nlow - 1 - before;
-              v                = lu[d.rs0 + (int64_t)a * d.len + pos];
-            }
-          rhs[a] = v;
+          T[k] = (k / TS_BR == k % TS_BR) ? 1.0 : 0.0;
+          F[k] = 0.0;
         }
-      double sol[TRSV_G];
+      __syncwarp();
+      const int r0b = d.r0;
+      for (int q = 0; q < d.len; ++q)
+        {
+          const TrsvItem gq = gdesc[d.rs0 + q];
+          const int      mg = gq.flags & 31, off = gq.r0 - r0b;
+          const unsigned fm = (unsigned)gq.fmask;
+          for (int a = 0; a < mg; ++a)
+            {
+              const double *row = lu + gq.rs0 + (int64_t)a * gq.len;
+              if (lane < mg && (UPPER ? lane >= a : lane < a))
+                T[(off + a) * TS_BR + off + lane] = row[gq.nlow + lane];
+              if (lane < TS_WIN && (fm & (1u << lane)))
+                {
+                  const int    before = __popc(fm & ((1u << lane) - 1u));
+                  const double v      = row[UPPER ? gq.nlow + mg + before : gq.nlow - 1 - before];
+                  const int    tr     = UPPER ? gq.r0 + mg + lane : gq.r0 - 1 - lane; // coupled row
+                  if (UPPER ? tr < r0b + m : tr >= r0b)
+                    T[(off + a) * TS_BR + tr - r0b] = v;
+                  else
+                    F[(off + a) * TS_BR + (UPPER ? tr - (r0b + m) : r0b - 1 - tr)] = v;
+                }
+            }
+        }
+      __syncwarp();
+      // lane c < 16 solves for column c of M, lane c >= 16 for column c - 16 of G
+      double y[TS_BR];
       if (UPPER)
         {
 #pragma unroll
-          for (int a = TRSV_G - 1; a >= 0; --a)
+          for (int a = TS_BR - 1; a >= 0; --a)
             {
-              double v = rhs[a];
+              double v = lane < TS_BR ? (lane == a ? 1.0 : 0.0) : F[a * TS_BR + lane - TS_BR];
 #pragma unroll
-              for (int b = TRSV_G - 1; b > a; --b)
-                v -= T[a][b] * sol[b];
-              sol[a] = v / T[a][a];
+              for (int b = TS_BR - 1; b > a; --b)
+                v -= T[a * TS_BR + b] * y[b];
+              y[a] = v / T[a * TS_BR + a];
             }
         }
       else
         {
 #pragma unroll
-          for (int a = 0; a < TRSV_G; ++a)
+          for (int a = 0; a < TS_BR; ++a)
             {
-              double v = rhs[a];
+              double v = lane < TS_BR ? (lane == a ? 1.0 : 0.0) : F[a * TS_BR + lane - TS_BR];
 #pragma unroll
               for (int b = 0; b < a; ++b)
-                v -= T[a][b] * sol[b];
-              sol[a] = v;
+                v -= T[a * TS_BR + b] * y[b];
+              y[a] = v;
             }
         }
-      double *M = reinterpret_cast<double *>(B + TS_OFF_M);
-      double *G = reinterpret_cast<double *>(B + TS_OFF_G);
+      // layout the solver reads without bank conflicts: C[jj][2 a + hh], jj < 8: G[a][8 hh + jj],
+      // jj >= 8: M[a][8 hh + jj - 8]
+      const int R2 = 2 * pad4(m);
+      double   *C  = reinterpret_cast<double *>(B + TS_OFF_C);
+      const int cc = lane & 15, hh = cc >> 3, jj = (cc & 7) + (lane < TS_BR ? 8 : 0);
 #pragma unroll
-      for (int a = 0; a < TRSV_G; ++a)
-        {
-          if (lane < TRSV_G)
-            M[a * TRSV_G + lane] = sol[a];
-          else if (dd < TS_WIN)
-            G[a * TS_WIN + dd] = sol[a];
-        }
+      for (int a = 0; a < TS_BR; ++a)
+        if (2 * a < R2)
+          C[jj * R2 + 2 * a + hh] = y[a];
     }
 
     // ---- the solve ---------------------------------------------------------------
-    // A TEAM of 1 + K warps owns one list of groups (chains, in the order the host
-    // scheduled them):
+    // A TEAM of 1 + K warps owns one list of BLOCKS (chains, in the order the host
+    // scheduled them); a block is up to 4 consecutive groups of one chain (<= 16 rows):
     //   * K helper warps take the groups round-robin.  A helper streams the items of
     //     its groups (column indices + factor entries) through its own ring, gathers
     //     the solution entries they refer to (re-reading until they are there),
     //     multiplies, folds in the right-hand side, reduces over the warp and posts
-    //     the four totals in the team's mailbox.  None of this depends on the chain,
-    //     so it runs ahead of it, on several groups at once.
-    //   * the solver warp is the chain's recurrence and nothing else: mailbox totals
-    //     minus the couplings to the last 16 rows of the chain (kept in a tiny
-    //     shared-memory window, coefficients from the solver's own stream), the 4x4
-    //     triangle, publish.  ~300 issue slots per group.
-    constexpr int TS_NSH  = 5;  // helper ring slots
-    constexpr int TS_NSS  = 3;  // solver ring slots
-    constexpr int TS_SCH  = 3;  // groups per solver ring slot (one bulk copy, one barrier wait)
-    constexpr int TS_MBOX = 8;  // mailbox entries per team
+    //     the group's totals in the block's mailbox entry.  None of this depends on the
+    //     chain, so it runs ahead of it, on several groups at once.
+    //   * the solver warp is the chain's recurrence and nothing else, a whole block per
+    //     step: out = -(M totals + G w) with w the last 16 rows of the chain before the
+    //     block (kept in a tiny shared-memory window) and M, G the block's recurrence
+    //     solved ahead of time; publish.  The chain advances 16 rows per step.
+    constexpr int TS_MBOX  = 8;  // mailbox entries (blocks) per team
     constexpr int TS_HSLOT = TS_OFF_COL0 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 4624
-    constexpr int TS_SSLOT = TS_OFF_COL1;                                   // 608
-    constexpr int TS_TEAM_AREA = 976; // windows 4 x 128 | mailbox 256 | solved counter 16 | barriers
-    static_assert(TS_MBOX == 8 && TS_NWIN == 4 && 128 * TS_NWIN + 32 * TS_MBOX + 16 + 8 * (4 * TS_NSH + TS_NSS) <= TS_TEAM_AREA,
+    constexpr int TS_SSLOT = TS_OFF_C + 256 * TS_BR;                        // 4112
+    // team area: windows 4 x 128 | mailbox 8 x 128 | solved counter 16 | barriers
+    constexpr int TS_TEAM_AREA = 1792;
+    static_assert(TS_MBOX == 8 && TS_NWIN == 4 &&
+                    128 * TS_NWIN + 128 * TS_MBOX + 16 + 8 * 5 * TS_NSLOT <= TS_TEAM_AREA,
                   "team area");
 
     template <bool UPPER>
@@ -325,24 +331,26 @@ namespace glsns
       if (team_in_cta >= n_teams_cta)
         return;
       const int64_t team      = (int64_t)team_in_cta * gridDim.x + blockIdx.x; // consecutive lists on different SMs
-      const size_t  team_smem = (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SCH * TS_SSLOT + TS_TEAM_AREA;
+      const size_t  team_smem = (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_NSLOT * TS_SSLOT + TS_TEAM_AREA;
       unsigned char *T0   = smem_all + (size_t)team_in_cta * team_smem;
-      unsigned char *area = T0 + (size_t)K * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SCH * TS_SSLOT;
+      unsigned char *area = T0 + (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_NSLOT * TS_SSLOT;
       double        *wsm_all = reinterpret_cast<double *>(area);         // [TS_NWIN][16] chain windows by row & 15
-      double        *mbox = reinterpret_cast<double *>(area + 128 * TS_NWIN); // [TS_MBOX][4], all-ones = empty
-      volatile int  *done = reinterpret_cast<volatile int *>(area + 128 * TS_NWIN + 32 * TS_MBOX); // groups solved
+      double        *mbox = reinterpret_cast<double *>(area + 128 * TS_NWIN); // [TS_MBOX][16], all-ones = empty
+      volatile int  *done = reinterpret_cast<volatile int *>(area + 128 * TS_NWIN + 128 * TS_MBOX); // blocks solved
       unsigned long long *bars_all =
-        reinterpret_cast<unsigned long long *>(area + 128 * TS_NWIN + 32 * TS_MBOX + 16);
+        reinterpret_cast<unsigned long long *>(area + 128 * TS_NWIN + 128 * TS_MBOX + 16);
       const TrsvWarpDir  *D        = dir + team * (K + 1) + role;
       const int64_t       n_items  = D->n_items;
       unsigned long long  policy;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      // team-wide initialisation by the solver warp (window zero, mailbox empty), made
+      // team-wide initialisation by the solver warp (windows zero, mailbox empty), made
       // visible to the helpers by the one CTA barrier of the kernel
       if (role == 0)
         {
           wsm_all[lane] = wsm_all[lane + 32] = 0.0; // TS_NWIN * 16 = 64 entries
-          reinterpret_cast<unsigned long long *>(mbox)[lane] = SENTINEL; // TS_MBOX * 4 = 32 entries, all empty
+#pragma unroll
+          for (int k = 0; k < TS_MBOX * TS_BR / 32; ++k)
+            reinterpret_cast<unsigned long long *>(mbox)[lane + 32 * k] = SENTINEL;
           if (lane == 0)
             *done = 0;
         }
@@ -354,22 +362,29 @@ namespace glsns
       if (role == 0)
         {
           // =============================== solver ===============================
-          unsigned char      *ring = T0 + (size_t)K * TS_NSH * TS_HSLOT;
-          unsigned long long *bars = bars_all + K * TS_NSH;
+          // One item per BLOCK (<= 16 rows): out = -(M totals + G w), the recurrence of the
+          // whole block solved ahead of time (trsv_pack_values_kernel).  Lane (a, hh) =
+          // (lane >> 1, lane & 1) takes row a and the columns 8 hh .. 8 hh + 7 of both G
+          // (window rows r0-1-d / r0+m+d at distance d) and M (totals of the block's own
+          // rows).  Coefficients of absent couplings are exactly zero and the window only
+          // ever holds finite numbers, so the window part needs no masking; the totals of
+          // rows the block does not have are masked (their mailbox entries stay empty).
+          unsigned char      *ring = T0 + (size_t)K * TS_NSLOT * TS_HSLOT;
+          unsigned long long *bars = bars_all + K * TS_NSLOT;
           int64_t             n_iss = 0;
           if (lane == 0)
             {
-              for (int s = 0; s < TS_NSS; ++s)
+              for (int s = 0; s < TS_NSLOT; ++s)
                 mbar_init(bars + s, 1);
               asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              for (int s = 0; s < TS_NSS && n_iss < n_items; ++s)
+              for (int s = 0; s < TS_NSLOT && s < n_items; ++s)
                 {
-                  const unsigned bytes = (unsigned)min((int64_t)TS_SCH, n_items - n_iss) * TS_SSLOT;
+                  const unsigned bytes = 16u * (unsigned)D->first16[s];
                   mbar_expect_tx(bars + s, bytes);
-                  bulk_load(ring + (size_t)s * TS_SCH * TS_SSLOT, src, bytes, bars + s, policy);
+                  bulk_load(ring + (size_t)s * TS_SSLOT, src, bytes, bars + s, policy);
                   src += bytes;
-                  n_iss += TS_SCH;
+                  ++n_iss;
                 }
             }
           __syncwarp();
@@ -383,37 +398,47 @@ namespace glsns
       tstage[k] += now_ - tlast;                \
       tlast = now_;                             \
     }
-          int sub = 0; // group inside the slot
+          const int a = lane >> 1, hh = lane & 1;
           for (int64_t g = 0; g < n_items; ++g)
             {
-              if (sub == 0)
-                while (!mbar_try_wait(bars + slot, phase))
-                  ;
+              while (!mbar_try_wait(bars + slot, phase))
+                ;
               TS_TICK(0)
-              const unsigned char *S  = ring + ((size_t)slot * TS_SCH + sub) * TS_SSLOT;
+              const unsigned char *S  = ring + (size_t)slot * TS_SSLOT;
               const int4           h  = *reinterpret_cast<const int4 *>(S);
-              const int            r0 = h.x, m = h.y & 7;
+              const int            r0 = h.x, m = h.y & 31, R2 = 2 * pad4(m);
               double              *wsm = wsm_all + 16 * ((h.y >> 12) & (TS_NWIN - 1));
-              // out = -(M totals + G w): lane (a, j) = (lane >> 3, lane & 7) takes columns j
-              // and j+8 of G (window rows r0-1-d / r0+m+d at distances d = j, j+8) and, for
-              // j < 4, column j of M.  Coefficients of absent couplings are exactly zero
-              // and the window only ever holds finite numbers: no masking.
-              const int     a = lane >> 3, j = lane & 7;
-              const double *G = reinterpret_cast<const double *>(S + TS_OFF_G) + a * TS_WIN;
-              const double  mm = reinterpret_cast<const double *>(S + TS_OFF_M)[a * TRSV_G + (j & 3)];
-              const double  w0 = wsm[(UPPER ? r0 + m + j : r0 - 1 - j) & 15];
-              const double  w1 = wsm[(UPPER ? r0 + m + j + 8 : r0 - 9 - j) & 15];
-              double        p  = G[j] * w0 + G[j + 8] * w1;
+              const double        *C   = reinterpret_cast<const double *>(S + TS_OFF_C) + lane;
+              const bool           on  = lane < R2;
+              double               cg[8], cm[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                {
+                  cg[j] = on ? C[j * R2] : 0.0;
+                  cm[j] = on ? C[(j + 8) * R2] : 0.0;
+                }
+              // the window part first: it is what the chain waits for
+              double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+              {
+                const int wb = UPPER ? r0 + m + 8 * hh : r0 - 1 - 8 * hh;
+#pragma unroll
+                for (int j = 0; j < 8; j += 4)
+                  {
+                    p0 += cg[j] * wsm[(UPPER ? wb + j : wb - j) & 15];
+                    p1 += cg[j + 1] * wsm[(UPPER ? wb + j + 1 : wb - j - 1) & 15];
+                    p2 += cg[j + 2] * wsm[(UPPER ? wb + j + 2 : wb - j - 2) & 15];
+                    p3 += cg[j + 3] * wsm[(UPPER ? wb + j + 3 : wb - j - 3) & 15];
+                  }
+              }
               TS_TICK(1)
-              // totals of everything else (minus the right-hand side), from a helper: the
+              // totals of everything else (minus the right-hand side), from the helpers: a
               // mailbox entry carries its own readiness (all-ones pattern = empty)
               const int mb = (int)(g & (TS_MBOX - 1));
               volatile unsigned long long *mv =
-                reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4);
-              unsigned long long tv;
+                reinterpret_cast<volatile unsigned long long *>(mbox + mb * TS_BR);
               {
                 long long spins = 0;
-                while (!__all_sync(0xffffffffu, (tv = mv[lane & 3]) != SENTINEL))
+                while (!__all_sync(0xffffffffu, (lane & 15) >= m || mv[lane & 15] != SENTINEL))
                   if ((++spins & 4095) == 0 &&
                       (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
                     {
@@ -422,17 +447,26 @@ namespace glsns
                     }
               }
               TS_TICK(2)
-              if (j < 4)
-                p += mm * __longlong_as_double((long long)tv);
+              {
+                const volatile double *tt = mbox + mb * TS_BR + 8 * hh;
+                const int     mr = m - 8 * hh; // rows of this half that exist
+#pragma unroll
+                for (int j = 0; j < 8; j += 4)
+                  {
+                    p0 += cm[j] * (j < mr ? tt[j] : 0.0);
+                    p1 += cm[j + 1] * (j + 1 < mr ? tt[j + 1] : 0.0);
+                    p2 += cm[j + 2] * (j + 2 < mr ? tt[j + 2] : 0.0);
+                    p3 += cm[j + 3] * (j + 3 < mr ? tt[j + 3] : 0.0);
+                  }
+              }
+              double p = (p0 + p1) + (p2 + p3);
               __syncwarp();
-              if (lane < TRSV_G) // hand the entry back: empty it, then let group g + TS_MBOX in
+              if (lane < TS_BR) // hand the entry back: empty it, then let block g + TS_MBOX in
                 mv[lane] = SENTINEL;
               if (lane == 0)
                 *done = (int)g + 1;
-              p += __shfl_xor_sync(0xffffffffu, p, 4);
-              p += __shfl_xor_sync(0xffffffffu, p, 2);
               p += __shfl_xor_sync(0xffffffffu, p, 1);
-              if (j == 0 && a < m)
+              if (hh == 0 && a < m)
                 {
                   const double v = -p;
                   st_result(x + r0 + a, v);
@@ -447,24 +481,21 @@ namespace glsns
                 }
               __syncwarp();
               TS_TICK(3)
-              if (++sub == TS_SCH)
-                { // the slot is used up: refill it with the groups TS_NSS slots ahead
-                  sub = 0;
-                  if (lane == 0 && n_iss < n_items)
-                    {
-                      const unsigned bytes = (unsigned)min((int64_t)TS_SCH, n_items - n_iss) * TS_SSLOT;
-                      mbar_expect_tx(bars + slot, bytes);
-                      bulk_load(ring + (size_t)slot * TS_SCH * TS_SSLOT, src, bytes, bars + slot, policy);
-                      src += bytes;
-                      n_iss += TS_SCH;
-                    }
-                  slot = slot + 1 == TS_NSS ? 0 : slot + 1;
-                  phase ^= slot == 0;
+              // the slot is used up: refill it with the block TS_NSLOT ahead
+              if (lane == 0 && n_iss < n_items)
+                {
+                  const unsigned bytes = 16u * (unsigned)h.w;
+                  mbar_expect_tx(bars + slot, bytes);
+                  bulk_load(ring + (size_t)slot * TS_SSLOT, src, bytes, bars + slot, policy);
+                  src += bytes;
+                  ++n_iss;
                 }
+              slot = slot + 1 == TS_NSLOT ? 0 : slot + 1;
+              phase ^= slot == 0;
               TS_TICK(4)
             }
           if (trace && lane == 0 && (team + 1) * 8 <= trace_n)
-            { // cycles in: ring wait, window product, mailbox wait, triangle+publish, release+refill
+            { // cycles in: ring wait, window product, mailbox wait, totals+publish, release+refill
               for (int k = 0; k < 6; ++k)
                 trace[2 * trace_n + team * 8 + k] = (unsigned long long)tstage[k];
               trace[2 * trace_n + team * 8 + 6] = (unsigned long long)n_items;
@@ -475,16 +506,16 @@ namespace glsns
 
       // =============================== helper ===============================
       const int           hid  = role - 1;
-      unsigned char      *ring = T0 + (size_t)hid * TS_NSH * TS_HSLOT;
-      unsigned long long *bars = bars_all + hid * TS_NSH;
+      unsigned char      *ring = T0 + (size_t)hid * TS_NSLOT * TS_HSLOT;
+      unsigned long long *bars = bars_all + hid * TS_NSLOT;
       int64_t             n_iss = 0;
       if (lane == 0)
         {
-          for (int s = 0; s < TS_NSH; ++s)
+          for (int s = 0; s < TS_NSLOT; ++s)
             mbar_init(bars + s, 1);
           asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          for (int s = 0; s < TS_NSH && s < n_items; ++s)
+          for (int s = 0; s < TS_NSLOT && s < n_items; ++s)
             {
               const unsigned bytes = 16u * (unsigned)D->first16[s];
               mbar_expect_tx(bars + s, bytes);
@@ -506,7 +537,6 @@ namespace glsns
         acc[a] = 0;
       int      slotG = 0, slotR = 0;
       unsigned phaseG = 0;
-      int64_t  seq    = hid; // position of the helper's current group in the team's list
       // one pipeline step: G(it) into set KG, R(it-2) from set (KG+1)%3
       auto step = [&](auto KG, const int64_t it) {
         constexpr int      kg = decltype(KG)::value, kr = (kg + 1) % 3;
@@ -540,9 +570,9 @@ namespace glsns
             for (int u = 0; u < TS_U; ++u)
               if (pendN & (1u << u))
                 bN[u] = ld_relaxed_u64(x + cN[u]);
-            if ((flags & IT_LAST) && lane < (flags & 7))
+            if ((flags & IT_LAST) && lane < (flags & 31))
               rS[kg] = rhs_vec[h.x + lane];
-            slotG = slotG + 1 == TS_NSH ? 0 : slotG + 1;
+            slotG = slotG + 1 == TS_NSLOT ? 0 : slotG + 1;
             phaseG ^= slotG == 0;
           }
         // ---- R(it-2): entries not there yet are re-read until they are; multiply ----
@@ -550,7 +580,7 @@ namespace glsns
           {
             const unsigned char *S     = ring + (size_t)slotR * TS_HSLOT;
             const int4           h     = *reinterpret_cast<const int4 *>(S);
-            const int            flags = h.y, m = flags & 7, cp = pad4(flags >> 16);
+            const int            flags = h.y, m = flags & 31, cp = pad4(flags >> 16);
             const double        *sval  = reinterpret_cast<const double *>(S + TS_OFF_COL0 + 4 * cp);
             long long            spins = 0;
             for (;;)
@@ -573,6 +603,17 @@ namespace glsns
                 for (int u = 0; u < TS_U; ++u)
                   if (pendG & (1u << u))
                     bG[u] = ld_relaxed_u64(x + cG[u]);
+                // the entries of the two items behind this one that were not there when they
+                // were first read are refreshed in the same round trip: when this item is
+                // done, they need no round trip of their own
+#pragma unroll
+                for (int u = 0; u < TS_U; ++u)
+                  {
+                    if ((pendN & (1u << u)) && bN[u] == SENTINEL)
+                      bN[u] = ld_relaxed_u64(x + cN[u]);
+                    if ((pS[(kg + 2) % 3] & (1u << u)) && bS[(kg + 2) % 3][u] == SENTINEL)
+                      bS[(kg + 2) % 3][u] = ld_relaxed_u64(x + cS[(kg + 2) % 3][u]);
+                  }
                 // bug guard: give up after seconds of waiting, or as soon as another
                 // warp has given up (the host reports GLSNS_ERR_CUDA)
                 if ((++spins & 1023) == 0 &&
@@ -590,50 +631,61 @@ namespace glsns
                 for (int a = 0; a < TRSV_G; ++a)
                   if (lane == a && a < m)
                     acc[a] -= rS[kr];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                  for (int a = 0; a < TRSV_G; ++a)
-                    acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
-                const int mb = (int)(seq & (TS_MBOX - 1));
-                volatile unsigned long long *mv =
-                  reinterpret_cast<volatile unsigned long long *>(mbox + mb * 4);
+                // four totals over 32 lanes in 6 shuffles: halve the number of rows a lane
+                // carries while the partners are 16 and 8 lanes apart, then sum over the
+                // rest; lane 8 a ends up with the total of row a
+                double tot;
+                {
+                  const bool   h16 = lane & 16, h8 = lane & 8;
+                  const double s0 = h16 ? acc[0] : acc[2], s1 = h16 ? acc[1] : acc[3];
+                  double       k0 = h16 ? acc[2] : acc[0], k1 = h16 ? acc[3] : acc[1];
+                  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                  tot = (h8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+                  tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+                  tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                  tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                }
+                // (header: position of the group's block in the team's list << 4 | row offset)
+                const int bseq = h.z >> 4, boff = h.z & 15;
+                volatile unsigned long long *mv = reinterpret_cast<volatile unsigned long long *>(
+                  mbox + (bseq & (TS_MBOX - 1)) * TS_BR + boff);
                 spins = 0;
-                // the entry is this group's once the solver is within TS_MBOX groups of it
-                while ((int64_t)*done + TS_MBOX <= seq)
+                // the entry is this block's once the solver is within TS_MBOX blocks of it
+                while (*done + TS_MBOX <= bseq)
                   if ((++spins & 4095) == 0 &&
                       (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
                     {
                       atomicExch(&counters[1], 2);
                       break;
                     }
-                if (lane < TRSV_G)
+                if ((lane & 7) == 0 && (lane >> 3) < m)
                   {
-                    double v = acc[0];
-#pragma unroll
-                    for (int a = 1; a < TRSV_G; ++a)
-                      if (lane == a)
-                        v = acc[a];
-                    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+                    unsigned long long b = (unsigned long long)__double_as_longlong(tot);
                     if (b == SENTINEL)
                       b = 0x7FF8000000000000ull;
-                    mv[lane] = b;
+                    mv[lane >> 3] = b;
+                    if (trace) // debugging aid: when were the row's totals posted
+                      {
+                        unsigned long long tns;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+                        trace[4 * trace_n + h.x + (lane >> 3)] = tns;
+                      }
                   }
 #pragma unroll
                 for (int a = 0; a < TRSV_G; ++a)
                   acc[a] = 0;
-                seq += K;
               }
             __syncwarp(); // every lane is done with the slot before it is refilled
             if (lane == 0 && n_iss < n_items)
               {
-                const unsigned bytes = 16u * (unsigned)h.w; // size of the item TS_NSH ahead
+                const unsigned bytes = 16u * (unsigned)h.w; // size of the item TS_NSLOT ahead
                 mbar_expect_tx(bars + slotR, bytes);
                 bulk_load(ring + (size_t)slotR * TS_HSLOT, src, bytes, bars + slotR, policy);
                 src += bytes;
                 ++n_iss;
               }
-            slotR = slotR + 1 == TS_NSH ? 0 : slotR + 1;
+            slotR = slotR + 1 == TS_NSLOT ? 0 : slotR + 1;
           }
       };
       for (int64_t it = 0; it < n_items + 2; it += 3)
@@ -663,7 +715,7 @@ namespace glsns
     size_t
     team_smem_bytes(int helpers)
     {
-      return (size_t)helpers * TS_NSH * TS_HSLOT + (size_t)TS_NSS * TS_SCH * TS_SSLOT + TS_TEAM_AREA;
+      return (size_t)helpers * TS_NSLOT * TS_HSLOT + (size_t)TS_NSLOT * TS_SSLOT + TS_TEAM_AREA;
     }
 
     TrsvConfig
@@ -768,13 +820,13 @@ namespace glsns
     ctx->trsv_grid       = ctx->n_sm;
     const int64_t NW     = (int64_t)ctx->trsv_grid * cfg.teams; // teams: one chain list each
     const int32_t max_level_gap = getenv("GLSNS_TRSV_GAP") ? atoi(getenv("GLSNS_TRSV_GAP")) : 2;
+    const int32_t max_block     = std::max(1, std::min(TS_BG, getenv("GLSNS_TRSV_BLOCK") ? atoi(getenv("GLSNS_TRSV_BLOCK")) : TS_BG));
     const int     K      = cfg.helpers;
 
-    std::vector<int32_t> glev(ng), fmask(ng), gapv(ng), cnt(ng), e_off(ng), order(ng), warp_of(ng),
-      slot_of(ng);
-    std::vector<uint8_t> link(ng), has_succ(ng), is_primary(ng);
+    std::vector<int32_t> glev(ng), fmask(ng), cnt(ng), e_off(ng), order(ng), blk_of(ng);
+    std::vector<uint8_t> link(ng);
 
-    // One sweep: levels, chain links, level-ordered schedule on NW warps, item lists.
+    // One sweep: levels, blocks, chain links, level-ordered schedule on NW teams, item lists.
     auto schedule = [&](const bool upper, TrsvSweep &sw, int32_t &n_levels) -> glsns_status {
       // entries of group g this sweep reads, [kb, ke) in CSR offsets of its first row
       auto range = [&](int64_t g, int64_t &kb, int64_t &ke) {
@@ -785,8 +837,8 @@ namespace glsns
           while (ke > kb && col[ke - 1] >= n)
             --ke; // ghost columns: outside the diagonal block
       };
+      // ---- group levels (the depth of the ordering's dependency DAG) and links ----
       int32_t nlev = 0;
-      std::fill(has_succ.begin(), has_succ.end(), 0);
       for (int64_t gi = 0; gi < ng; ++gi)
         {
           const int64_t g = upper ? ng - 1 - gi : gi;
@@ -801,8 +853,8 @@ namespace glsns
             }
           glev[g] = l;
           nlev    = std::max(nlev, l);
-          // chain link: the group depends on its neighbour in the numbering, with
-          // nothing but diagonal-only rows (and fewer than a window of them) in between
+          // link: the group depends on its neighbour in the numbering, with nothing but
+          // diagonal-only rows (and fewer than a window of them) in between
           const int64_t p = upper ? g + 1 : g - 1;
           link[g]         = 0;
           if (p >= 0 && p < ng)
@@ -826,13 +878,12 @@ namespace glsns
                           break;
                         }
                 }
+              // bit 1: the neighbour's rows are adjacent and it was solved just before this
+              // group can be (no other input of the group is much younger): the two are
+              // worth solving as one block
+              if (link[g] && gap == 0 && l - glev[p] <= max_level_gap)
+                link[g] |= 2;
             }
-          // a predecessor solved long before this group needs it is no link: its rows
-          // reach the group through L2 in time, and the team is free for another chain
-          if (link[g] && l - glev[p] > max_level_gap)
-            link[g] = 0;
-          if (link[g])
-            has_succ[p] = 1;
         }
       n_levels = ng ? nlev + 1 : 0;
       // groups by level (within a level in sweep order)
@@ -856,8 +907,69 @@ namespace glsns
           GLSNS_TRY(dev_upload(ctx, ctx->fgroups, fg.data(), fg.size()));
           GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
-      // list scheduling: a chained group follows its predecessor on the same warp;
-      // a chain head takes the warp that has been free the longest
+      // ---- blocks: runs of <= TS_BG linked groups with adjacent rows, in sweep order ----
+      // Everything a block needs from outside was numbered before its first group (in sweep
+      // order), so nothing outside it can wait for part of it: solving its rows together
+      // (one step of the solver warp) cannot dead-lock, and it removes the hops between them
+      // from the critical path.
+      std::vector<int32_t> b_first, b_ng, b_r0, b_m;
+      b_first.reserve(ng / 2 + 1), b_ng.reserve(ng / 2 + 1), b_r0.reserve(ng / 2 + 1), b_m.reserve(ng / 2 + 1);
+      for (int64_t gi = 0; gi < ng; ++gi)
+        {
+          const int64_t g = upper ? ng - 1 - gi : gi;
+          if (gi > 0 && (link[g] & 2) && b_ng.back() < max_block && b_m.back() + grp_m[g] <= TS_BR)
+            {
+              ++b_ng.back();
+              b_m.back() += grp_m[g];
+              if (upper)
+                b_r0.back() = grp_ptr[g];
+            }
+          else
+            {
+              b_first.push_back((int32_t)g), b_ng.push_back(1), b_r0.push_back(grp_ptr[g]),
+                b_m.push_back(grp_m[g]);
+            }
+          blk_of[g] = (int32_t)b_first.size() - 1;
+        }
+      const int64_t nb = (int64_t)b_first.size();
+      auto          group_of_block = [&](int64_t b, int32_t q) -> int64_t { // q-th group in sweep order
+        return upper ? (int64_t)b_first[b] - q : (int64_t)b_first[b] + q;
+      };
+      // block levels and block links (block ids run in sweep order: the predecessor of the
+      // first group of block b is the last group of block b - 1)
+      std::vector<int32_t> blev(nb), border(nb), team_of(nb), slot_of(nb), bseq(nb);
+      std::vector<uint8_t> blink(nb), has_succ(nb, 0), is_primary(nb);
+      int32_t              nblev = 0;
+      for (int64_t b = 0; b < nb; ++b)
+        {
+          int32_t l = 0;
+          for (int32_t q = 0; q < b_ng[b]; ++q)
+            {
+              int64_t kb, ke;
+              range(group_of_block(b, q), kb, ke);
+              for (int64_t k = kb; k < ke; ++k)
+                {
+                  const int32_t dg = grp_of[col[k]];
+                  if (dg >= 0 && blk_of[dg] != b)
+                    l = std::max(l, blev[blk_of[dg]] + 1);
+                }
+            }
+          blev[b]  = l;
+          nblev    = std::max(nblev, l);
+          blink[b] = b > 0 && (link[b_first[b]] & 1) && l - blev[b - 1] <= max_level_gap;
+          if (blink[b])
+            has_succ[b - 1] = 1;
+        }
+      {
+        std::vector<int64_t> start(nblev + 2, 0);
+        for (int64_t b = 0; b < nb; ++b)
+          start[blev[b] + 1]++;
+        for (int32_t l = 0; l <= nblev; ++l)
+          start[l + 1] += start[l];
+        for (int64_t b = 0; b < nb; ++b)
+          border[start[blev[b]]++] = (int32_t)b;
+      }
+      // ---- list scheduling: a chained block follows its predecessor on the same team ----
       // Every team has TS_NWIN chain slots (one window each).  A chain head takes a slot
       // of the least loaded team: `bucket[k]` lists teams believed to run k chains
       // (entries are validated when popped).
@@ -886,47 +998,51 @@ namespace glsns
         return -1;
       };
       int64_t rr = 0, n_heads = 0, n_steals = 0, n_interrupted = 0;
-      for (int64_t t = 0; t < ng; ++t)
+      for (int64_t t = 0; t < nb; ++t)
         {
-          const int32_t g = order[t];
-          const int64_t p = upper ? (int64_t)g + 1 : (int64_t)g - 1;
-          const int32_t r0 = grp_ptr[g], m = grp_m[g];
+          const int32_t b = border[t];
           // A chain runs through one window of its team.  When every window of every
-          // team is taken, a group is placed on a busy team as a GUEST: solved in list
+          // team is taken, a block is placed on a busy team as a GUEST: solved in list
           // order without touching any window, so the chains there keep their forwarding.
           int32_t ws; // team * TS_NWIN + slot
           bool    chained = false, primary = true;
-          if (link[g] && is_primary[p] && last_of[slot_of[p]] == p)
+          if (blink[b] && is_primary[b - 1] && last_of[slot_of[b - 1]] == b - 1)
             {
-              ws      = slot_of[p];
+              ws      = slot_of[b - 1];
               chained = true;
             }
           else if ((ws = take_slot()) >= 0)
-            n_interrupted += link[g]; // chain head, or the successor of a guest: a fresh window
+            n_interrupted += blink[b]; // chain head, or the successor of a guest: a fresh window
           else
             {
-              ws      = (link[g] ? warp_of[p] : (int32_t)(rr++ % NW)) * TS_NWIN;
+              ws      = (blink[b] ? team_of[b - 1] : (int32_t)(rr++ % NW)) * TS_NWIN;
               primary = false;
               ++n_steals;
             }
-          const int32_t w = ws / TS_NWIN;
-          n_heads += !link[g];
-          is_primary[g] = primary;
+          n_heads += !blink[b];
+          is_primary[b] = primary;
+          team_of[b]    = ws / TS_NWIN;
+          slot_of[b]    = ws;
           if (!chained && primary) // a new chain starts here: first row (lower) / end row (upper)
-            chain_edge[ws] = upper ? r0 + m : r0;
-          // entries that couple to the rows of this chain still held in registers: the
-          // run next to the in-group block, at most TS_WIN rows away
-          int64_t kb, ke;
-          range(g, kb, ke);
-          uint32_t fm = 0;
-          int32_t  nf = 0;
-          if (chained)
+            chain_edge[ws] = upper ? b_r0[b] + b_m[b] : b_r0[b];
+          // Entries that couple a group to the rows of its own block and, on a chain, to the
+          // chain rows still in the window: the run next to the in-group block, at most
+          // TS_WIN rows away.  They are the solver's (T and F of the block); the helpers
+          // take the rest.
+          const int32_t edge = chained ? chain_edge[ws] : (upper ? b_r0[b] + b_m[b] : b_r0[b]);
+          for (int32_t q = 0; q < b_ng[b]; ++q)
             {
+              const int64_t g  = group_of_block(b, q);
+              const int32_t r0 = grp_ptr[g], m = grp_m[g];
+              int64_t       kb, ke;
+              range(g, kb, ke);
+              uint32_t fm = 0;
+              int32_t  nf = 0;
               if (!upper)
                 for (int64_t k = ke - 1; k >= kb; --k)
                   {
                     const int32_t d = r0 - 1 - col[k];
-                    if (d >= TS_WIN || col[k] < chain_edge[ws] || grp_of[col[k]] < 0)
+                    if (d >= TS_WIN || col[k] < edge || grp_of[col[k]] < 0)
                       break;
                     fm |= 1u << d;
                     ++nf;
@@ -935,91 +1051,99 @@ namespace glsns
                 for (int64_t k = kb; k < ke; ++k)
                   {
                     const int32_t d = col[k] - (r0 + m);
-                    if (d >= TS_WIN || col[k] >= chain_edge[ws] || grp_of[col[k]] < 0)
+                    if (d >= TS_WIN || col[k] >= edge || grp_of[col[k]] < 0)
                       break;
                     fm |= 1u << d;
                     ++nf;
                   }
-              // rows between the predecessor and this group (diagonal-only ones): the
-              // kernel shifts its register window by that much first
-              gapv[g] = (int32_t)(upper ? grp_ptr[p] - (r0 + m) : r0 - (grp_ptr[p] + grp_m[p]));
+              fmask[g] = (int32_t)fm;
+              e_off[g] = (int32_t)((upper ? kb + nf : kb) - rowptr[grp_ptr[g]]);
+              cnt[g]   = (int32_t)(ke - kb - nf);
             }
-          else
-            gapv[g] = 0;
-          fmask[g] = (int32_t)fm;
-          e_off[g] = (int32_t)((upper ? kb + nf : kb) - rowptr[grp_ptr[g]]);
-          cnt[g]   = (int32_t)(ke - kb - nf);
-          warp_of[g] = w;
-          slot_of[g] = ws;
           if (primary)
             {
-              if (has_succ[g])
-                last_of[ws] = g; // (last group of the chain in this window so far)
+              if (has_succ[b])
+                last_of[ws] = b; // (last block of the chain in this window so far)
               else
                 { // the chain ends here: the window is free again
                   last_of[ws] = -1;
-                  --n_live[w];
-                  bucket[n_live[w]].push_back(w);
+                  --n_live[team_of[b]];
+                  bucket[n_live[team_of[b]]].push_back(team_of[b]);
                 }
             }
         }
       if (getenv("GLSNS_TRSV_DEBUG"))
         fprintf(stderr,
-                "trsv_analyse %s: %lld groups, %d levels, %lld teams, %lld chain heads, %lld taken "
-                "as guests on busy teams, %lld chains restarted\n",
-                upper ? "upper" : "lower", (long long)ng, nlev + 1, (long long)NW, (long long)n_heads,
-                (long long)n_steals, (long long)n_interrupted);
-      // item lists: per team one solver list (one item per group) and K helper lists
-      // (the groups round-robin, <= TS_CH entries per item)
+                "trsv_analyse %s: %lld groups, %d levels; %lld blocks, %d block levels, %lld teams, "
+                "%lld chain heads, %lld taken as guests on busy teams, %lld chains restarted\n",
+                upper ? "upper" : "lower", (long long)ng, nlev + 1, (long long)nb, nblev + 1,
+                (long long)NW, (long long)n_heads, (long long)n_steals, (long long)n_interrupted);
+      // ---- item lists: per team one solver list (one item per block) and K helper lists
+      // (the team's groups round-robin, <= TS_CH entries per item) ----
       const int64_t        NWARP = NW * (K + 1);
-      std::vector<int64_t> n_it(NWARP + 1, 0), team_cnt(NW, 0);
-      std::vector<int32_t> seq_in_team(ng);
-      for (int64_t t = 0; t < ng; ++t)
+      std::vector<int64_t> n_it(NWARP + 1, 0), team_blocks(NW, 0), team_groups(NW, 0);
+      std::vector<int32_t> helper_of(ng);
+      for (int64_t t = 0; t < nb; ++t)
         {
-          const int32_t g  = order[t];
-          const int64_t tm = warp_of[g];
-          const int64_t j  = team_cnt[tm]++;
-          seq_in_team[g]   = (int32_t)j;
+          const int32_t b  = border[t];
+          const int64_t tm = team_of[b];
+          bseq[b]          = (int32_t)team_blocks[tm]++;
           n_it[tm * (K + 1) + 0 + 1] += 1;
-          n_it[tm * (K + 1) + 1 + (j % K) + 1] += std::max<int64_t>(1, (cnt[g] + TS_CH - 1) / TS_CH);
+          for (int32_t q = 0; q < b_ng[b]; ++q)
+            {
+              const int64_t g = group_of_block(b, q);
+              helper_of[g]    = (int32_t)(team_groups[tm]++ % K);
+              n_it[tm * (K + 1) + 1 + helper_of[g] + 1] += std::max<int64_t>(1, (cnt[g] + TS_CH - 1) / TS_CH);
+            }
         }
       for (int64_t w = 0; w < NWARP; ++w)
         n_it[w + 1] += n_it[w];
-      std::vector<TrsvItem> items((size_t)n_it[NWARP]);
+      std::vector<TrsvItem> items((size_t)n_it[NWARP]), gdesc((size_t)ng);
       std::vector<int64_t>  fill(n_it.begin(), n_it.end() - 1);
-      for (int64_t t = 0; t < ng; ++t)
+      int64_t               n_gdesc = 0;
+      for (int64_t t = 0; t < nb; ++t)
         {
-          const int32_t g = order[t];
-          const int64_t i = grp_ptr[g];
-          const int32_t m = grp_m[g], len = (int32_t)(rowptr[i + 1] - rowptr[i]);
-          const int64_t tm = warp_of[g], j = seq_in_team[g];
+          const int32_t b  = border[t];
+          const int64_t tm = team_of[b];
           {
             TrsvItem &it = items[(size_t)fill[tm * (K + 1)]++];
-            it.rs0 = rowptr[i], it.r0 = (int32_t)i, it.len = len, it.e_off = 0;
-            it.flags = m | IT_SOLVER | (is_primary[g] ? 0 : IT_GUEST) | ((slot_of[g] % TS_NWIN) << 12);
-            it.nlow  = (int32_t)(diag[i] - rowptr[i]);
-            it.fmask = fmask[g];
+            it.rs0 = n_gdesc, it.r0 = b_r0[b], it.len = b_ng[b], it.e_off = 0, it.nlow = 0, it.fmask = 0;
+            it.flags = b_m[b] | IT_SOLVER | (is_primary[b] ? 0 : IT_GUEST) | ((slot_of[b] % TS_NWIN) << 12);
           }
-          const int32_t nchunk = std::max(1, (cnt[g] + TS_CH - 1) / TS_CH);
-          for (int32_t c = 0; c < nchunk; ++c)
+          for (int32_t q = 0; q < b_ng[b]; ++q)
             {
-              TrsvItem  &it   = items[(size_t)fill[tm * (K + 1) + 1 + (j % K)]++];
-              const int  cntc = std::max(0, std::min(TS_CH, cnt[g] - c * TS_CH));
-              const bool last = c == nchunk - 1;
-              it.rs0   = rowptr[i];
-              it.r0    = (int32_t)i;
-              it.len   = len;
-              it.e_off = e_off[g] + c * TS_CH;
-              it.flags = m | (last ? IT_LAST : 0) | (cntc << 16);
-              it.nlow  = (int32_t)(diag[i] - rowptr[i]);
-              it.fmask = 0;
+              const int64_t g = group_of_block(b, q);
+              const int64_t i = grp_ptr[g];
+              const int32_t m = grp_m[g], len = (int32_t)(rowptr[i + 1] - rowptr[i]);
+              {
+                TrsvItem &gd = gdesc[(size_t)n_gdesc++];
+                gd.rs0 = rowptr[i], gd.r0 = (int32_t)i, gd.len = len, gd.e_off = 0, gd.flags = m;
+                gd.nlow = (int32_t)(diag[i] - rowptr[i]), gd.fmask = fmask[g];
+              }
+              const int32_t nchunk = std::max(1, (cnt[g] + TS_CH - 1) / TS_CH);
+              for (int32_t c = 0; c < nchunk; ++c)
+                {
+                  TrsvItem  &it   = items[(size_t)fill[tm * (K + 1) + 1 + helper_of[g]]++];
+                  // (the entries solved last come last: the upper sweep takes the chunks of a
+                  // row from the far end, so that a helper waits on the group's final item only)
+                  const int  ch   = upper ? nchunk - 1 - c : c;
+                  const int  cntc = std::max(0, std::min(TS_CH, cnt[g] - ch * TS_CH));
+                  const bool last = c == nchunk - 1;
+                  it.rs0   = rowptr[i];
+                  it.r0    = (int32_t)i;
+                  it.len   = len;
+                  it.e_off = e_off[g] + ch * TS_CH;
+                  it.flags = m | (last ? IT_LAST : 0) | (cntc << 16);
+                  it.nlow  = (int32_t)(diag[i] - rowptr[i]);
+                  it.fmask = (bseq[b] << 4) | (int32_t)(i - b_r0[b]); // where its totals go
+                }
             }
         }
       std::vector<int32_t> &row_warp = upper ? ctx->trsv_row_warp_u : ctx->trsv_row_warp_l;
       row_warp.assign((size_t)n, -1);
       for (int64_t g = 0; g < ng; ++g)
         for (int32_t a = 0; a < grp_m[g]; ++a)
-          row_warp[grp_ptr[g] + a] = warp_of[g] | (fmask[g] ? 1 << 30 : 0);
+          row_warp[grp_ptr[g] + a] = team_of[blk_of[g]] | (fmask[g] ? 1 << 30 : 0);
       // stream layout: the blobs of one warp back to back, warps one after another
       const int64_t        nit = n_it[NWARP];
       std::vector<int64_t> blob_off((size_t)nit);
@@ -1038,15 +1162,16 @@ namespace glsns
               blob_off[(size_t)k] = off;
               off += 16 * (int64_t)b16;
               const int64_t j = k - n_it[w];
-              if (j < TS_NSH)
+              if (j < TS_NSLOT)
                 D.first16[j] = b16;
               else
-                next16[(size_t)(k - TS_NSH)] = b16; // (helper lists; the solver's blobs have one size)
+                next16[(size_t)(k - TS_NSLOT)] = b16;
             }
         }
       sw.n_items      = nit;
       sw.stream_bytes = off;
       GLSNS_TRY(dev_upload(ctx, sw.items, items.data(), items.size()));
+      GLSNS_TRY(dev_upload(ctx, sw.gdesc, gdesc.data(), gdesc.size()));
       GLSNS_TRY(dev_upload(ctx, sw.blob_off, blob_off.data(), blob_off.size()));
       GLSNS_TRY(dev_upload(ctx, sw.next16, next16.data(), next16.size()));
       GLSNS_TRY(dev_upload(ctx, sw.dir, reinterpret_cast<const unsigned char *>(dirv.data()),
@@ -1085,14 +1210,16 @@ namespace glsns
       {
         const int64_t nit = ctx->trsv_l.n_items;
         trsv_pack_values_kernel<false><<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-          nit, ctx->trsv_l.items.p, ctx->trsv_l.blob_off.p, ctx->lu.p, ctx->trsv_l.stream.p);
+          nit, ctx->trsv_l.items.p, ctx->trsv_l.gdesc.p, ctx->trsv_l.blob_off.p, ctx->lu.p,
+          ctx->trsv_l.stream.p);
         ctx->kernel_launches++;
       }
     if (ctx->trsv_u.n_items)
       {
         const int64_t nit = ctx->trsv_u.n_items;
         trsv_pack_values_kernel<true><<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-          nit, ctx->trsv_u.items.p, ctx->trsv_u.blob_off.p, ctx->lu.p, ctx->trsv_u.stream.p);
+          nit, ctx->trsv_u.items.p, ctx->trsv_u.gdesc.p, ctx->trsv_u.blob_off.p, ctx->lu.p,
+          ctx->trsv_u.stream.p);
         ctx->kernel_launches++;
       }
     GLSNS_CUDA(ctx, cudaGetLastError());

@@ -1,7 +1,9 @@
-"""Where does the time of the triangular solves go?  Traces one ILU apply (publish time of every
-row in both sweeps, tools: glsns_ilu_apply_trace) and walks the dependency DAG on the host:
-for every group, the wait between its last-arriving input and its own publication, split by
-whether that input came from the same warp (register window) or through L2.
+"""Where does the time of the triangular solves go?  Traces one ILU apply (tools:
+glsns_ilu_apply_trace: when every row was published, when its totals reached the team's mailbox)
+and walks the dependency DAG on the host, block by block (a block = the rows one solver step
+publishes together): the wait between a block's last-arriving input and its publication, split
+into the helper part (input published -> totals posted) and the solver part (posted -> published),
+by whether that input came from the same team (shared-memory window) or through L2.
     python tools/trsv_trace.py N"""
 import json, sys
 sys.path.insert(0, ".")
@@ -17,75 +19,80 @@ x = np.random.default_rng(5).standard_normal(m.n_dofs)
 for _ in range(3):
     z, tl, tu, wl, wu = hp.ilu_apply_trace(x)
 rp, col, N = m.array("row_ptr"), m.array("col_idx"), m.n_dofs
-lens = np.diff(rp)
+pct = lambda v: [float(np.percentile(v, p)) for p in (10, 50, 90)] + [len(v)] if len(v) else None
 out = {"n": n}
-for name, t, w, upper in (("lower", tl, wl, False), ("upper", tu, wu, True)):
+for name, t, tp, w, upper in (("lower", tl, hp.last_trace_posts[0], wl, False),
+                              ("upper", tu, hp.last_trace_posts[1], wu, True)):
     ok = w >= 0
-    t = t.astype(np.int64); t0 = t[ok].min(); t = t - t0
-    warp = w & 0xFFFFFF; chained = (w >> 30) & 1
-    # group heads: first row of each group = rows whose predecessor row has a different publish... use patterns
+    t = t.astype(np.int64); t0 = t[ok].min(); t = t - t0; tp = tp.astype(np.int64) - t0
+    team = w & 0xFFFFFF
+    # blocks: runs of adjacent rows of one team published within 100 ns of each other
     rows = np.nonzero(ok)[0]
-    # per row: last-arriving dependency
-    dt_same, dt_other, crit_is_same = [], [], []
-    other_chained, other_head, other_dist = [], [], []
-    pure = {1000: [], 3000: [], 10000: []}  # chain step when every other-warp input is older than .. ns
-    step = max(1, len(rows) // 60000)
-    for i in rows[::step]:
-        c = col[rp[i]:rp[i + 1]]
-        c = c[(c > i) & (c < N)] if upper else c[c < i]
+    new = np.ones(len(rows), dtype=bool)
+    new[1:] = (np.diff(rows) != 1) | (team[rows[1:]] != team[rows[:-1]]) | (np.abs(np.diff(t[rows])) > 100)
+    bid = np.cumsum(new) - 1
+    blk = -np.ones(N, dtype=np.int64); blk[rows] = bid
+    nb = int(bid[-1]) + 1
+    bstart = rows[new]; bend = np.append(rows[np.nonzero(new)[0][1:] - 1], rows[-1]) + 1
+    info = {}
+
+    def block_inputs(b):
+        if b in info:
+            return info[b]
+        r0, r1 = bstart[b], bend[b]
+        c = col[rp[r0]:rp[r1]]
+        c = c[(c >= r1) & (c < N)] if upper else c[c < r0]
         c = c[w[c] >= 0]
-        # drop own group (rows published at the same instant by the same warp adjacent)
-        c = c[np.abs(c - i) >= 4] if len(c) else c
-        if not len(c):
+        res = None
+        if len(c):
+            same = team[c] == team[r0]
+            cs, co = c[same], c[~same]
+            js = int(cs[np.argmax(t[cs])]) if len(cs) else -1
+            jo = int(co[np.argmax(t[co])]) if len(co) else -1
+            res = (js, jo, int(t[r0:r1].max()), int(tp[r0:r1].max()))
+        info[b] = res
+        return res
+
+    A = {k: [] for k in ("chain_total", "chain_after_post", "cross_total", "cross_helper", "cross_solver",
+                         "cross_input_age_when_chain_last", "rows_per_block")}
+    for b in range(0, nb, max(1, nb // 40000)):
+        A["rows_per_block"].append(bend[b] - bstart[b])
+        r = block_inputs(b)
+        if r is None:
             continue
-        j = c[np.argmax(t[c])]
-        d = t[i] - t[j]
-        same = warp[j] == warp[i]
-        (dt_same if same else dt_other).append(d)
-        if not same:
-            (other_chained if chained[i] else other_head).append(d)
-            other_dist.append(abs(int(j) - int(i)))
-        if same:
-            oth = c[warp[c] != warp[i]]
-            age = t[j] - (t[oth].max() if len(oth) else -10**9)   # how long before the same-warp input
-            for k in pure:
-                if age > k:
-                    pure[k].append(d)
-    ds, do = np.array(dt_same), np.array(dt_other)
-    out[name] = {"span_us": float(t[ok].max() / 1e3), "rows_sampled": len(ds) + len(do),
-                 "frac_last_input_same_warp": len(ds) / max(1, len(ds) + len(do)),
-                 "frac_rows_chained": float(chained[ok].mean()),
-                 "wait_after_last_input_same_warp_ns": [float(np.percentile(ds, p)) for p in (10, 50, 90)] if len(ds) else None,
-                 "pure_chain_step_ns_p10_p50_p90_by_min_age_of_other_inputs":
-                     {k: [float(np.percentile(v, p)) for p in (10, 50, 90)] + [len(v)] for k, v in pure.items() if len(v)},
-                 "other_team_last_input:_chained_rows_(n,p50_ns)_vs_chain_heads_(n,p50_ns)":
-                     [len(other_chained), float(np.median(other_chained)) if other_chained else None,
-                      len(other_head), float(np.median(other_head)) if other_head else None],
-                 "other_team_last_input_row_distance_p10_p50_p90":
-                     [float(np.percentile(other_dist, p)) for p in (10, 50, 90)] if other_dist else None,
-                 "wait_after_last_input_other_warp_ns": [float(np.percentile(do, p)) for p in (10, 50, 90)] if len(do) else None}
-    # critical path by time: walk back from the last published row through last-arriving inputs
-    i = int(np.argmax(np.where(ok, t, -1))); hops_same = hops_other = 0; time_same = time_other = 0
-    while True:
-        c = col[rp[i]:rp[i + 1]]
-        c = c[(c > i) & (c < N)] if upper else c[c < i]
-        c = c[w[c] >= 0]
-        if not len(c):
-            break
-        j = int(c[np.argmax(t[c])])
-        if warp[j] == warp[i]:
-            hops_same += 1; time_same += t[i] - t[j]
+        js, jo, tpub, tpost = r
+        ts_, to_ = (t[js] if js >= 0 else -10**12), (t[jo] if jo >= 0 else -10**12)
+        if ts_ >= to_:
+            A["chain_total"].append(tpub - ts_); A["chain_after_post"].append(tpub - tpost)
+            if jo >= 0:
+                A["cross_input_age_when_chain_last"].append(ts_ - to_)
         else:
-            hops_other += 1; time_other += t[i] - t[j]
-        i = j
-    out[name]["critical_path"] = {"same_warp_hops": hops_same, "same_warp_us": time_same / 1e3,
-                                  "other_warp_hops": hops_other, "other_warp_us": time_other / 1e3}
+            A["cross_total"].append(tpub - to_); A["cross_helper"].append(tpost - to_); A["cross_solver"].append(tpub - tpost)
+    o = {"span_us": float(t[ok].max() / 1e3), "blocks": nb, "mean_rows_per_block": float(np.mean(A["rows_per_block"]))}
+    for k in A:
+        if k != "rows_per_block":
+            o[k + "_ns_p10_p50_p90_n"] = pct(np.array(A[k]))
+    # critical path by time: walk back from the last published block through last-arriving inputs
+    b = int(blk[int(np.argmax(np.where(ok, t, -1)))])
+    hs = ho = 0; ts = to = th = tsol = 0
+    while True:
+        r = block_inputs(b)
+        if r is None:
+            break
+        js, jo, tpub, tpost = r
+        if jo < 0 or (js >= 0 and t[js] >= t[jo]):
+            hs += 1; ts += tpub - t[js]; b = int(blk[js])
+        else:
+            ho += 1; to += tpub - t[jo]; th += tpost - t[jo]; tsol += tpub - tpost; b = int(blk[jo])
+    o["critical_path"] = {"chain_hops": hs, "chain_us": ts / 1e3, "cross_hops": ho, "cross_us": to / 1e3,
+                          "cross_helper_part_us": th / 1e3, "cross_solver_part_us": tsol / 1e3}
+    out[name] = o
 for name, pl in zip(("lower", "upper"), hp.last_trace_polls):
     nw = min(len(pl) // 8, 148 * 4)
     st = pl[:nw * 8].reshape(nw, 8).astype(np.float64)
     busy = st[st[:, 6] > 0]
     tot = busy[:, :5].sum(axis=0)
-    out[name]["solver_cycles_per_group_[ring_wait,window,mailbox_wait,triangle_publish,release_refill]"] = [float(v) for v in tot / busy[:, 6].sum()]
+    out[name]["solver_cycles_per_block_[ring_wait,window,mailbox_wait,totals_publish,release_refill]"] = [float(v) for v in tot / busy[:, 6].sum()]
     k = int(np.argmax(st[:, 6]))
-    out[name]["busiest_solver_groups_and_cycles_per_group"] = [float(st[k, 6])] + [float(v / st[k, 6]) for v in st[k, :5]]
+    out[name]["busiest_solver_blocks_and_cycles_per_block"] = [float(st[k, 6])] + [float(v / st[k, 6]) for v in st[k, :5]]
 print(json.dumps(out, indent=1))
