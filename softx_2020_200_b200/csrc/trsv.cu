@@ -322,9 +322,10 @@ namespace glsns
     __global__ void __launch_bounds__(512, 1)
     trsv_team_kernel(const TrsvWarpDir *__restrict__ dir, const unsigned char *__restrict__ stream,
                      const double *__restrict__ rhs_vec, double *x, int *counters,
-                     unsigned long long *trace, const int64_t trace_n, const int K)
+                     unsigned long long *trace, const int64_t trace_n, const int K_gate /* helpers per team */)
     {
       extern __shared__ __align__(128) unsigned char smem_all[];
+      const int K = K_gate;
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
       const int team_in_cta = warp / (K + 1), role = warp - team_in_cta * (K + 1);
       const int n_teams_cta = (blockDim.x >> 5) / (K + 1);
@@ -537,6 +538,7 @@ namespace glsns
         acc[a] = 0;
       int      slotG = 0, slotR = 0;
       unsigned phaseG = 0;
+      unsigned long long n_rounds = 0, n_polled = 0, n_waited = 0; // debugging aid (trace)
       // one pipeline step: G(it) into set KG, R(it-2) from set (KG+1)%3
       auto step = [&](auto KG, const int64_t it) {
         constexpr int      kg = decltype(KG)::value, kr = (kg + 1) % 3;
@@ -599,6 +601,12 @@ namespace glsns
                     }
                 if (!__any_sync(0xffffffffu, pendG != 0))
                   break;
+                if (trace)
+                  {
+                    n_waited += spins == 0;
+                    ++n_rounds;
+                    n_polled += __popc(pendG);
+                  }
 #pragma unroll
                 for (int u = 0; u < TS_U; ++u)
                   if (pendG & (1u << u))
@@ -695,6 +703,19 @@ namespace glsns
             step(std::integral_constant<int, 1>(), it + 1);
           if (it + 2 < n_items + 2)
             step(std::integral_constant<int, 2>(), it + 2);
+        }
+      if (trace && (team + 1) * 8 <= trace_n)
+        { // per helper lane: items that had to wait, polling rounds, entries re-read
+          for (int o = 16; o > 0; o >>= 1)
+            n_polled += __shfl_xor_sync(0xffffffffu, n_polled, o);
+          if (lane == 0)
+            {
+              unsigned long long *hc = trace + 2 * trace_n + 8 * (int64_t)gridDim.x * n_teams_cta + team * 4;
+              atomicAdd(hc + 0, (unsigned long long)n_items);
+              atomicAdd(hc + 1, n_waited);
+              atomicAdd(hc + 2, n_rounds);
+              atomicAdd(hc + 3, n_polled);
+            }
         }
     }
 
@@ -819,7 +840,7 @@ namespace glsns
     const TrsvConfig cfg = trsv_config();
     ctx->trsv_grid       = ctx->n_sm;
     const int64_t NW     = (int64_t)ctx->trsv_grid * cfg.teams; // teams: one chain list each
-    const int32_t max_level_gap = getenv("GLSNS_TRSV_GAP") ? atoi(getenv("GLSNS_TRSV_GAP")) : 2;
+    const int32_t max_level_gap = getenv("GLSNS_TRSV_GAP") ? atoi(getenv("GLSNS_TRSV_GAP")) : 1;
     const int32_t max_block     = std::max(1, std::min(TS_BG, getenv("GLSNS_TRSV_BLOCK") ? atoi(getenv("GLSNS_TRSV_BLOCK")) : TS_BG));
     const int     K      = cfg.helpers;
 

@@ -19,6 +19,12 @@ x = np.random.default_rng(5).standard_normal(m.n_dofs)
 for _ in range(3):
     z, tl, tu, wl, wu = hp.ilu_apply_trace(x)
 rp, col, N = m.array("row_ptr"), m.array("col_idx"), m.n_dofs
+if len(sys.argv) > 2:  # raw trace for offline analysis: ns offsets from the first publication of each sweep
+    def rel(t, ref):
+        t = t.astype(np.int64); return np.where(t > 0, t - ref, -1).astype(np.int32)
+    r0l, r0u = int(tl[wl >= 0].min()), int(tu[wu >= 0].min())
+    np.savez_compressed(sys.argv[2], tl=rel(tl, r0l), tu=rel(tu, r0u), pl=rel(hp.last_trace_posts[0], r0l),
+                        pu=rel(hp.last_trace_posts[1], r0u), wl=wl, wu=wu)
 pct = lambda v: [float(np.percentile(v, p)) for p in (10, 50, 90)] + [len(v)] if len(v) else None
 out = {"n": n}
 for name, t, tp, w, upper in (("lower", tl, hp.last_trace_posts[0], wl, False),
@@ -88,11 +94,13 @@ for name, t, tp, w, upper in (("lower", tl, hp.last_trace_posts[0], wl, False),
                           "cross_helper_part_us": th / 1e3, "cross_solver_part_us": tsol / 1e3}
     out[name] = o
 for name, pl in zip(("lower", "upper"), hp.last_trace_polls):
-    nw = min(len(pl) // 8, 148 * 4)
+    nw = min(len(pl) // 12, 148 * 3)
     st = pl[:nw * 8].reshape(nw, 8).astype(np.float64)
     busy = st[st[:, 6] > 0]
     tot = busy[:, :5].sum(axis=0)
     out[name]["solver_cycles_per_block_[ring_wait,window,mailbox_wait,totals_publish,release_refill]"] = [float(v) for v in tot / busy[:, 6].sum()]
+    hc = pl[nw * 8:nw * 12].reshape(nw, 4).astype(np.float64).sum(axis=0)
+    out[name]["helpers_[items,items_that_waited,poll_rounds,entries_re_read]"] = [float(v) for v in hc]
     k = int(np.argmax(st[:, 6]))
     out[name]["busiest_solver_blocks_and_cycles_per_block"] = [float(st[k, 6])] + [float(v / st[k, 6]) for v in st[k, :5]]
 print(json.dumps(out, indent=1))
