@@ -959,11 +959,21 @@ namespace glsns
       // block levels and block links (block ids run in sweep order: the predecessor of the
       // first group of block b is the last group of block b - 1)
       std::vector<int32_t> blev(nb), border(nb), team_of(nb), slot_of(nb), bseq(nb);
+      std::vector<int64_t> best(nb);
       std::vector<uint8_t> blink(nb), has_succ(nb, 0), is_primary(nb);
       int32_t              nblev = 0;
+      // `best`: when a block can be solved at the earliest, in units of one chain step, if a
+      // value that travels to another team (L2, a helper's gather and reduction, the mailbox)
+      // takes cost_cross of them; the lists are ordered by it.  With both costs 1 (the
+      // default) it is the block level.  Weighted orders (cross = 3: where the DAG is mostly
+      // chains the front advances several levels in the time a level takes elsewhere) were
+      // measured: -4 % at 32^3 cells, +5 % at 64^3.
+      const int64_t cost_chain = getenv("GLSNS_TRSV_COST_CHAIN") ? atoi(getenv("GLSNS_TRSV_COST_CHAIN")) : 1;
+      const int64_t cost_cross = getenv("GLSNS_TRSV_COST_CROSS") ? atoi(getenv("GLSNS_TRSV_COST_CROSS")) : 1;
       for (int64_t b = 0; b < nb; ++b)
         {
           int32_t l = 0;
+          int64_t e = 0;
           for (int32_t q = 0; q < b_ng[b]; ++q)
             {
               int64_t kb, ke;
@@ -972,24 +982,27 @@ namespace glsns
                 {
                   const int32_t dg = grp_of[col[k]];
                   if (dg >= 0 && blk_of[dg] != b)
-                    l = std::max(l, blev[blk_of[dg]] + 1);
+                    {
+                      const int32_t db = blk_of[dg];
+                      l                = std::max(l, blev[db] + 1);
+                      e = std::max(e, best[db] + (db == b - 1 && (link[b_first[b]] & 1) ? cost_chain : cost_cross));
+                    }
                 }
             }
           blev[b]  = l;
+          best[b]  = e;
           nblev    = std::max(nblev, l);
           blink[b] = b > 0 && (link[b_first[b]] & 1) && l - blev[b - 1] <= max_level_gap;
           if (blink[b])
             has_succ[b - 1] = 1;
         }
-      {
-        std::vector<int64_t> start(nblev + 2, 0);
-        for (int64_t b = 0; b < nb; ++b)
-          start[blev[b] + 1]++;
-        for (int32_t l = 0; l <= nblev; ++l)
-          start[l + 1] += start[l];
-        for (int64_t b = 0; b < nb; ++b)
-          border[start[blev[b]]++] = (int32_t)b;
-      }
+      // (a key that grows along every dependency keeps the lists dead-lock free: the blocked
+      // block with the smallest key waits on a block with a smaller one, which is some team's
+      // current or earlier item)
+      for (int64_t b = 0; b < nb; ++b)
+        border[b] = (int32_t)b;
+      std::stable_sort(border.begin(), border.end(),
+                       [&](int32_t x, int32_t y) { return best[x] < best[y]; });
       // ---- list scheduling: a chained block follows its predecessor on the same team ----
       // Every team has TS_NWIN chain slots (one window each).  A chain head takes a slot
       // of the least loaded team: `bucket[k]` lists teams believed to run k chains
