@@ -156,6 +156,14 @@ typedef struct
 } glsns_mesh_desc;
 
 /* `linear solver` subsection (source/core/parameters.cc:507-559). */
+typedef enum
+{
+  GLSNS_SOLVER_GMRES    = 0, /* method = gmres:    solve_system_GMRES,    gls_navier_stokes.cc:1242-1289 */
+  GLSNS_SOLVER_BICGSTAB = 1  /* method = bicgstab: solve_system_BiCGStab, gls_navier_stokes.cc:1291-1340 */
+  /* method = amg (solve_system_AMG, Trilinos ML) is not built: the host mirror throws the
+     reference's "This solver is not allowed" */
+} glsns_solver_method;
+
 typedef struct
 {
   double  relative_residual; /* default 1e-3  */
@@ -165,6 +173,7 @@ typedef struct
   int32_t ilu_fill;          /* default 0 (only 0 is built so far) */
   double  ilu_atol;          /* default 1e-8  */
   double  ilu_rtol;          /* default 1.0   */
+  int32_t method;            /* glsns_solver_method, default GLSNS_SOLVER_GMRES */
 } glsns_linear_solver_params;
 
 typedef struct

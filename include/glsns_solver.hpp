@@ -683,8 +683,10 @@ namespace glsns
       const double relative_residual = nsparam.linear_solver.relative_residual;
       if (nsparam.linear_solver.solver == Parameters::LinearSolver::SolverType::gmres)
         solve_system_GMRES(initial_step, absolute_residual, relative_residual, renewed_matrix);
+      else if (nsparam.linear_solver.solver == Parameters::LinearSolver::SolverType::bicgstab)
+        solve_system_BiCGStab(initial_step, absolute_residual, relative_residual, renewed_matrix);
       else
-        // bicgstab / amg are not built on the device; the reference's own message for an
+        // amg (Trilinos ML) is not built on the device; the reference's own message for an
         // unknown method (:1158)
         throw std::runtime_error("This solver is not allowed");
     }
@@ -744,8 +746,27 @@ namespace glsns
 
     // solve_system_GMRES (:1242-1289)
     void
-    solve_system_GMRES(const bool /*initial_step*/, const double absolute_residual,
+    solve_system_GMRES(const bool initial_step, const double absolute_residual,
                        const double relative_residual, const bool renewed_matrix)
+    {
+      solve_system_Krylov(GLSNS_SOLVER_GMRES, "solve_system_GMRES", initial_step,
+                          absolute_residual, relative_residual, renewed_matrix);
+    }
+
+    // solve_system_BiCGStab (:1291-1340)
+    void
+    solve_system_BiCGStab(const bool initial_step, const double absolute_residual,
+                          const double relative_residual, const bool renewed_matrix)
+    {
+      solve_system_Krylov(GLSNS_SOLVER_BICGSTAB, "solve_system_BiCGStab", initial_step,
+                          absolute_residual, relative_residual, renewed_matrix);
+    }
+
+    // the body the two share in the reference (tolerance rule, ILU renewal, printing, distribute)
+    void
+    solve_system_Krylov(const glsns_solver_method method, const char *what,
+                        const bool /*initial_step*/, const double absolute_residual,
+                        const double relative_residual, const bool renewed_matrix)
     {
       const double linear_solver_tolerance =
         std::max(relative_residual * system_rhs.l2_norm(), absolute_residual);
@@ -766,11 +787,12 @@ namespace glsns
       p.ilu_fill          = (int)nsparam.linear_solver.ilu_precond_fill;
       p.ilu_atol          = nsparam.linear_solver.ilu_precond_atol;
       p.ilu_rtol          = nsparam.linear_solver.ilu_precond_rtol;
+      p.method            = (int32_t)method;
       const glsns_status s =
         glsns_solve_linear_system(ctx, &p, 0, newton_update.data(), &last_solve);
       if (s == GLSNS_ERR_NO_CONVERGENCE)
         throw NoConvergence(last_solve.iterations, last_solve.true_residual);
-      check(s, "solve_system_GMRES");
+      check(s, what);
       if (nsparam.linear_solver.verbosity != Parameters::Verbosity::quiet)
         pcout << "  -Iterative solver took : " << last_solve.iterations << " steps " << std::endl;
     }

@@ -17,6 +17,9 @@ What is restated here (numpy) and in gls_oracle.c (the heavy loops), with the re
 * assembleGLS (:231-777)                       -> gls_oracle.c: glso_assemble
 * setup_ILU (:1161-1176)                       -> gls_oracle.c: glso_ilu0
 * solve_system_GMRES (:1242-1289)              -> gls_oracle.c: glso_gmres
+* solve_system_BiCGStab (:1291-1340)           -> bicgstab (PARITY UNPINNED: no reference test or
+  example uses `method = bicgstab`; AztecOO's AZ_bicgstab is restated from the published
+  right-preconditioned algorithm, van der Vorst 1992 as in the Aztec user's guide)
 * NewtonNonLinearSolver::solve (include/core/newton_non_linear_solver.h:76-139) -> newton_solve
 * calculate_L2_error (source/solvers/navier_stokes_base.cc:255-380)              -> l2_error
 * bdf_coefficients (source/core/bdf.cc:46-75), sdirk_coefficients (source/core/sdirk.cc:11-44)
@@ -496,18 +499,70 @@ def gmres(mesh, val, lu, dp, b, tol, max_iters=1000, restart=30, block_ptr=None)
     return x, it.value, tr.value, st == 0, hist[:it.value + 1]
 
 
+def bicgstab(mesh, val, lu, dp, b, tol, max_iters=1000, block_ptr=None):
+    """solve_system_BiCGStab (gls_navier_stokes.cc:1291-1340): TrilinosWrappers::SolverBicgstab ->
+    AztecOO AZ_bicgstab, right-preconditioned with the ILU, zero initial guess, stop on ||r||_2 < tol.
+    PARITY UNPINNED (see the module header).  Returns (x, iterations, true_residual, converged)."""
+    n = mesh.ndof
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(n)
+    r = b.copy()
+    rt = b.copy()
+    rho = float(rt @ r)
+    res = math.sqrt(float(r @ r))
+    rho_old = alpha = omega = 1.0
+    p = v = None
+    it = 0
+    ok = res < tol
+    while not ok and it < max_iters:
+        if rho == 0.0 or omega == 0.0:
+            break
+        if it == 0:
+            p = r.copy()
+        else:
+            beta = (rho / rho_old) * (alpha / omega)
+            p = p - omega * v
+            p = r + beta * p
+        ph = ilu_apply(mesh, lu, dp, p, block_ptr)
+        v = spmv(mesh, val, ph)
+        d = float(rt @ v)
+        if d == 0.0:
+            break
+        alpha = rho / d
+        x = x + alpha * ph
+        r = r - alpha * v                      # s
+        sh = ilu_apply(mesh, lu, dp, r, block_ptr)
+        t = spmv(mesh, val, sh)
+        tt = float(t @ t)
+        omega = float(r @ t) / tt if tt != 0.0 else 0.0
+        x = x + omega * sh
+        r = r - omega * t
+        rho_old, rho = rho, float(rt @ r)
+        res = math.sqrt(float(r @ r))
+        it += 1
+        ok = res < tol
+    tr = float(np.linalg.norm(b - spmv(mesh, val, x)))
+    return x, it, tr, ok
+
+
 class NoConvergence(RuntimeError):
     """SolverControl::NoConvergence stand-in."""
 
 
 def solve_linear_system(mesh, val, rhs, rel=1e-3, abs_=1e-8, max_iters=1000, ilu_atol=1e-8,
-                        ilu_rtol=1.0, restart=30, block_ptr=None):
-    """solve_system_GMRES (gls_navier_stokes.cc:1242-1289). Returns (newton_update, iters, res)."""
+                        ilu_rtol=1.0, restart=30, block_ptr=None, method="gmres"):
+    """solve_system_GMRES / solve_system_BiCGStab (gls_navier_stokes.cc:1242-1340).
+    Returns (newton_update, iters, res)."""
     tol = max(rel * float(np.linalg.norm(rhs)), abs_)
     lu, dp = ilu0(mesh, val, ilu_atol, ilu_rtol, block_ptr)
-    x, it, res, ok, _ = gmres(mesh, val, lu, dp, rhs, tol, max_iters, restart, block_ptr)
+    if method == "bicgstab":
+        x, it, res, ok = bicgstab(mesh, val, lu, dp, rhs, tol, max_iters, block_ptr)
+    elif method == "gmres":
+        x, it, res, ok, _ = gmres(mesh, val, lu, dp, rhs, tol, max_iters, restart, block_ptr)
+    else:
+        raise RuntimeError("This solver is not allowed")     # :1158
     if not ok:
-        raise NoConvergence("GMRES did not converge in %d iterations" % it)
+        raise NoConvergence("%s did not converge in %d iterations" % (method, it))
     x[mesh.constrained != 0] = 0.0      # zero_constraints.distribute (:1287)
     return x, it, res
 

@@ -46,7 +46,7 @@ class MeshDesc(C.Structure):
 class LinearSolverParams(C.Structure):
     _fields_ = [("relative_residual", C.c_double), ("minimum_residual", C.c_double),
                 ("max_iterations", C.c_int32), ("restart", C.c_int32), ("ilu_fill", C.c_int32),
-                ("ilu_atol", C.c_double), ("ilu_rtol", C.c_double)]
+                ("ilu_atol", C.c_double), ("ilu_rtol", C.c_double), ("method", C.c_int32)]
 
 
 class SolveInfo(C.Structure):

@@ -543,13 +543,16 @@ glsns_solve_linear_system(glsns_context *ctx, const glsns_linear_solver_params *
   if (!p || p->max_iterations < 0 || !(p->relative_residual >= 0) ||
       !(p->minimum_residual >= 0))
     return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "bad linear solver parameters");
+  if (p->method != GLSNS_SOLVER_GMRES && p->method != GLSNS_SOLVER_BICGSTAB)
+    return fail(ctx, GLSNS_ERR_UNSUPPORTED, "This solver is not allowed");
   if (!ctx->have_mesh || !ctx->have_matrix || !ctx->have_rhs)
     return fail(ctx, GLSNS_ERR_STATE, "assemble_matrix_and_rhs must precede solve_linear_system");
   // gls_navier_stokes.cc:1270-1271
   if (renewed_matrix || !ctx->have_ilu)
     GLSNS_TRY(glsns_setup_ilu(ctx, p->ilu_fill, p->ilu_atol, p->ilu_rtol));
   timer_begin(ctx, T_SOLVE);
-  glsns_status s = gmres_solve(ctx, p, info);
+  glsns_status s = p->method == GLSNS_SOLVER_BICGSTAB ? bicgstab_solve(ctx, p, info) :
+                                                        gmres_solve(ctx, p, info);
   timer_end(ctx, T_SOLVE);
   cudaStreamSynchronize(ctx->stream);
   timers_drain(ctx);

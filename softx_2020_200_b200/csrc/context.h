@@ -234,6 +234,8 @@ namespace glsns
   glsns_status device_norm2(glsns_context *ctx, const double *x, double *out);
   glsns_status gmres_solve(glsns_context *ctx, const glsns_linear_solver_params *p,
                            glsns_solve_info *info);
+  glsns_status bicgstab_solve(glsns_context *ctx, const glsns_linear_solver_params *p,
+                           glsns_solve_info *info);
   glsns_status time_orthog(glsns_context *ctx, int nvec);
   glsns_status launch_axpy_constraints(glsns_context *ctx, double alpha);
   glsns_status launch_zero_constrained(glsns_context *ctx, double *x);

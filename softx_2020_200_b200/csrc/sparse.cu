@@ -84,12 +84,28 @@ namespace glsns
       const int64_t gtid   = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
       const int     lane   = threadIdx.x & (TPG - 1);
       const int64_t stride = ((int64_t)gridDim.x * blockDim.x) / TPG;
-      for (int64_t g = gtid / TPG; g < n_groups; g += stride)
+      // the group descriptor and the row pointers of the NEXT group are requested before the
+      // current group's entries: three dependent loads (group -> row pointer -> entries -> x)
+      // per group become one
+      int64_t g = gtid / TPG;
+      int2    gr_n = make_int2(0, 0);
+      int64_t rs_n = 0, re_n = 0;
+      if (g < n_groups)
         {
-          const int2    gr = groups[g];
+          gr_n = groups[g];
+          rs_n = rowptr[gr_n.x], re_n = rowptr[gr_n.x + 1];
+        }
+      for (; g < n_groups; g += stride)
+        {
+          const int2    gr = gr_n;
           const int     r0 = gr.x, m = gr.y;
-          const int64_t rs = rowptr[r0];
-          const int     len = (int)(rowptr[r0 + 1] - rs);
+          const int64_t rs = rs_n;
+          const int     len = (int)(re_n - rs);
+          if (g + stride < n_groups)
+            {
+              gr_n = groups[g + stride];
+              rs_n = rowptr[gr_n.x], re_n = rowptr[gr_n.x + 1];
+            }
           double        s[4][2];
 #pragma unroll
           for (int a = 0; a < 4; ++a)

@@ -704,7 +704,7 @@ namespace glsns
           if (it + 2 < n_items + 2)
             step(std::integral_constant<int, 2>(), it + 2);
         }
-      if (trace && (team + 1) * 8 <= trace_n)
+      if (trace && 8 * (int64_t)gridDim.x * n_teams_cta + (team + 1) * 4 <= trace_n)
         { // per helper lane: items that had to wait, polling rounds, entries re-read
           for (int o = 16; o > 0; o >>= 1)
             n_polled += __shfl_xor_sync(0xffffffffu, n_polled, o);
@@ -848,7 +848,9 @@ namespace glsns
     std::vector<uint8_t> link(ng);
 
     // One sweep: levels, blocks, chain links, level-ordered schedule on NW teams, item lists.
-    auto schedule = [&](const bool upper, TrsvSweep &sw, int32_t &n_levels) -> glsns_status {
+    // `when` (may be null): for every row, when a traced application published it (ns)
+    auto schedule = [&](const bool upper, TrsvSweep &sw, int32_t &n_levels,
+                        const unsigned long long *when) -> glsns_status {
       // entries of group g this sweep reads, [kb, ke) in CSR offsets of its first row
       auto range = [&](int64_t g, int64_t &kb, int64_t &ke) {
         const int64_t i = grp_ptr[g];
@@ -920,7 +922,7 @@ namespace glsns
             order[start[glev[g]]++] = (int32_t)g;
           }
       }
-      if (!upper)
+      if (!upper && !when)
         { // the factorisation takes the groups in the same order (sparse.cu)
           std::vector<int2> fg((size_t)ng);
           for (int64_t t = 0; t < ng; ++t)
@@ -962,7 +964,12 @@ namespace glsns
       std::vector<int64_t> best(nb);
       std::vector<uint8_t> blink(nb), has_succ(nb, 0), is_primary(nb);
       int32_t              nblev = 0;
-      // `best`: when a block can be solved at the earliest, in units of one chain step, if a
+      // `best`, the key the lists are ordered by.  With a trace (`when`): the moment the block's
+      // last input was published in that run, i.e. when the block could have been solved -- a
+      // team that orders its list by level makes a chain that is ready wait behind one that
+      // is late, and how late is only known from a run.  (A block is published strictly after
+      // its inputs, so this key grows along every dependency, as the dead-lock argument needs.)
+      // Without a trace: when a block can be solved at the earliest, in units of one chain step, if a
       // value that travels to another team (L2, a helper's gather and reduction, the mailbox)
       // takes cost_cross of them; the lists are ordered by it.  With both costs 1 (the
       // default) it is the block level.  Weighted orders (cross = 3: where the DAG is mostly
@@ -985,7 +992,8 @@ namespace glsns
                     {
                       const int32_t db = blk_of[dg];
                       l                = std::max(l, blev[db] + 1);
-                      e = std::max(e, best[db] + (db == b - 1 && (link[b_first[b]] & 1) ? cost_chain : cost_cross));
+                      e = when ? std::max<int64_t>(e, (int64_t)when[col[k]]) :
+                                 std::max(e, best[db] + (db == b - 1 && (link[b_first[b]] & 1) ? cost_chain : cost_cross));
                     }
                 }
             }
@@ -1211,6 +1219,9 @@ namespace glsns
       GLSNS_TRY(dev_upload(ctx, sw.dir, reinterpret_cast<const unsigned char *>(dirv.data()),
                            dirv.size() * sizeof(TrsvWarpDir)));
       GLSNS_TRY(dev_alloc(ctx, sw.stream, (size_t)std::max<int64_t>(off, 16)));
+      // (all-zero factor entries until the first factorisation: the schedule can be run, and
+      // timed, on them -- every solution is 0, the waiting and the traffic are the real ones)
+      GLSNS_CUDA(ctx, cudaMemsetAsync(sw.stream.p, 0, (size_t)std::max<int64_t>(off, 16), ctx->stream));
       if (nit)
         {
           trsv_pack_static_kernel<<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
@@ -1221,8 +1232,95 @@ namespace glsns
       GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
       return GLSNS_OK;
     };
-    GLSNS_TRY(schedule(false, ctx->trsv_l, ctx->levels_l));
-    GLSNS_TRY(schedule(true, ctx->trsv_u, ctx->levels_u));
+    GLSNS_TRY(schedule(false, ctx->trsv_l, ctx->levels_l, nullptr));
+    GLSNS_TRY(schedule(true, ctx->trsv_u, ctx->levels_u, nullptr));
+
+    // ---- profile-guided list order ----
+    // The level order assumes that every level takes the same time everywhere; it does not
+    // (chains advance several levels in the time a hop between teams takes), and a team then
+    // keeps a chain that is ready waiting behind one that is late (tools/trsv_trace.py: a few
+    // dozen such stalls of 10-20 us were 30 % of a sweep).  So: run the schedule once on zero
+    // factors with the trace on, re-order the lists by when each block's inputs were there,
+    // keep the new schedule if it is faster, repeat.  Once per sparsity pattern.
+    const int rounds = getenv("GLSNS_TRSV_TUNE") ? atoi(getenv("GLSNS_TRSV_TUNE")) : 3;
+    if (rounds > 0 && ng > 0)
+      {
+        DevBuf<double>             r, z;
+        DevBuf<unsigned long long> tr;
+        GLSNS_TRY(dev_alloc(ctx, r, (size_t)n));
+        GLSNS_TRY(dev_alloc(ctx, z, (size_t)n));
+        GLSNS_TRY(dev_alloc(ctx, tr, (size_t)6 * n));
+        GLSNS_TRY(dev_alloc(ctx, ctx->ytmp, (size_t)n));
+        GLSNS_TRY(dev_alloc(ctx, ctx->dinv, (size_t)n));
+        GLSNS_CUDA(ctx, cudaMemsetAsync(r.p, 0, sizeof(double) * n, ctx->stream));
+        GLSNS_CUDA(ctx, cudaMemsetAsync(ctx->dinv.p, 0, sizeof(double) * n, ctx->stream));
+        GLSNS_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 2 * sizeof(int32_t), ctx->stream));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0), cudaEventCreate(&e1);
+        auto time_apply = [&](float &ms) -> glsns_status {
+          ms = 1e30f;
+          for (int rep = 0; rep < 3; ++rep)
+            {
+              cudaEventRecord(e0, ctx->stream);
+              GLSNS_TRY(launch_ilu_apply(ctx, r.p, z.p, nullptr));
+              cudaEventRecord(e1, ctx->stream);
+              GLSNS_TRY(check_counters(ctx, "ILU apply (schedule tuning)"));
+              float t = 0;
+              cudaEventElapsedTime(&t, e0, e1);
+              ms = std::min(ms, t);
+            }
+          return GLSNS_OK;
+        };
+        std::vector<unsigned long long> when((size_t)2 * n);
+        float                           t_cur = 0;
+        glsns_status                    st    = time_apply(t_cur);
+        for (int round = 0; round < rounds && st == GLSNS_OK; ++round)
+          {
+            GLSNS_CUDA(ctx, cudaMemsetAsync(tr.p, 0, sizeof(unsigned long long) * 6 * n, ctx->stream));
+            if ((st = launch_ilu_apply(ctx, r.p, z.p, tr.p)) != GLSNS_OK ||
+                (st = check_counters(ctx, "ILU apply (schedule tuning)")) != GLSNS_OK)
+              break;
+            GLSNS_CUDA(ctx, cudaMemcpyAsync(when.data(), tr.p, sizeof(unsigned long long) * 2 * n,
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+            GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int sweep = 0; sweep < 2; ++sweep)
+              { // times relative to the sweep's first publication (0 = not a row of the sweep)
+                unsigned long long *w = when.data() + (size_t)sweep * n, t0 = ~0ull;
+                for (int64_t i = 0; i < n; ++i)
+                  if (w[i])
+                    t0 = std::min(t0, w[i]);
+                for (int64_t i = 0; i < n; ++i)
+                  w[i] = w[i] ? w[i] - t0 + 1 : 0;
+              }
+            TrsvSweep keep_l, keep_u;
+            std::swap(keep_l, ctx->trsv_l), std::swap(keep_u, ctx->trsv_u);
+            std::vector<int32_t> rw_l = ctx->trsv_row_warp_l, rw_u = ctx->trsv_row_warp_u;
+            int32_t              dummy;
+            if ((st = schedule(false, ctx->trsv_l, dummy, when.data())) != GLSNS_OK ||
+                (st = schedule(true, ctx->trsv_u, dummy, when.data() + n)) != GLSNS_OK)
+              break;
+            float t_new = 0;
+            if ((st = time_apply(t_new)) != GLSNS_OK)
+              break;
+            if (getenv("GLSNS_TRSV_DEBUG"))
+              fprintf(stderr, "trsv_analyse: tuning round %d: %.3f ms -> %.3f ms\n", round, t_cur, t_new);
+            if (t_new < t_cur)
+              {
+                t_cur = t_new;
+                keep_l.release(), keep_u.release();
+              }
+            else
+              { // no better: back to the previous schedule, done
+                std::swap(keep_l, ctx->trsv_l), std::swap(keep_u, ctx->trsv_u);
+                keep_l.release(), keep_u.release();
+                ctx->trsv_row_warp_l = rw_l, ctx->trsv_row_warp_u = rw_u;
+                break;
+              }
+          }
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+        r.release(), z.release(), tr.release();
+        GLSNS_TRY(st);
+      }
     return GLSNS_OK;
   }
 

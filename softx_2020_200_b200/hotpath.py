@@ -155,10 +155,12 @@ class GLSHotPath:
 
     def solve_linear_system(self, relative_residual=1e-3, minimum_residual=1e-8,
                             max_iterations=1000, restart=30, ilu_fill=0, ilu_atol=1e-8,
-                            ilu_rtol=1.0, renewed_matrix=True, download=True):
-        """Returns (newton_update or None, info dict). Raises NoConvergence like deal.II."""
+                            ilu_rtol=1.0, renewed_matrix=True, download=True, method="gmres"):
+        """Returns (newton_update or None, info dict). Raises NoConvergence like deal.II.
+        method: the .prm `linear solver/method`, "gmres" or "bicgstab"."""
         p = LinearSolverParams(relative_residual, minimum_residual, max_iterations, restart,
-                               ilu_fill, ilu_atol, ilu_rtol)
+                               ilu_fill, ilu_atol, ilu_rtol,
+                               {"gmres": 0, "bicgstab": 1, "amg": 2}[method])
         info = SolveInfo()
         out = np.empty(self.n_owned) if download else None
         st = self._L.glsns_solve_linear_system(self._ctx, C.byref(p), 1 if renewed_matrix else 0,

@@ -189,6 +189,59 @@ def test_newton_solution_matches_oracle(oracle, dim, n, pu, pp, nu):
     hp.close()
 
 
+@pytest.mark.parametrize("dim,n,pu,pp,nu", [(2, 16, 1, 1, 1.0), (3, 4, 2, 2, 1.0), (2, 8, 2, 2, 0.1)])
+def test_bicgstab_matches_oracle(oracle, dim, n, pu, pp, nu):
+    """`method = bicgstab` (solve_system_BiCGStab, gls_navier_stokes.cc:1291-1340): same matrix, same
+    ILU, iteration count within +-1 of the oracle's restatement, solution to the solver tolerance,
+    logged residual = the true one."""
+    mesh = oracle.BoxMesh(dim, n, pu, pp)
+    force = mesh.evaluate_force(mms.forcing_2d if dim == 2 else mms.forcing_3d)
+    U = 0.1 * random_state(mesh)
+    pr = oracle.scheme_params("steady", None, nu)
+    val, rhs = oracle.assemble(mesh, U, pr, True, force)
+    tol = max(1e-8 * np.linalg.norm(rhs), 1e-12)
+    lu, dp = oracle.ilu0(mesh, val, 1e-10, 1.0)
+    x_ref, it_ref, tr_ref, ok = oracle.bicgstab(mesh, val, lu, dp, rhs, tol, 2000)
+    assert ok
+    hp = hotpath_from_oracle_mesh(mesh, nu, force)
+    hp.set_vector("evaluation_point", U)
+    hp.assemble(True)
+    x, info = hp.solve_linear_system(relative_residual=1e-8, minimum_residual=1e-12,
+                                     max_iterations=2000, ilu_atol=1e-10, method="bicgstab")
+    assert abs(info["iterations"] - it_ref) <= 1
+    assert info["true_residual"] < 10 * tol
+    x_ref[mesh.constrained != 0] = 0.0
+    assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+    # and against GMRES on the same system
+    xg, _ = hp.solve_linear_system(relative_residual=1e-10, minimum_residual=1e-13,
+                                   max_iterations=2000, ilu_atol=1e-10)
+    assert np.linalg.norm(x - xg) <= 1e-6 * np.linalg.norm(xg)
+    from softx_2020_200_b200 import GlsnsError
+    with pytest.raises(GlsnsError, match="This solver is not allowed"):
+        hp.solve_linear_system(method="amg")
+    hp.close()
+
+
+def test_bicgstab_through_the_cpp_mirror(oracle):
+    """`set method = bicgstab` in the .prm reaches solve_system_BiCGStab and Newton converges to the
+    same discrete solution as with GMRES (restart_01's problem: velocity L2 error 0.0343628)."""
+    import re
+    from softx_2020_200_b200.mesh import BoxMesh
+    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.test_host_mirror import _match_numbering
+    mesh = BoxMesh(2, 16, 1, 1, with_q_points=True)
+    force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)
+    s = GLSNavierStokesSolver(mesh, "subsection linear solver\n set method = bicgstab\nend\n", force)
+    s.set_vector("present_solution", np.zeros(mesh.n_dofs))
+    s.solve_non_linear_system("steady", False, True)
+    assert len(re.findall(r"-Iterative solver took : (\d+) steps", s.log)) == 3
+    nat = BoxMesh(2, 16, 1, 1, renumber=False)
+    om = oracle.BoxMesh(2, 16, 1, 1, renumber=_match_numbering(nat, mesh, 2))
+    err_u, _ = oracle.l2_error(om, s.present_solution, mms.exact_2d)
+    assert abs(err_u - 0.0343628) < 2e-6
+    s.close()
+
+
 def test_gmres_no_convergence_and_state_errors(oracle):
     from softx_2020_200_b200 import GlsnsError, NoConvergence
     mesh = oracle.BoxMesh(2, 8, 1, 1)

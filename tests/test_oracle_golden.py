@@ -96,3 +96,20 @@ def test_oracle_reproduces_committed_fixtures(oracle, name):
     assert np.array_equal(lu, fx["ilu"])
     assert np.array_equal(oracle.ilu_apply(mesh, lu, dp, fx["x"]), fx["ilu_apply"])
     assert np.array_equal(oracle.spmv(mesh, val, fx["x"]), fx["spmv"])
+
+
+def test_oracle_bicgstab_agrees_with_pinned_gmres(oracle):
+    """solve_system_BiCGStab has no golden vector in the reference (no test uses it): the oracle's
+    restatement is checked against the pinned GMRES path on restart_01's first Newton system."""
+    from tests import mms
+    mesh = oracle.BoxMesh(2, 16, 1, 1)
+    force = mesh.evaluate_force(mms.forcing_2d)
+    val, rhs = oracle.assemble(mesh, np.zeros(mesh.ndof), oracle.scheme_params("steady", None, 1.0),
+                               True, force)
+    xg, itg, _ = oracle.solve_linear_system(mesh, val, rhs, rel=1e-10, abs_=1e-14)
+    xb, itb, res = oracle.solve_linear_system(mesh, val, rhs, rel=1e-10, abs_=1e-14, method="bicgstab")
+    assert res < 1e-9 * np.linalg.norm(rhs)
+    assert np.linalg.norm(xb - xg) <= 1e-7 * np.linalg.norm(xg)
+    assert itb < itg            # two products per iteration
+    with pytest.raises(RuntimeError, match="This solver is not allowed"):
+        oracle.solve_linear_system(mesh, val, rhs, method="amg")
