@@ -170,7 +170,7 @@ typedef struct
   double  minimum_residual;  /* default 1e-8  */
   int32_t max_iterations;    /* default 1000  */
   int32_t restart;           /* deal.II SolverGMRES default: 30 */
-  int32_t ilu_fill;          /* default 0 (only 0 is built so far) */
+  int32_t ilu_fill;          /* default 0; k > 0: level-of-fill ILU(k) as Ifpack builds it */
   double  ilu_atol;          /* default 1e-8  */
   double  ilu_rtol;          /* default 1.0   */
   int32_t method;            /* glsns_solver_method, default GLSNS_SOLVER_GMRES */
@@ -257,7 +257,14 @@ glsns_status glsns_accept_evaluation_point(glsns_context *ctx);
 /* ---- inspection (parity tests, benchmarks) -------------------------------- */
 glsns_status glsns_get_matrix_values(glsns_context *ctx, double *values, int64_t nnz);
 glsns_status glsns_set_matrix_values(glsns_context *ctx, const double *values, int64_t nnz);
+/* L\U on the pattern of the installed fill level (glsns_get_ilu_pattern); for fill = 0 that is
+   the mesh's own pattern. */
 glsns_status glsns_get_ilu_values(glsns_context *ctx, double *values, int64_t nnz);
+/* The factor pattern: the mesh's CSR for fill = 0, the level-of-fill pattern of the rank-local
+   block (a superset, explicit zeros in the matrix) once glsns_setup_ilu ran with fill > 0.
+   Any of nnz / row_ptr [n_owned+1] / col_idx [*nnz] may be NULL. */
+glsns_status glsns_get_ilu_pattern(glsns_context *ctx, int64_t *nnz, int64_t *row_ptr,
+                                   int32_t *col_idx);
 /* y = A x on the device matrix; x is [n_dofs] (ghosted), y is [n_owned]. */
 glsns_status glsns_spmv(glsns_context *ctx, const double *x, double *y);
 /* z = (LU)^-1 r, both [n_owned]. */

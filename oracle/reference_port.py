@@ -15,7 +15,10 @@ What is restated here (numpy) and in gls_oracle.c (the heavy loops), with the re
   inhomogeneous Dirichlet constraints (:79-183), the sparsity pattern with
   keep_constrained_dofs=false (:204-213);
 * assembleGLS (:231-777)                       -> gls_oracle.c: glso_assemble
-* setup_ILU (:1161-1176)                       -> gls_oracle.c: glso_ilu0
+* setup_ILU (:1161-1176)                       -> gls_oracle.c: glso_ilu0; `ilu preconditioner fill`
+  = k > 0 -> iluk_pattern (Ifpack's level-of-fill graph, restated; ILU(k) = ILU(0) on that pattern.
+  PARITY of k > 0 pinned only through solver-independent results: the reference prints no
+  iteration counts for fill > 0)
 * solve_system_GMRES (:1242-1289)              -> gls_oracle.c: glso_gmres
 * solve_system_BiCGStab (:1291-1340)           -> bicgstab (PARITY UNPINNED: no reference test or
   example uses `method = bicgstab`; AztecOO's AZ_bicgstab is restated from the published
@@ -473,6 +476,56 @@ def ilu0(mesh, val, atol=1e-8, rtol=1.0, block_ptr=None):
     return lu, dp
 
 
+def iluk_pattern(mesh, fill, block_ptr=None):
+    """Level-of-fill pattern ILU(fill) of every diagonal block (Ifpack_IlukGraph behind
+    TrilinosWrappers::PreconditionILU::AdditionalData(ilu_fill, ...), call site
+    gls_navier_stokes.cc:1166-1175): entries of A have level 0, eliminating row i with row k creates
+    (i, j) for each (k, j), j > k, at level lev(i,k) + lev(k,j) + 1, kept when <= fill.
+    Returns a mesh-like object (ndof, rowptr, col: A's entries plus the fill positions) and `a2p`,
+    the position of every entry of A in it.  Pure Python: small cases only."""
+    import heapq
+    import types
+    bp, nb = _blocks(mesh.ndof, block_ptr)
+    rows, upper = [], {}
+    for b in range(nb):
+        b0, b1 = int(bp[b]), int(bp[b + 1])
+        for i in range(b0, b1):
+            cols = mesh.col[mesh.rowptr[i]:mesh.rowptr[i + 1]]
+            lev = {int(c): 0 for c in cols if b0 <= c < b1}
+            outside = [int(c) for c in cols if not b0 <= c < b1]
+            todo = [c for c in lev if c < i]
+            heapq.heapify(todo)
+            while todo:
+                k = heapq.heappop(todo)
+                for j, lkj in upper[k]:
+                    nl = lev[k] + lkj + 1
+                    if nl > fill:
+                        continue
+                    if j in lev:
+                        lev[j] = min(lev[j], nl)
+                    else:
+                        lev[j] = nl
+                        if j < i:
+                            heapq.heappush(todo, j)
+            upper[i] = sorted((j, l) for j, l in lev.items() if j > i)
+            rows.append(sorted(list(lev) + outside))
+    rowptr = np.zeros(mesh.ndof + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum([len(r) for r in rows])
+    col = np.array([c for r in rows for c in r], dtype=np.int32)
+    a2p = np.empty(mesh.rowptr[-1], dtype=np.int64)
+    for i in range(mesh.ndof):
+        a2p[mesh.rowptr[i]:mesh.rowptr[i + 1]] = rowptr[i] + np.searchsorted(
+            col[rowptr[i]:rowptr[i + 1]], mesh.col[mesh.rowptr[i]:mesh.rowptr[i + 1]])
+    return types.SimpleNamespace(ndof=mesh.ndof, rowptr=rowptr, col=col), a2p
+
+
+def pad_values(padded, a2p, val):
+    """A's values on the level-of-fill pattern (explicit zeros at the fill positions)."""
+    out = np.zeros(padded.rowptr[-1])
+    out[a2p] = val
+    return out
+
+
 def ilu_apply(mesh, lu, dp, r, block_ptr=None):
     bp, nb = _blocks(mesh.ndof, block_ptr)
     z = np.zeros(mesh.ndof)
@@ -550,10 +603,14 @@ class NoConvergence(RuntimeError):
 
 
 def solve_linear_system(mesh, val, rhs, rel=1e-3, abs_=1e-8, max_iters=1000, ilu_atol=1e-8,
-                        ilu_rtol=1.0, restart=30, block_ptr=None, method="gmres"):
+                        ilu_rtol=1.0, restart=30, block_ptr=None, method="gmres", ilu_fill=0):
     """solve_system_GMRES / solve_system_BiCGStab (gls_navier_stokes.cc:1242-1340).
     Returns (newton_update, iters, res)."""
     tol = max(rel * float(np.linalg.norm(rhs)), abs_)
+    constrained = mesh.constrained
+    if ilu_fill > 0:                     # ILU(k) = ILU(0) on the level-of-fill pattern
+        mesh, a2p = iluk_pattern(mesh, ilu_fill, block_ptr)
+        val = pad_values(mesh, a2p, val)
     lu, dp = ilu0(mesh, val, ilu_atol, ilu_rtol, block_ptr)
     if method == "bicgstab":
         x, it, res, ok = bicgstab(mesh, val, lu, dp, rhs, tol, max_iters, block_ptr)
@@ -563,7 +620,7 @@ def solve_linear_system(mesh, val, rhs, rel=1e-3, abs_=1e-8, max_iters=1000, ilu
         raise RuntimeError("This solver is not allowed")     # :1158
     if not ok:
         raise NoConvergence("%s did not converge in %d iterations" % (method, it))
-    x[mesh.constrained != 0] = 0.0      # zero_constraints.distribute (:1287)
+    x[constrained != 0] = 0.0           # zero_constraints.distribute (:1287)
     return x, it, res
 
 

@@ -92,6 +92,7 @@ SYMBOLS = {
     "glsns_get_matrix_values": (C.c_int, [ctx_p, c_double_p, C.c_int64]),
     "glsns_set_matrix_values": (C.c_int, [ctx_p, c_double_p, C.c_int64]),
     "glsns_get_ilu_values": (C.c_int, [ctx_p, c_double_p, C.c_int64]),
+    "glsns_get_ilu_pattern": (C.c_int, [ctx_p, c_i64_p, c_i64_p, c_i32_p]),
     "glsns_spmv": (C.c_int, [ctx_p, c_double_p, c_double_p]),
     "glsns_ilu_apply": (C.c_int, [ctx_p, c_double_p, c_double_p]),
     "glsns_ilu_levels": (C.c_int, [ctx_p, c_i32_p, c_i32_p]),

@@ -246,6 +246,7 @@ glsns_destroy(glsns_context *ctx)
   ctx->trsv_l.release();
   ctx->trsv_u.release();
   ctx->dinv.release();
+  ctx->a2p.release();
   ctx->diag_rows.release();
   ctx->fgroups.release();
   ctx->sgroups.release();
@@ -335,6 +336,9 @@ glsns_set_mesh(glsns_context *ctx, const glsns_mesh_desc *m)
   for (bool &b : ctx->vec_set)
     b = false;
   ctx->n_dofs = m->n_dofs, ctx->n_owned = m->n_owned, ctx->n_cells = m->n_cells, ctx->nnz = nnz;
+  ctx->nnz_base = nnz, ctx->ilu_fill = 0;
+  ctx->base_rowptr.clear(), ctx->base_col.clear();
+  ctx->a2p.release();
   ctx->geometry_per_q = m->geometry_per_q ? 1 : 0;
   ctx->n_colors       = m->n_colors;
   ctx->color_ptr.assign(m->color_ptr, m->color_ptr + (m->n_cells ? m->n_colors + 1 : 0));
@@ -519,8 +523,8 @@ glsns_setup_ilu(glsns_context *ctx, int32_t fill, double atol, double rtol)
   CHECK_CTX(ctx);
   if (!ctx->have_mesh || !ctx->have_matrix)
     return fail(ctx, GLSNS_ERR_STATE, "no matrix to factorise");
-  if (fill != 0)
-    return fail(ctx, GLSNS_ERR_UNSUPPORTED, "only ilu preconditioner fill = 0 is built");
+  // fill = k > 0: ILU(0) on the level-of-fill pattern (installed when the level changes)
+  GLSNS_TRY(ilu_install_fill(ctx, fill));
   timer_begin(ctx, T_SETUP_ILU);
   glsns_status s = launch_ilu_factor(ctx, atol, rtol);
   timer_end(ctx, T_SETUP_ILU);
@@ -617,12 +621,9 @@ glsns_get_matrix_values(glsns_context *ctx, double *values, int64_t nnz)
   CHECK_CTX(ctx);
   if (!ctx->have_mesh || !ctx->have_matrix)
     return fail(ctx, GLSNS_ERR_STATE, "no matrix");
-  if (!values || nnz != ctx->nnz)
+  if (!values || nnz != ctx->nnz_base)
     return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "nnz mismatch");
-  GLSNS_CUDA(ctx, cudaMemcpyAsync(values, ctx->val.p, sizeof(double) * nnz,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-  GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return GLSNS_OK;
+  return matrix_values_to_host(ctx, ctx->val.p, values);
 }
 
 glsns_status
@@ -631,11 +632,9 @@ glsns_set_matrix_values(glsns_context *ctx, const double *values, int64_t nnz)
   CHECK_CTX(ctx);
   if (!ctx->have_mesh)
     return fail(ctx, GLSNS_ERR_STATE, "no mesh");
-  if (!values || nnz != ctx->nnz)
+  if (!values || nnz != ctx->nnz_base)
     return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "nnz mismatch");
-  GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->val.p, values, sizeof(double) * nnz,
-                                  cudaMemcpyHostToDevice, ctx->stream));
-  GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  GLSNS_TRY(matrix_values_from_host(ctx, values));
   ctx->have_matrix = true;
   ctx->have_ilu    = false;
   return GLSNS_OK;
@@ -651,6 +650,24 @@ glsns_get_ilu_values(glsns_context *ctx, double *values, int64_t nnz)
     return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "nnz mismatch");
   GLSNS_CUDA(ctx, cudaMemcpyAsync(values, ctx->lu.p, sizeof(double) * nnz,
                                   cudaMemcpyDeviceToHost, ctx->stream));
+  GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GLSNS_OK;
+}
+
+glsns_status
+glsns_get_ilu_pattern(glsns_context *ctx, int64_t *nnz, int64_t *row_ptr, int32_t *col_idx)
+{
+  CHECK_CTX(ctx);
+  if (!ctx->have_mesh)
+    return fail(ctx, GLSNS_ERR_STATE, "no mesh");
+  if (nnz)
+    *nnz = ctx->nnz;
+  if (row_ptr)
+    GLSNS_CUDA(ctx, cudaMemcpyAsync(row_ptr, ctx->rowptr.p, sizeof(int64_t) * (ctx->n_owned + 1),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+  if (col_idx)
+    GLSNS_CUDA(ctx, cudaMemcpyAsync(col_idx, ctx->col.p, sizeof(int32_t) * ctx->nnz,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
   GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return GLSNS_OK;
 }

@@ -105,6 +105,15 @@ struct glsns_context
   // ---- mesh ----
   bool    have_mesh = false;
   int64_t n_dofs = 0, n_owned = 0, n_cells = 0, nnz = 0;
+  // ilu preconditioner fill = k > 0: the device pattern is the level-of-fill pattern of the
+  // rank-local block (the entries of A plus explicit zeros at the fill positions), so that
+  // ILU(k) is ILU(0) on it; the pattern the host handed over (what the inspection calls and
+  // the host see) is kept here, `a2p` maps its entries into the padded one
+  int32_t               ilu_fill = 0;
+  int64_t               nnz_base = 0;
+  std::vector<int64_t>  base_rowptr;
+  std::vector<int32_t>  base_col;
+  glsns::DevBuf<int64_t> a2p;
   int32_t geometry_per_q = 0, n_colors = 0;
   glsns::DevBuf<int32_t> cell_dofs, col, color_cells, order_l, diag_rows;
   glsns::TrsvSweep                trsv_l, trsv_u;
@@ -220,6 +229,9 @@ namespace glsns
   // sparse.cu
   glsns_status launch_spmv(glsns_context *ctx, const double *x, double *y);
   glsns_status ilu_analyse(glsns_context *ctx, const int64_t *rowptr, const int32_t *col);
+  glsns_status ilu_install_fill(glsns_context *ctx, int32_t fill);
+  glsns_status matrix_values_to_host(glsns_context *ctx, const double *dev_padded, double *host_base);
+  glsns_status matrix_values_from_host(glsns_context *ctx, const double *host_base);
   glsns_status launch_ilu_factor(glsns_context *ctx, double atol, double rtol);
   glsns_status launch_ilu_apply(glsns_context *ctx, const double *r, double *z,
                                 unsigned long long *trace = nullptr);

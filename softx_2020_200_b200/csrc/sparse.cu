@@ -648,6 +648,243 @@ namespace glsns
     return GLSNS_OK;
   }
 
+  // ------------------------------------------------- ILU(k), k > 0
+  namespace
+  {
+    // dst[map[k]] = src[k] / dst[k] = src[map[k]]
+    __global__ void __launch_bounds__(256)
+    scatter_values_kernel(const int64_t n, const int64_t *__restrict__ map,
+                          const double *__restrict__ src, double *__restrict__ dst)
+    {
+      const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (k < n)
+        dst[map[k]] = src[k];
+    }
+    __global__ void __launch_bounds__(256)
+    gather_values_kernel(const int64_t n, const int64_t *__restrict__ map,
+                         const double *__restrict__ src, double *__restrict__ dst)
+    {
+      const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (k < n)
+        dst[k] = src[map[k]];
+    }
+
+    // Level-of-fill pattern of the rank-local diagonal block: what Ifpack_IlukGraph builds
+    // for TrilinosWrappers::PreconditionILU::AdditionalData(ilu_fill = k, ..., overlap = 0)
+    // (reference call site source/solvers/gls_navier_stokes.cc:1166-1175).  Entries of A
+    // have level 0; eliminating row i with row k < i creates (i, j) for every (k, j), j > k,
+    // with level lev(i,k) + lev(k,j) + 1, kept if <= k (the minimum over all k).  Columns
+    // >= n (ghosts, outside the block) stay in their rows and take no part.
+    void
+    iluk_symbolic(const int64_t n, const int64_t *rowptr, const int32_t *col, const int fill,
+                  std::vector<int64_t> &prow, std::vector<int32_t> &pcol)
+    {
+      constexpr int32_t    END = INT32_MAX;
+      std::vector<uint8_t> plev;
+      std::vector<int64_t> pdiag((size_t)n, -1), pghost((size_t)n, 0); // diagonal / first ghost entry
+      std::vector<int32_t> next((size_t)n + 1), lev((size_t)n, 0), ghosts;
+      std::vector<int64_t> mark((size_t)n, -1);
+      prow.assign((size_t)n + 1, 0);
+      pcol.clear();
+      pcol.reserve((size_t)rowptr[n] * (fill + 1));
+      plev.reserve((size_t)rowptr[n] * (fill + 1));
+      for (int64_t i = 0; i < n; ++i)
+        {
+          ghosts.clear();
+          int32_t prev = (int32_t)n; // head of the sorted list
+          for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+            {
+              const int32_t c = col[k];
+              if (c >= n)
+                {
+                  ghosts.push_back(c);
+                  continue;
+                }
+              next[prev] = c, prev = c;
+              lev[c] = 0, mark[c] = i;
+            }
+          next[prev] = END;
+          for (int32_t k = next[n]; k < i; k = next[k])
+            {
+              const int lk = lev[k];
+              int32_t   p  = k;
+              for (int64_t t = pdiag[k] + 1; t < pghost[k]; ++t)
+                {
+                  const int nl = lk + plev[(size_t)t] + 1;
+                  if (nl > fill)
+                    continue;
+                  const int32_t j = pcol[(size_t)t];
+                  if (mark[j] == i)
+                    lev[j] = std::min(lev[j], nl);
+                  else
+                    {
+                      while (next[p] < j)
+                        p = next[p];
+                      next[j] = next[p], next[p] = j;
+                      mark[j] = i, lev[j] = nl;
+                    }
+                  p = j;
+                }
+            }
+          for (int32_t c = next[n]; c != END; c = next[c])
+            {
+              if (c == i)
+                pdiag[i] = (int64_t)pcol.size();
+              pcol.push_back(c), plev.push_back((uint8_t)lev[c]);
+            }
+          pghost[i] = (int64_t)pcol.size();
+          for (int32_t c : ghosts)
+            pcol.push_back(c), plev.push_back(0);
+          prow[i + 1] = (int64_t)pcol.size();
+        }
+    }
+  } // namespace
+
+  // setup_ILU with `ilu preconditioner fill` = fill != the installed level: switch the device
+  // pattern (and with it the SpMV groups, the factorisation order and the triangular-solve
+  // schedule); the matrix values move along.
+  glsns_status
+  ilu_install_fill(glsns_context *ctx, const int32_t fill)
+  {
+    const int64_t n = ctx->n_owned;
+    if (fill < 0 || fill > 200)
+      return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "ilu preconditioner fill must be in 0..200");
+    if (fill == ctx->ilu_fill)
+      return GLSNS_OK;
+    if (ctx->base_rowptr.empty())
+      { // the installed pattern is the host's: fetch it (host arrays were only borrowed)
+        ctx->base_rowptr.resize((size_t)n + 1);
+        ctx->base_col.resize((size_t)ctx->nnz);
+        ctx->nnz_base = ctx->nnz;
+        GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->base_rowptr.data(), ctx->rowptr.p,
+                                        sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost,
+                                        ctx->stream));
+        GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->base_col.data(), ctx->col.p,
+                                        sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost,
+                                        ctx->stream));
+        GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      }
+    const int64_t        nnz_b = ctx->nnz_base;
+    std::vector<int64_t> prow;
+    std::vector<int32_t> pcol;
+    if (fill > 0)
+      {
+        for (int64_t i = 0; i < n; ++i)
+          if (!std::binary_search(ctx->base_col.begin() + ctx->base_rowptr[i],
+                                  ctx->base_col.begin() + ctx->base_rowptr[i + 1], (int32_t)i))
+            return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "sparsity pattern lacks a diagonal entry");
+        iluk_symbolic(n, ctx->base_rowptr.data(), ctx->base_col.data(), fill, prow, pcol);
+      }
+    const int64_t *nrow = fill > 0 ? prow.data() : ctx->base_rowptr.data();
+    const int32_t *ncol = fill > 0 ? pcol.data() : ctx->base_col.data();
+    const int64_t  nnz_p = nrow[n];
+    // values: installed pattern -> host pattern -> new pattern
+    DevBuf<double> base_val, new_val;
+    GLSNS_TRY(dev_alloc(ctx, base_val, (size_t)std::max<int64_t>(nnz_b, 1)));
+    GLSNS_TRY(dev_alloc(ctx, new_val, (size_t)std::max<int64_t>(nnz_p, 1)));
+    const unsigned gb = (unsigned)((nnz_b + 255) / 256);
+    if (nnz_b)
+      {
+        if (ctx->a2p.p)
+          gather_values_kernel<<<gb, 256, 0, ctx->stream>>>(nnz_b, ctx->a2p.p, ctx->val.p, base_val.p);
+        else
+          GLSNS_CUDA(ctx, cudaMemcpyAsync(base_val.p, ctx->val.p, sizeof(double) * nnz_b,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+    if (fill > 0)
+      {
+        std::vector<int64_t> a2p((size_t)nnz_b);
+        for (int64_t i = 0; i < n; ++i)
+          {
+            int64_t t = prow[i];
+            for (int64_t k = ctx->base_rowptr[i]; k < ctx->base_rowptr[i + 1]; ++k)
+              {
+                while (pcol[(size_t)t] != ctx->base_col[(size_t)k])
+                  ++t; // (both sorted over the block, ghosts in the same order behind it)
+                a2p[(size_t)k] = t++;
+              }
+          }
+        GLSNS_TRY(dev_upload(ctx, ctx->a2p, a2p.data(), a2p.size()));
+        GLSNS_CUDA(ctx, cudaMemsetAsync(new_val.p, 0, sizeof(double) * nnz_p, ctx->stream));
+        if (nnz_b)
+          scatter_values_kernel<<<gb, 256, 0, ctx->stream>>>(nnz_b, ctx->a2p.p, base_val.p, new_val.p);
+        GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // a2p goes out of scope
+      }
+    else
+      {
+        ctx->a2p.release();
+        if (nnz_b)
+          GLSNS_CUDA(ctx, cudaMemcpyAsync(new_val.p, base_val.p, sizeof(double) * nnz_b,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+    GLSNS_CUDA(ctx, cudaGetLastError());
+    GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    base_val.release();
+    ctx->val.release();
+    ctx->val = new_val; // (plain handle: pointer + size)
+    ctx->lu.release();
+    ctx->nnz = nnz_p;
+    GLSNS_TRY(dev_upload(ctx, ctx->rowptr, nrow, (size_t)n + 1));
+    GLSNS_TRY(dev_upload(ctx, ctx->col, ncol, (size_t)nnz_p));
+    GLSNS_TRY(ilu_analyse(ctx, nrow, ncol));
+    GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->epoch    = 0;
+    ctx->ilu_fill = fill;
+    ctx->have_ilu = false;
+    if (fill == 0)
+      {
+        ctx->base_rowptr.clear(), ctx->base_rowptr.shrink_to_fit();
+        ctx->base_col.clear(), ctx->base_col.shrink_to_fit();
+      }
+    return GLSNS_OK;
+  }
+
+  // matrix values as the host sees them (its own pattern), whatever pattern is installed
+  glsns_status
+  matrix_values_to_host(glsns_context *ctx, const double *dev_padded, double *host_base)
+  {
+    const int64_t nb = ctx->a2p.p ? ctx->nnz_base : ctx->nnz;
+    if (!ctx->a2p.p)
+      {
+        GLSNS_CUDA(ctx, cudaMemcpyAsync(host_base, dev_padded, sizeof(double) * nb,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+        GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return GLSNS_OK;
+      }
+    DevBuf<double> tmp;
+    GLSNS_TRY(dev_alloc(ctx, tmp, (size_t)std::max<int64_t>(nb, 1)));
+    if (nb)
+      gather_values_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(nb, ctx->a2p.p,
+                                                                                   dev_padded, tmp.p);
+    GLSNS_CUDA(ctx, cudaMemcpyAsync(host_base, tmp.p, sizeof(double) * nb, cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+    GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tmp.release();
+    return GLSNS_OK;
+  }
+
+  glsns_status
+  matrix_values_from_host(glsns_context *ctx, const double *host_base)
+  {
+    const int64_t nb = ctx->a2p.p ? ctx->nnz_base : ctx->nnz;
+    if (!ctx->a2p.p)
+      {
+        GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->val.p, host_base, sizeof(double) * nb,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+        GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return GLSNS_OK;
+      }
+    DevBuf<double> tmp;
+    GLSNS_TRY(dev_upload(ctx, tmp, host_base, (size_t)nb));
+    GLSNS_CUDA(ctx, cudaMemsetAsync(ctx->val.p, 0, sizeof(double) * ctx->nnz, ctx->stream));
+    if (nb)
+      scatter_values_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(nb, ctx->a2p.p,
+                                                                                    tmp.p, ctx->val.p);
+    GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tmp.release();
+    return GLSNS_OK;
+  }
+
   glsns_status
   check_counters(glsns_context *ctx, const char *what)
   {

@@ -191,10 +191,22 @@ class GLSHotPath:
         v = _c(values, np.float64)
         self._check(self._L.glsns_set_matrix_values(self._ctx, _ptr(v, c_double_p), v.size))
 
+    def get_ilu_pattern(self):
+        """(row_ptr, col_idx) of the factors: the mesh's CSR for fill 0, the level-of-fill pattern
+        after setup_ilu(fill > 0)."""
+        nnz = C.c_int64()
+        self._check(self._L.glsns_get_ilu_pattern(self._ctx, C.byref(nnz), None, None))
+        rp, col = np.empty(self.n_owned + 1, dtype=np.int64), np.empty(nnz.value, dtype=np.int32)
+        self._check(self._L.glsns_get_ilu_pattern(self._ctx, None, _ptr(rp, _lib.c_i64_p),
+                                                  _ptr(col, c_i32_p)))
+        return rp, col
+
     def get_ilu_values(self):
-        out = np.empty(self.nnz)
-        self._check(self._L.glsns_get_ilu_values(self._ctx, _ptr(out, c_double_p), self.nnz))
-        return out
+        nnz = C.c_int64()
+        self._check(self._L.glsns_get_ilu_pattern(self._ctx, C.byref(nnz), None, None))
+        v = np.empty(nnz.value)
+        self._check(self._L.glsns_get_ilu_values(self._ctx, _ptr(v, c_double_p), nnz.value))
+        return v
 
     def spmv(self, x):
         x = _c(x, np.float64)

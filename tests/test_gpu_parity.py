@@ -118,9 +118,86 @@ def test_ilu_diagonal_perturbation_and_zero_pivot(oracle):
         hp.setup_ilu(0, 0.0, 1.0)
     assert e.value.status == 4  # GLSNS_ERR_ZERO_PIVOT
     with pytest.raises(GlsnsError) as e:
-        hp.setup_ilu(1, 1e-8, 1.0)
-    assert e.value.status == 6  # fill > 0 not built
+        hp.setup_ilu(-1, 1e-8, 1.0)
+    assert e.value.status == 1  # GLSNS_ERR_BAD_ARGUMENT
     hp.close()
+
+
+@pytest.mark.parametrize("dim,n,pu,pp,fills", [(2, 8, 1, 1, (1, 4, 2, 0)), (2, 5, 2, 2, (1, 2)),
+                                               (3, 3, 1, 1, (1, 2)), (3, 2, 2, 2, (1,))])
+def test_ilu_fill_levels_against_oracle(oracle, dim, n, pu, pp, fills):
+    """`ilu preconditioner fill = k` (setup_ILU, gls_navier_stokes.cc:1161-1176; the shipped cavity
+    and cylinder examples use 1, mms2d_gls.prm 4): the level-of-fill pattern, the factors on it and
+    their application against the oracle; the matrix the host sees keeps its own pattern; levels
+    can be switched back and forth."""
+    mesh = oracle.BoxMesh(dim, n, pu, pp)
+    hp = hotpath_from_oracle_mesh(mesh, 0.1, None)
+    a_ref, b_ref = oracle.assemble(mesh, random_state(mesh, scale=0.5),
+                                   oracle.scheme_params("steady", None, 0.1), True)
+    hp.set_matrix_values(a_ref)
+    x = np.random.default_rng(7).standard_normal(mesh.ndof)
+    y_ref = oracle.spmv(mesh, a_ref, x)
+    for fill in fills:
+        hp.setup_ilu(fill, 1e-8, 1.0)
+        pm, a2p = oracle.iluk_pattern(mesh, fill)
+        rp, col = hp.get_ilu_pattern()
+        assert np.array_equal(rp, pm.rowptr) and np.array_equal(col, pm.col)
+        lu_ref, dp = oracle.ilu0(pm, oracle.pad_values(pm, a2p, a_ref), 1e-8, 1.0)
+        assert row_scaled_error(pm, hp.get_ilu_values(), lu_ref) <= 1e-10
+        z_ref = oracle.ilu_apply(pm, lu_ref, dp, x)
+        assert np.max(np.abs(hp.ilu_apply(x) - z_ref)) <= 1e-9 * np.max(np.abs(z_ref))
+        # the matrix is unchanged, on the host's pattern and in the product
+        assert np.array_equal(hp.get_matrix_values(), a_ref)
+        assert np.max(np.abs(hp.spmv(x) - y_ref)) <= 1e-13 * np.max(np.abs(y_ref))
+    hp.close()
+
+
+def test_gmres_with_ilu_fill_and_reassembly(oracle):
+    """GMRES + ILU(k) through solve_linear_system, including a re-assembly on the padded pattern
+    (second Newton iteration): iteration counts against the oracle, and fewer than with ILU(0)."""
+    mesh = oracle.BoxMesh(2, 16, 1, 1)
+    force = mesh.evaluate_force(mms.forcing_2d)
+    pr = oracle.scheme_params("steady", None, 1.0)
+    hp = hotpath_from_oracle_mesh(mesh, 1.0, force)
+    U = np.zeros(mesh.ndof)
+    its = {}
+    for fill in (0, 1, 4):
+        hp.set_vector("evaluation_point", U)
+        hp.assemble(True)
+        val, rhs = oracle.assemble(mesh, U, pr, True, force)
+        x_ref, it_ref, _ = oracle.solve_linear_system(mesh, val, rhs, rel=1e-8, abs_=1e-12,
+                                                      ilu_fill=fill)
+        x, info = hp.solve_linear_system(relative_residual=1e-8, minimum_residual=1e-12,
+                                         ilu_fill=fill)
+        assert abs(info["iterations"] - it_ref) <= 1
+        assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+        assert row_scaled_error(mesh, hp.get_matrix_values(), val) <= TOL_ENTRY
+        its[fill] = info["iterations"]
+        U = mesh.apply_nonzero_constraints(U + x)        # next linearisation point
+    assert its[4] < its[1] <= its[0] + 2
+    hp.close()
+
+
+def test_mms2d_gls_prm_with_its_shipped_ilu_fill(oracle):
+    """applications_tests/gls_navier_stokes_2d/mms2d_gls.prm runs GMRES with `ilu preconditioner
+    fill = 4` (:84); its output table (mms2d_gls.output:24-26) through the mirrored C++ interface
+    with that setting: 256 cells -> velocity L2 error 3.4363e-02."""
+    from softx_2020_200_b200.mesh import BoxMesh
+    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.test_host_mirror import _match_numbering
+    mesh = BoxMesh(2, 16, 1, 1, with_q_points=True)
+    force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)
+    prm = ("subsection linear solver\n set method = gmres\n set ilu preconditioner fill = 4\n"
+           " set ilu preconditioner absolute tolerance = 1e-12\n set relative residual = 1e-4\n"
+           " set minimum residual = 1e-9\n set verbosity = verbose\nend\n")
+    s = GLSNavierStokesSolver(mesh, prm, force)
+    s.set_vector("present_solution", np.zeros(mesh.n_dofs))
+    s.solve_non_linear_system("steady", False, True)
+    nat = BoxMesh(2, 16, 1, 1, renumber=False)
+    om = oracle.BoxMesh(2, 16, 1, 1, renumber=_match_numbering(nat, mesh, 2))
+    err_u, _ = oracle.l2_error(om, s.present_solution, mms.exact_2d)
+    assert float("%.5g" % err_u) == 3.4363e-02
+    s.close()
 
 
 def _newton_gpu(hp, mesh, U0, scheme="steady", dts=None, tol=1e-6, max_it=10, lin=None, log=None):

@@ -113,3 +113,39 @@ def test_oracle_bicgstab_agrees_with_pinned_gmres(oracle):
     assert itb < itg            # two products per iteration
     with pytest.raises(RuntimeError, match="This solver is not allowed"):
         oracle.solve_linear_system(mesh, val, rhs, method="amg")
+
+
+def test_oracle_ilu_fill_levels(oracle):
+    """ILU(k) restatement: k = 0 is the matrix pattern, the pattern grows with k up to the one of the
+    complete LU factorisation, and there the factors ARE the (pivot-free) LU factors."""
+    from tests import mms
+    mesh = oracle.BoxMesh(2, 6, 1, 1)
+    val, _ = oracle.assemble(mesh, np.zeros(mesh.ndof), oracle.scheme_params("steady", None, 1.0),
+                             True, mesh.evaluate_force(mms.forcing_2d))
+    p0, a2p0 = oracle.iluk_pattern(mesh, 0)
+    assert np.array_equal(p0.rowptr, mesh.rowptr) and np.array_equal(p0.col, mesh.col)
+    assert np.array_equal(a2p0, np.arange(mesh.rowptr[-1]))
+    nnz = [int(oracle.iluk_pattern(mesh, k)[0].rowptr[-1]) for k in (0, 1, 2, 4, 200)]
+    assert nnz == sorted(nnz) and nnz[1] > nnz[0]
+    pm, a2p = oracle.iluk_pattern(mesh, 200)
+    lu, dp = oracle.ilu0(pm, oracle.pad_values(pm, a2p, val), 0.0, 1.0)
+    n = mesh.ndof
+    D = np.zeros((n, n))
+    rows = np.repeat(np.arange(n), np.diff(mesh.rowptr))
+    D[rows, mesh.col] = val
+    for i in range(n):                       # dense IKJ elimination without pivoting
+        for k in range(i):
+            if D[i, k] != 0.0:
+                D[i, k] /= D[k, k]
+                D[i, k + 1:] -= D[i, k] * D[k, k + 1:]
+    assert np.count_nonzero(D) == nnz[-1]
+    prow = np.repeat(np.arange(n), np.diff(pm.rowptr))
+    ref = D[prow, pm.col]
+    assert np.max(np.abs(lu - ref)) <= 1e-9 * np.max(np.abs(ref))
+    # block-Jacobi: the fill never crosses a block boundary
+    bp = np.array([0, n // 2, n])
+    pb, _ = oracle.iluk_pattern(mesh, 2, bp)
+    brow = np.repeat(np.arange(n), np.diff(pb.rowptr))
+    base = set(zip(rows.tolist(), mesh.col.tolist()))
+    for i, j in zip(brow.tolist(), pb.col.tolist()):
+        assert (i, j) in base or (i < n // 2) == (j < n // 2)
