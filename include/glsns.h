@@ -244,6 +244,24 @@ glsns_status glsns_solve_linear_system(glsns_context *ctx,
                                        const glsns_linear_solver_params *params,
                                        int32_t renewed_matrix, double *newton_update_out,
                                        glsns_solve_info *info);
+/* assemble_L2_projection (source/solvers/gls_navier_stokes.cc:829-914): the mass system of
+   set_initial_condition(L2projection) into system_matrix / system_rhs, scattered with the
+   non-zero constraints.  initial_at_q: [n_cells][n_q][dim+1], the initial-condition function
+   (u, p) at the quadrature points (initial_condition->uvwp.vector_value_list, :871-872).
+   Follow with glsns_solve_linear_system (the reference uses tolerances 1e-15, :800) and
+   glsns_distribute_constraints(GLSNS_VEC_NEWTON_UPDATE). */
+glsns_status glsns_assemble_l2_projection(glsns_context *ctx, const double *initial_at_q);
+/* nonzero_constraints.distribute(v) (solve_system_GMRES with initial_step = true, :1287):
+   constrained entries of a device vector take their constraint values. */
+glsns_status glsns_distribute_constraints(glsns_context *ctx, glsns_vector which);
+/* calculate_CFL (source/solvers/postprocessing_cfl.cc:34-87): max over the cells of
+   |u(cell centre)| / h * time_step, h from the cell measure and fe_degree (= fe.degree of the
+   FESystem), all-reduced (max) over the ranks.  `which`: a ghosted vector (present_solution,
+   evaluation_point, ...); shape_u_at_centre: [n_su], the scalar velocity shape functions at the
+   point of QGauss(1). */
+glsns_status glsns_calculate_cfl(glsns_context *ctx, glsns_vector which,
+                                 const double *shape_u_at_centre, int32_t fe_degree,
+                                 double time_step, double *cfl);
 /* Device-resident line-search trial (newton_non_linear_solver.h:113-116):
    evaluation_point = present_solution + alpha * newton_update, then
    apply_constraints (constrained dofs take constraint_values), ghosts updated. */

@@ -691,6 +691,44 @@ namespace glsns
         throw std::runtime_error("This solver is not allowed");
     }
 
+    // set_initial_condition(Parameters::InitialConditionType::L2projection)
+    // (gls_navier_stokes.cc:795-803): assemble_L2_projection(); solve_system_GMRES(true, 1e-15,
+    // 1e-15, true); present_solution = newton_update.  initial_at_q: the initial-condition
+    // function (u, p) at the quadrature points, [n_cells][n_q][dim+1] (what
+    // initial_condition->uvwp.vector_value_list delivers, :871-872).  finish_time_step() and
+    // postprocess() stay with the caller.
+    void
+    set_initial_condition_L2projection(const double *initial_at_q)
+    {
+      check(glsns_assemble_l2_projection(ctx, initial_at_q), "assemble_L2_projection");
+      check(glsns_get_vector(ctx, GLSNS_VEC_SYSTEM_RHS, system_rhs.data(), n_owned), "get rhs");
+      system_rhs.cached_norm = -1;
+      solve_system_GMRES(true, 1e-15, 1e-15, true);
+      for (int64_t i = 0; i < n_owned; ++i)
+        present_solution[i] = newton_update[i];
+      check(glsns_set_vector(ctx, GLSNS_VEC_PRESENT_SOLUTION, present_solution.data(), n_dofs),
+            "set present_solution");
+      check(glsns_update_ghosts(ctx, GLSNS_VEC_PRESENT_SOLUTION), "ghost import");
+      check(glsns_get_vector(ctx, GLSNS_VEC_PRESENT_SOLUTION, present_solution.data(), n_dofs),
+            "get present_solution");
+    }
+
+    // calculate_CFL(dof_handler, present_solution, fem_parameters, time_step, communicator)
+    // (source/solvers/postprocessing_cfl.cc:34-87; called from navier_stokes_base.cc:436-441)
+    double
+    calculate_CFL(const double *shape_u_at_centre, const double time_step)
+    {
+      check(glsns_set_vector(ctx, GLSNS_VEC_PRESENT_SOLUTION, present_solution.data(), n_dofs),
+            "set present_solution");
+      double    cfl = 0;
+      const int deg = (int)std::max(nsparam.fem_parameters.velocity_order,
+                                    nsparam.fem_parameters.pressure_order);
+      check(glsns_calculate_cfl(ctx, GLSNS_VEC_PRESENT_SOLUTION, shape_u_at_centre, deg, time_step,
+                                &cfl),
+            "calculate_CFL");
+      return cfl;
+    }
+
     // state the time-stepping glue sets (navier_stokes_base.h:291-293, simulation_control.h:239)
     Vector              solution_m1, solution_m2, solution_m3;
     std::vector<double> time_steps_vector = {1.0, 1.0, 1.0, 1.0};
@@ -765,7 +803,7 @@ namespace glsns
     // the body the two share in the reference (tolerance rule, ILU renewal, printing, distribute)
     void
     solve_system_Krylov(const glsns_solver_method method, const char *what,
-                        const bool /*initial_step*/, const double absolute_residual,
+                        const bool initial_step, const double absolute_residual,
                         const double relative_residual, const bool renewed_matrix)
     {
       const double linear_solver_tolerance =
@@ -793,6 +831,10 @@ namespace glsns
       if (s == GLSNS_ERR_NO_CONVERGENCE)
         throw NoConvergence(last_solve.iterations, last_solve.true_residual);
       check(s, what);
+      if (initial_step && !constraint_values.empty()) // nonzero_constraints.distribute (:1287)
+        for (int64_t i = 0; i < n_owned; ++i)
+          if (constrained[i])
+            newton_update[i] = constraint_values[i];
       if (nsparam.linear_solver.verbosity != Parameters::Verbosity::quiet)
         pcout << "  -Iterative solver took : " << last_solve.iterations << " steps " << std::endl;
     }

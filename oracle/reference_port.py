@@ -23,6 +23,9 @@ What is restated here (numpy) and in gls_oracle.c (the heavy loops), with the re
 * solve_system_BiCGStab (:1291-1340)           -> bicgstab (PARITY UNPINNED: no reference test or
   example uses `method = bicgstab`; AztecOO's AZ_bicgstab is restated from the published
   right-preconditioned algorithm, van der Vorst 1992 as in the Aztec user's guide)
+* assemble_L2_projection (:829-914) + set_initial_condition(L2projection) (:795-803)
+                                                -> assemble_l2_projection, l2_projection
+* calculate_CFL (source/solvers/postprocessing_cfl.cc:34-87)                     -> calculate_cfl
 * NewtonNonLinearSolver::solve (include/core/newton_non_linear_solver.h:76-139) -> newton_solve
 * calculate_L2_error (source/solvers/navier_stokes_base.cc:255-380)              -> l2_error
 * bdf_coefficients (source/core/bdf.cc:46-75), sdirk_coefficients (source/core/sdirk.cc:11-44)
@@ -622,6 +625,83 @@ def solve_linear_system(mesh, val, rhs, rel=1e-3, abs_=1e-8, max_iters=1000, ilu
         raise NoConvergence("%s did not converge in %d iterations" % (method, it))
     x[constrained != 0] = 0.0           # zero_constraints.distribute (:1287)
     return x, it, res
+
+
+def assemble_l2_projection(mesh, initial):
+    """assemble_L2_projection (gls_navier_stokes.cc:829-914), literally: per cell, per quadrature
+    point, local(i,j) += (phi_u_j . phi_u_i + phi_p_j phi_p_i) JxW, local_rhs(i) += (phi_u_i . u0 +
+    phi_p_i p0) JxW, then nonzero_constraints.distribute_local_to_global (:902-909, default
+    use_inhomogeneities_for_rhs = false: constrained row -> |local(i,i)| on the diagonal, zero rhs;
+    constrained column j -> rhs_i -= local(i,j) g_j).  `initial(x)`: points [m][dim] -> [m][dim+1].
+    Returns (val on mesh's CSR, rhs).  numpy, small cases."""
+    fe, dim = mesh.fe, mesh.dim
+    n_su, n_sp, nq = fe.Nu.shape[1], fe.Np.shape[1], fe.Nu.shape[0]
+    n = dim * n_su + n_sp
+    comp = np.concatenate([np.repeat(np.arange(dim), n_su), np.full(n_sp, dim)])
+    phi = np.zeros((nq, n))                       # value of the dof's own component
+    for c in range(dim):
+        phi[:, c * n_su:(c + 1) * n_su] = fe.Nu
+    phi[:, dim * n_su:] = fe.Np
+    same = comp[:, None] == comp[None, :]
+    val = np.zeros(mesh.rowptr[-1])
+    rhs = np.zeros(mesh.ndof)
+    g = np.where(mesh.constrained != 0, mesh.constraint_value, 0.0)
+    for c in range(mesh.ncell):
+        dofs = mesh.cell_dofs[c]
+        JxW = np.broadcast_to(mesh.cell_detJ[c], (nq,)) * fe.wq
+        u0 = initial(mesh.qpoints[c].reshape(nq, dim))           # [nq][dim+1]
+        local = np.einsum("qi,qj,q->ij", phi, phi, JxW) * same
+        lrhs = np.einsum("qi,qi,q->i", phi, u0[:, comp], JxW)
+        con = mesh.constrained[dofs] != 0
+        for i in range(n):
+            gi = dofs[i]
+            rs, re = mesh.rowptr[gi], mesh.rowptr[gi + 1]
+            if con[i]:
+                val[rs + np.searchsorted(mesh.col[rs:re], gi)] += abs(local[i, i])
+                continue
+            r = lrhs[i]
+            for j in range(n):
+                if local[i, j] == 0.0 and not same[i, j]:
+                    continue
+                if con[j]:
+                    r -= local[i, j] * g[dofs[j]]
+                else:
+                    val[rs + np.searchsorted(mesh.col[rs:re], dofs[j])] += local[i, j]
+            rhs[gi] += r
+    return val, rhs
+
+
+def l2_projection(mesh, initial, ilu_atol=1e-8, rel=1e-15, abs_=1e-15):
+    """set_initial_condition(L2projection) (gls_navier_stokes.cc:795-803): assemble_L2_projection,
+    solve_system_GMRES(true, 1e-15, 1e-15, true), present_solution = newton_update (constrained dofs
+    take the nonzero constraint values, :1287)."""
+    val, rhs = assemble_l2_projection(mesh, initial)
+    tol = max(rel * float(np.linalg.norm(rhs)), abs_)
+    lu, dp = ilu0(mesh, val, ilu_atol, 1.0)
+    x, it, res, ok, _ = gmres(mesh, val, lu, dp, rhs, tol, 1000, 30)
+    return mesh.apply_nonzero_constraints(x), it, ok
+
+
+def calculate_cfl(mesh, U, time_step):
+    """calculate_CFL (source/solvers/postprocessing_cfl.cc:34-87): QGauss(1), h from the cell measure
+    and fe.degree (the FESystem's: the larger of the two orders), max over the cells."""
+    dim = mesh.dim
+    n_su = mesh.fe.Nu.shape[1]
+    degree = float(max(mesh.pu, mesh.pp))
+    Nc = shape_at_centre(mesh.dim, mesh.pu)
+    cfl = 0.0
+    for c in range(mesh.ncell):
+        meas = mesh.cell_measure[c]
+        h = (math.sqrt(4.0 * meas / math.pi) if dim == 2 else (6 * meas / math.pi) ** (1.0 / 3.0)) / degree
+        u = np.array([Nc @ U[mesh.cell_dofs[c][d * n_su:(d + 1) * n_su]] for d in range(dim)])
+        cfl = max(cfl, float(np.linalg.norm(u)) / h * time_step)
+    return cfl
+
+
+def shape_at_centre(dim, p):
+    """Scalar FE_Q(p) shape functions at the point of QGauss(1), in the ordering of FETables."""
+    Nu, _, _ = _tensor_tables(dim, p, np.array([0.5]))[:3]
+    return np.asarray(Nu).reshape(-1)
 
 
 def newton_solve(mesh, U0, params, force=None, tol=1e-6, max_it=10, lin=None, hist=(None,) * 3,

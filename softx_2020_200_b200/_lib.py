@@ -86,6 +86,9 @@ SYMBOLS = {
     "glsns_setup_ilu": (C.c_int, [ctx_p, C.c_int32, C.c_double, C.c_double]),
     "glsns_solve_linear_system": (C.c_int, [ctx_p, C.POINTER(LinearSolverParams), C.c_int32,
                                             c_double_p, C.POINTER(SolveInfo)]),
+    "glsns_assemble_l2_projection": (C.c_int, [ctx_p, c_double_p]),
+    "glsns_distribute_constraints": (C.c_int, [ctx_p, C.c_int]),
+    "glsns_calculate_cfl": (C.c_int, [ctx_p, C.c_int, c_double_p, C.c_int32, C.c_double, c_double_p]),
     "glsns_line_search_point": (C.c_int, [ctx_p, C.c_double]),
     "glsns_update_ghosts": (C.c_int, [ctx_p, C.c_int]),
     "glsns_accept_evaluation_point": (C.c_int, [ctx_p]),

@@ -518,6 +518,71 @@ glsns_rhs_norm(glsns_context *ctx, double *norm)
 }
 
 glsns_status
+glsns_assemble_l2_projection(glsns_context *ctx, const double *initial_at_q)
+{
+  CHECK_CTX(ctx);
+  if (!ctx->have_mesh)
+    return fail(ctx, GLSNS_ERR_STATE, "no mesh");
+  if (!initial_at_q && ctx->n_cells)
+    return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "null pointer");
+  glsns::DevBuf<double> init;
+  GLSNS_TRY(dev_upload(ctx, init, initial_at_q,
+                       (size_t)ctx->n_cells * ctx->n_q * (ctx->dim + 1)));
+  timer_begin(ctx, T_ASSEMBLE_SYSTEM);
+  glsns_status s = launch_l2_projection(ctx, init.p);
+  timer_end(ctx, T_ASSEMBLE_SYSTEM);
+  cudaStreamSynchronize(ctx->stream);
+  timers_drain(ctx);
+  init.release();
+  GLSNS_TRY(s);
+  ctx->have_matrix = ctx->have_rhs = true;
+  ctx->have_ilu                    = false;
+  ctx->vec_set[GLSNS_VEC_SYSTEM_RHS] = true;
+  return GLSNS_OK;
+}
+
+glsns_status
+glsns_distribute_constraints(glsns_context *ctx, glsns_vector which)
+{
+  CHECK_CTX(ctx);
+  if (!ctx->have_mesh)
+    return fail(ctx, GLSNS_ERR_STATE, "no mesh");
+  if ((int)which < 0 || (int)which > 6 || !ctx->vec_set[which])
+    return fail(ctx, GLSNS_ERR_STATE, "vector has not been produced yet");
+  const int64_t len = is_ghosted_input(which) ? ctx->n_dofs : ctx->n_owned;
+  GLSNS_TRY(launch_distribute_constraints(ctx, ctx->vec[which].p, len));
+  GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GLSNS_OK;
+}
+
+glsns_status
+glsns_calculate_cfl(glsns_context *ctx, glsns_vector which, const double *shape_u_at_centre,
+                    int32_t fe_degree, double time_step, double *cfl)
+{
+  CHECK_CTX(ctx);
+  if (!ctx->have_mesh)
+    return fail(ctx, GLSNS_ERR_STATE, "no mesh");
+  if (!shape_u_at_centre || !cfl || fe_degree < 1)
+    return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "bad calculate_CFL arguments");
+  if ((int)which < 0 || (int)which > 6 || !is_ghosted_input(which) || !ctx->vec_set[which])
+    return fail(ctx, GLSNS_ERR_STATE, "calculate_CFL needs a ghosted solution vector that is set");
+  glsns::DevBuf<double> tab, out;
+  GLSNS_TRY(dev_upload(ctx, tab, shape_u_at_centre, (size_t)ctx->n_su));
+  GLSNS_TRY(dev_alloc(ctx, out, 1));
+  glsns_status s = launch_cfl(ctx, tab.p, ctx->vec[which].p, time_step, (double)fe_degree, out.p);
+  if (s == GLSNS_OK)
+    {
+      cudaMemcpyAsync(cfl, out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        s = fail(ctx, GLSNS_ERR_CUDA, "calculate_CFL");
+    }
+  else
+    cudaStreamSynchronize(ctx->stream);
+  tab.release(), out.release();
+  return s;
+}
+
+glsns_status
 glsns_setup_ilu(glsns_context *ctx, int32_t fill, double atol, double rtol)
 {
   CHECK_CTX(ctx);

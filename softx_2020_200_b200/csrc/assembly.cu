@@ -21,6 +21,8 @@
 // the scatter is a plain read-modify-write, atomic free and deterministic.
 #include <math.h>
 
+#include <algorithm>
+
 #include "context.h"
 
 namespace glsns
@@ -574,6 +576,175 @@ namespace glsns
         }
     }
 
+    // ---- assemble_L2_projection (reference: source/solvers/gls_navier_stokes.cc:829-914) ----
+    // The mass system of set_initial_condition(L2projection): local(i,j) = (phi_u_j . phi_u_i +
+    // phi_p_j phi_p_i) JxW (non-zero only inside one solution component), local_rhs(i) =
+    // (phi_u_i . u0 + phi_p_i p0) JxW with (u0, p0) the initial-condition function at the
+    // quadrature points, scattered with the NONZERO constraints (:902-909,
+    // AffineConstraints::distribute_local_to_global with its default
+    // use_inhomogeneities_for_rhs = false): couplings to a constrained column j move to the
+    // right-hand side as -local(i,j) g_j, a constrained row keeps |local(i,i)| on its diagonal
+    // and a zero right-hand side (solve_system_GMRES(initial_step = true) distributes the
+    // constraint values afterwards).  One cell per CTA, cells colour by colour.
+    struct L2Args
+    {
+      int            n_su, n_sp, n_q;
+      const double  *shape_u, *shape_p, *weights;
+      const int32_t *cell_list, *cell_dofs;
+      int            geometry_per_q;
+      const double  *det_jac, *init; // init: [n_cells][n_q][dim + 1]
+      int64_t        n_owned;
+      const uint8_t *constrained;
+      const double  *cvalues; // may be null (all constraints homogeneous)
+      const int64_t *rowptr, *diag_pos;
+      const int32_t *col;
+      double        *val, *rhs;
+    };
+
+    template <int DIM>
+    __global__ void __launch_bounds__(256)
+    l2_projection_cells(const L2Args A)
+    {
+      extern __shared__ double smem[];
+      const int     n_su = A.n_su, n_sp = A.n_sp, nq = A.n_q;
+      const int     n    = DIM * n_su + n_sp;
+      const int     tid = threadIdx.x, nt = blockDim.x;
+      const int64_t cell = A.cell_list[blockIdx.x];
+      double  *sJxW = smem;     // [nq]
+      double  *sG   = sJxW + nq; // [n] constraint values
+      int64_t *sRow = (int64_t *)(sG + n);
+      int32_t *sDof = (int32_t *)(sRow + 2 * n);
+      int32_t *sCon = sDof + n;
+      for (int q = tid; q < nq; q += nt)
+        sJxW[q] = A.det_jac[A.geometry_per_q ? (cell * nq + q) : cell] * A.weights[q];
+      for (int k = tid; k < n; k += nt)
+        {
+          const int32_t g = A.cell_dofs[cell * n + k];
+          sDof[k]         = g;
+          sCon[k]         = A.constrained[g];
+          sG[k]           = (A.constrained[g] && A.cvalues) ? A.cvalues[g] : 0.0;
+          if (g < A.n_owned)
+            sRow[2 * k] = A.rowptr[g], sRow[2 * k + 1] = A.rowptr[g + 1];
+          else
+            sRow[2 * k] = sRow[2 * k + 1] = 0;
+        }
+      __syncthreads();
+      // matrix: thread (a, b) owns the scalar mass entries of shapes a and b
+      const int nmax = n_su > n_sp ? n_su : n_sp;
+      for (int pair = tid; pair < nmax * nmax; pair += nt)
+        {
+          const int  a = pair / nmax, b = pair - a * nmax;
+          const bool uu = a < n_su && b < n_su, pp = a < n_sp && b < n_sp;
+          double     mu = 0, mp = 0;
+          for (int q = 0; q < nq; ++q)
+            {
+              if (uu)
+                mu += A.shape_u[q * n_su + a] * A.shape_u[q * n_su + b] * sJxW[q];
+              if (pp)
+                mp += A.shape_p[q * n_sp + a] * A.shape_p[q * n_sp + b] * sJxW[q];
+            }
+          for (int c = 0; c <= DIM; ++c)
+            {
+              if (c < DIM ? !uu : !pp)
+                continue;
+              const int     i = c < DIM ? c * n_su + a : DIM * n_su + a;
+              const int     j = c < DIM ? c * n_su + b : DIM * n_su + b;
+              const double  m = c < DIM ? mu : mp;
+              const int32_t gi = sDof[i];
+              if (gi >= A.n_owned)
+                continue;
+              if (sCon[i])
+                {
+                  if (a == b)
+                    A.val[A.diag_pos[gi]] += fabs(m);
+                  continue;
+                }
+              if (sCon[j])
+                continue;
+              A.val[find_col(A.col, sRow[2 * i], sRow[2 * i + 1], sDof[j])] += m;
+            }
+        }
+      // right-hand side: one thread per local dof (fixed summation order)
+      for (int i = tid; i < n; i += nt)
+        {
+          const int32_t gi = sDof[i];
+          if (gi >= A.n_owned || sCon[i])
+            continue;
+          const int     c  = i < DIM * n_su ? i / n_su : DIM;
+          const int     ns = c < DIM ? n_su : n_sp, base = c < DIM ? c * n_su : DIM * n_su;
+          const int     a  = i - base;
+          const double *N  = c < DIM ? A.shape_u : A.shape_p;
+          double        r  = 0;
+          for (int q = 0; q < nq; ++q)
+            r += N[q * ns + a] * A.init[(cell * nq + q) * (DIM + 1) + c] * sJxW[q];
+          for (int b = 0; b < ns; ++b)
+            if (sCon[base + b])
+              {
+                double m = 0;
+                for (int q = 0; q < nq; ++q)
+                  m += N[q * ns + a] * N[q * ns + b] * sJxW[q];
+                r -= m * sG[base + b];
+              }
+          A.rhs[gi] += r;
+        }
+    }
+
+    // ---- calculate_CFL (reference: source/solvers/postprocessing_cfl.cc:34-87) ----
+    // max over cells of |u(cell centre)| / h * dt, h from the cell measure (:69-72), the
+    // velocity at the one point of QGauss(1).  One thread per cell, block maxima in `partial`.
+    template <int DIM>
+    __global__ void __launch_bounds__(256)
+    cfl_cells(const int64_t n_cells, const int n_su, const int n_loc, const double degree,
+              const int32_t *__restrict__ cell_dofs, const double *__restrict__ measure,
+              const double *__restrict__ shape_centre, const double *__restrict__ U,
+              const double dt, double *__restrict__ partial)
+    {
+      __shared__ double sh[256];
+      double            best = 0;
+      for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells;
+           c += (int64_t)gridDim.x * blockDim.x)
+        {
+          const double h = (DIM == 2 ? sqrt(4. * measure[c] / M_PI) : pow(6 * measure[c] / M_PI, 1. / 3.)) / degree;
+          double       u2 = 0;
+          for (int d = 0; d < DIM; ++d)
+            {
+              double u = 0;
+              for (int a = 0; a < n_su; ++a)
+                u += shape_centre[a] * U[cell_dofs[c * n_loc + d * n_su + a]];
+              u2 += u * u;
+            }
+          best = fmax(best, sqrt(u2) / h * dt);
+        }
+      sh[threadIdx.x] = best;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1)
+        {
+          if (threadIdx.x < o)
+            sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]);
+          __syncthreads();
+        }
+      if (threadIdx.x == 0)
+        partial[blockIdx.x] = sh[0];
+    }
+    __global__ void __launch_bounds__(256)
+    max_partials_kernel(const int n, const double *__restrict__ partial, double *__restrict__ out)
+    {
+      __shared__ double sh[256];
+      double            best = 0;
+      for (int i = threadIdx.x; i < n; i += 256)
+        best = fmax(best, partial[i]);
+      sh[threadIdx.x] = best;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1)
+        {
+          if (threadIdx.x < o)
+            sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]);
+          __syncthreads();
+        }
+      if (threadIdx.x == 0)
+        *out = sh[0];
+    }
+
     size_t
     assembly_smem_bytes(int dim, int n_su, int n_sp, int nq)
     {
@@ -641,5 +812,57 @@ namespace glsns
       }
     GLSNS_CUDA(ctx, cudaGetLastError());
     return GLSNS_OK;
+  }
+  glsns_status
+  launch_l2_projection(glsns_context *ctx, const double *init_dev)
+  {
+    L2Args A;
+    A.n_su = ctx->n_su, A.n_sp = ctx->n_sp, A.n_q = ctx->n_q;
+    A.shape_u = ctx->shape_u.p, A.shape_p = ctx->shape_p.p, A.weights = ctx->weights.p;
+    A.cell_dofs      = ctx->cell_dofs.p;
+    A.geometry_per_q = ctx->geometry_per_q;
+    A.det_jac = ctx->det_jac.p, A.init = init_dev;
+    A.n_owned     = ctx->n_owned;
+    A.constrained = ctx->constrained.p;
+    A.cvalues     = ctx->cvalues.p;
+    A.rowptr = ctx->rowptr.p, A.diag_pos = ctx->diag_pos.p, A.col = ctx->col.p;
+    A.val = ctx->val.p, A.rhs = ctx->vec[GLSNS_VEC_SYSTEM_RHS].p;
+    const int    n    = ctx->dim * A.n_su + A.n_sp;
+    const size_t smem = sizeof(double) * (A.n_q + n) + sizeof(int64_t) * 2 * n + sizeof(int32_t) * 2 * n;
+    auto         kern = ctx->dim == 2 ? l2_projection_cells<2> : l2_projection_cells<3>;
+    GLSNS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLSNS_CUDA(ctx, cudaMemsetAsync(ctx->val.p, 0, sizeof(double) * ctx->nnz, ctx->stream));
+    GLSNS_CUDA(ctx, cudaMemsetAsync(A.rhs, 0, sizeof(double) * ctx->n_owned, ctx->stream));
+    for (int c = 0; c < ctx->n_colors; ++c)
+      {
+        const int32_t n_in = ctx->color_ptr[c + 1] - ctx->color_ptr[c];
+        if (n_in == 0)
+          continue;
+        A.cell_list = ctx->color_cells.p + ctx->color_ptr[c];
+        kern<<<n_in, 256, smem, ctx->stream>>>(A);
+        ctx->kernel_launches++;
+      }
+    GLSNS_CUDA(ctx, cudaGetLastError());
+    return GLSNS_OK;
+  }
+
+  // *out_dev = max over the local cells (all-reduced over ranks)
+  glsns_status
+  launch_cfl(glsns_context *ctx, const double *shape_centre_dev, const double *U, double dt,
+             double degree, double *out_dev)
+  {
+    const int64_t nc = ctx->n_cells;
+    const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>((nc + 255) / 256, (int64_t)ctx->n_sm * 8));
+    GLSNS_TRY(dev_alloc(ctx, ctx->partials, (size_t)64 * ctx->n_sm * 8));
+    if (ctx->dim == 2)
+      cfl_cells<2><<<grid, 256, 0, ctx->stream>>>(nc, ctx->n_su, ctx->n_loc, degree, ctx->cell_dofs.p,
+                                                   ctx->measure.p, shape_centre_dev, U, dt, ctx->partials.p);
+    else
+      cfl_cells<3><<<grid, 256, 0, ctx->stream>>>(nc, ctx->n_su, ctx->n_loc, degree, ctx->cell_dofs.p,
+                                                   ctx->measure.p, shape_centre_dev, U, dt, ctx->partials.p);
+    max_partials_kernel<<<1, 256, 0, ctx->stream>>>(grid, ctx->partials.p, out_dev);
+    ctx->kernel_launches += 2;
+    GLSNS_CUDA(ctx, cudaGetLastError());
+    return allreduce_max(ctx, out_dev, 1);
   }
 } // namespace glsns

@@ -31,7 +31,7 @@ namespace glsns
       int (*GroupEnd)()                                                             = nullptr;
       const char *(*GetErrorString)(int)                                            = nullptr;
     };
-    constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+    constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
 
     NcclApi &
     api()
@@ -139,6 +139,17 @@ namespace glsns
       return GLSNS_OK;
     return nccl_check(ctx,
                       api().AllReduce(dev, dev, (size_t)n, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm,
+                                      ctx->stream),
+                      "ncclAllReduce");
+  }
+
+  glsns_status
+  allreduce_max(glsns_context *ctx, double *dev, int n)
+  {
+    if (ctx->n_ranks == 1)
+      return GLSNS_OK;
+    return nccl_check(ctx,
+                      api().AllReduce(dev, dev, (size_t)n, NCCL_FLOAT64, NCCL_MAX, ctx->nccl_comm,
                                       ctx->stream),
                       "ncclAllReduce");
   }

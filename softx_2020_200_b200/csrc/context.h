@@ -257,5 +257,10 @@ namespace glsns
                          const uint8_t unique_id[128]);
   void         comm_destroy(glsns_context *ctx);
   glsns_status allreduce_sum(glsns_context *ctx, double *dev, int n);
+  glsns_status allreduce_max(glsns_context *ctx, double *dev, int n);
+  glsns_status launch_distribute_constraints(glsns_context *ctx, double *x, int64_t n);
+  glsns_status launch_l2_projection(glsns_context *ctx, const double *init_dev);
+  glsns_status launch_cfl(glsns_context *ctx, const double *shape_centre_dev, const double *U,
+                          double dt, double degree, double *out_dev);
   glsns_status halo_exchange(glsns_context *ctx, double *ghosted);
 } // namespace glsns

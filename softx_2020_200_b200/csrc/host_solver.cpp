@@ -194,6 +194,46 @@ glsnsh_solver_solve_non_linear_system(void *handle, int method, int first_iterat
     }
 }
 
+// set_initial_condition(L2projection) / calculate_CFL of the mirror.  Return 0 ok, 3
+// NoConvergence, 1 any other exception.
+int
+glsnsh_solver_set_initial_condition_l2(void *handle, const double *initial_at_q)
+{
+  SolverHandle *h = (SolverHandle *)handle;
+  try
+    {
+      h->solver->set_initial_condition_L2projection(initial_at_q);
+      return 0;
+    }
+  catch (const glsns::NoConvergence &e)
+    {
+      h->error = e.what();
+      return 3;
+    }
+  catch (const std::exception &e)
+    {
+      h->error = e.what();
+      return 1;
+    }
+}
+
+int
+glsnsh_solver_calculate_cfl(void *handle, const double *shape_u_at_centre, double time_step,
+                            double *cfl)
+{
+  SolverHandle *h = (SolverHandle *)handle;
+  try
+    {
+      *cfl = h->solver->calculate_CFL(shape_u_at_centre, time_step);
+      return 0;
+    }
+  catch (const std::exception &e)
+    {
+      h->error = e.what();
+      return 1;
+    }
+}
+
 // everything the solver wrote to pcout so far
 const char *
 glsnsh_solver_log(void *handle)

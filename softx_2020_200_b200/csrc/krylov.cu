@@ -181,6 +181,17 @@ namespace glsns
           x[t] = 0.0;
     }
 
+    // AffineConstraints::distribute for Dirichlet constraints: x_i = g_i on constrained dofs
+    __global__ void __launch_bounds__(VB)
+    distribute_kernel(const int64_t n, const uint8_t *__restrict__ constrained,
+                      const double *__restrict__ cvalues, double *__restrict__ x)
+    {
+      const int64_t stride = (int64_t)gridDim.x * VB;
+      for (int64_t t = (int64_t)blockIdx.x * VB + threadIdx.x; t < n; t += stride)
+        if (constrained[t])
+          x[t] = cvalues ? cvalues[t] : 0.0;
+    }
+
     // evaluation_point = present + alpha*update, constrained dofs <- constraint values
     __global__ void __launch_bounds__(VB)
     line_search_kernel(const int64_t n, const double alpha, const double *__restrict__ present,
@@ -261,6 +272,16 @@ namespace glsns
   {
     const int64_t n = ctx->n_owned;
     zero_constrained_kernel<<<vec_grid(ctx, n), VB, 0, ctx->stream>>>(n, ctx->constrained.p, x);
+    ctx->kernel_launches++;
+    GLSNS_CUDA(ctx, cudaGetLastError());
+    return GLSNS_OK;
+  }
+
+  glsns_status
+  launch_distribute_constraints(glsns_context *ctx, double *x, int64_t n)
+  {
+    distribute_kernel<<<vec_grid(ctx, n), VB, 0, ctx->stream>>>(n, ctx->constrained.p,
+                                                                ctx->cvalues.p, x);
     ctx->kernel_launches++;
     GLSNS_CUDA(ctx, cudaGetLastError());
     return GLSNS_OK;

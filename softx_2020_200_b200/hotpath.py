@@ -145,6 +145,25 @@ class GLSHotPath:
         self._check(self._L.glsns_assemble(self._ctx, 1 if assemble_matrix else 0,
                                            _lib.SCHEMES[scheme], _ptr(ts, c_double_p)))
 
+    def assemble_l2_projection(self, initial_at_q):
+        """assemble_L2_projection (gls_navier_stokes.cc:829-914); initial_at_q [n_cells][n_q][dim+1]."""
+        a = _c(initial_at_q, np.float64)
+        assert a.size == self.n_cells * self.n_q * (self.dim + 1)
+        self._check(self._L.glsns_assemble_l2_projection(self._ctx, _ptr(a, c_double_p)))
+
+    def distribute_constraints(self, which):
+        """nonzero_constraints.distribute on a device vector."""
+        self._check(self._L.glsns_distribute_constraints(self._ctx, _lib.VEC[which]))
+
+    def calculate_cfl(self, which, shape_u_at_centre, fe_degree, time_step):
+        """calculate_CFL (postprocessing_cfl.cc:34-87) of a ghosted device vector."""
+        t = _c(shape_u_at_centre, np.float64)
+        assert t.size == self.n_su
+        v = C.c_double()
+        self._check(self._L.glsns_calculate_cfl(self._ctx, _lib.VEC[which], _ptr(t, c_double_p),
+                                                fe_degree, time_step, C.byref(v)))
+        return v.value
+
     def rhs_norm(self):
         v = C.c_double()
         self._check(self._L.glsns_rhs_norm(self._ctx, C.byref(v)))

@@ -29,6 +29,10 @@ def _bind(L):
     L.glsnsh_solver_set_time_steps.argtypes = [C.c_void_p, _lib.c_double_p, C.c_int]
     L.glsnsh_solver_solve_non_linear_system.restype = C.c_int
     L.glsnsh_solver_solve_non_linear_system.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.glsnsh_solver_set_initial_condition_l2.restype = C.c_int
+    L.glsnsh_solver_set_initial_condition_l2.argtypes = [C.c_void_p, _lib.c_double_p]
+    L.glsnsh_solver_calculate_cfl.restype = C.c_int
+    L.glsnsh_solver_calculate_cfl.argtypes = [C.c_void_p, _lib.c_double_p, C.c_double, _lib.c_double_p]
     L.glsnsh_solver_log.restype = C.c_char_p
     L.glsnsh_solver_log.argtypes = [C.c_void_p]
     L._glsnsh_solver_bound = True
@@ -75,6 +79,26 @@ class GLSNavierStokesSolver:
             raise NoConvergence(self._L.glsnsh_solver_error(self._h).decode(), {})
         if rc:
             raise RuntimeError(self._L.glsnsh_solver_error(self._h).decode())
+
+    def set_initial_condition_l2_projection(self, initial_at_q):
+        """set_initial_condition(L2projection) (gls_navier_stokes.cc:795-803); initial_at_q
+        [n_cells, n_q, dim+1]: the initial-condition function at the quadrature points."""
+        a = np.ascontiguousarray(initial_at_q, dtype=np.float64)
+        assert a.size == self.mesh.n_cells * self.mesh.n_q * (self.mesh.dim + 1)
+        rc = self._L.glsnsh_solver_set_initial_condition_l2(self._h, a.ctypes.data_as(_lib.c_double_p))
+        if rc == 3:
+            raise NoConvergence(self._L.glsnsh_solver_error(self._h).decode(), {})
+        if rc:
+            raise RuntimeError(self._L.glsnsh_solver_error(self._h).decode())
+
+    def calculate_cfl(self, shape_u_at_centre, time_step):
+        """calculate_CFL (postprocessing_cfl.cc:34-87) of present_solution."""
+        t = np.ascontiguousarray(shape_u_at_centre, dtype=np.float64)
+        v = C.c_double()
+        if self._L.glsnsh_solver_calculate_cfl(self._h, t.ctypes.data_as(_lib.c_double_p), time_step,
+                                               C.byref(v)):
+            raise RuntimeError(self._L.glsnsh_solver_error(self._h).decode())
+        return v.value
 
     @property
     def log(self):

@@ -149,3 +149,36 @@ def test_oracle_ilu_fill_levels(oracle):
     base = set(zip(rows.tolist(), mesh.col.tolist()))
     for i, j in zip(brow.tolist(), pb.col.tolist()):
         assert (i, j) in base or (i < n // 2) == (j < n // 2)
+
+
+def _linear_field(dim):
+    """A field inside every FE_Q(p >= 1) space: its L2 projection is its nodal interpolant."""
+    def f(x):
+        out = np.zeros((len(x), dim + 1))
+        for c in range(dim + 1):
+            out[:, c] = 0.3 * (c + 1) + sum((0.2 + 0.1 * c + 0.05 * d) * x[:, d] for d in range(dim))
+        return out
+    return f
+
+
+@pytest.mark.parametrize("dim,n,pu,pp", [(2, 4, 1, 1), (2, 3, 2, 2), (2, 3, 2, 1), (3, 2, 2, 2)])
+def test_oracle_l2_projection_and_cfl(oracle, dim, n, pu, pp):
+    """assemble_L2_projection + set_initial_condition(L2projection): a field of the FE space comes
+    back as its nodal values (constrained dofs carry the constraint values); calculate_CFL of a
+    uniform velocity is |u| dt / h with h from the cell measure."""
+    f = _linear_field(dim)
+    lid = lambda x: f(x)[:, :dim]                     # Dirichlet data consistent with the field
+    bcs = {b: ("function", lid) for b in range(2 * dim)}
+    mesh = oracle.BoxMesh(dim, n, pu, pp, bcs=bcs)
+    U, it, ok = oracle.l2_projection(mesh, f, rel=1e-13, abs_=1e-14)
+    assert ok
+    exact = f(mesh.dof_coords)[np.arange(mesh.ndof), mesh.dof_comp]
+    assert np.max(np.abs(U - exact)) <= 1e-10
+    # uniform velocity (1, 2[, 2]): CFL = |u| dt / h
+    V = np.zeros(mesh.ndof)
+    vel = np.array([1.0, 2.0, 2.0])[:dim]
+    for c in range(dim):
+        V[mesh.dof_comp == c] = vel[c]
+    meas = mesh.cell_measure[0]
+    h = (np.sqrt(4 * meas / np.pi) if dim == 2 else (6 * meas / np.pi) ** (1 / 3)) / max(pu, pp)
+    assert abs(oracle.calculate_cfl(mesh, V, 0.01) - np.linalg.norm(vel) * 0.01 / h) <= 1e-14
