@@ -385,6 +385,70 @@ def test_l2_projection_initial_condition_through_the_cpp_mirror(oracle):
     s.close()
 
 
+CAVITY_PRM = """
+# examples/01-cavity/cavity.prm as shipped (physical properties :15-17, FEM :63-66,
+# non-linear solver :78-83, linear solver :88-97); BASELINE.json configs[0]
+subsection physical properties
+    set kinematic viscosity            = %g
+end
+subsection FEM
+    set velocity order            = 1
+    set pressure order            = 1
+end
+subsection non-linear solver
+  set tolerance               = 1e-8
+  set max iterations          = 10
+  set residual precision      = 2
+  set verbosity               = verbose
+end
+subsection linear solver
+  set method                                 = gmres
+  set max iters                              = 5000
+  set relative residual                      = 1e-9
+  set minimum residual                       = 1e-9
+  set ilu preconditioner fill                = 1
+  set ilu preconditioner absolute tolerance  = 1e-12
+  set ilu preconditioner relative tolerance  = 1.00
+  set verbosity               = verbose
+end
+"""
+
+
+@pytest.mark.parametrize("nu,n", [(1.0, 64), (0.005, 32)])
+def test_example_01_cavity_prm_as_shipped(oracle, nu, n):
+    """BASELINE.json configs[0], the reference's CPU-runnable case: 2D lid-driven cavity
+    (hyper_cube -1:1 colorized, bc 0-2 noslip, bc 3 u = 1; examples/01-cavity/cavity.prm:20-60),
+    Q1-Q1, steady Newton + GMRES/ILU(1) with the file's own solver settings, at its shipped
+    viscosity (initial refinement 6 = 64^2 cells) and at Re = 400 (nu = 0.005), through the mirrored
+    GLSNavierStokesSolver against the oracle's Newton solve: same Newton iteration count, GMRES
+    counts within +-2, same discrete solution."""
+    import re
+    from softx_2020_200_b200.mesh import BoxMesh
+    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.test_host_mirror import _match_numbering
+    bcs = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (3, "function", (1.0, 0.0))]
+    mesh = BoxMesh(2, n, 1, 1, bcs=bcs)
+    s = GLSNavierStokesSolver(mesh, CAVITY_PRM % nu, None)
+    s.set_vector("present_solution", mesh.initial_state())
+    s.solve_non_linear_system("steady", False, True)
+    its = [int(k) for k in re.findall(r"-Iterative solver took : (\d+) steps", s.log)]
+    lid = lambda x: np.stack([np.ones(len(x)), 0 * x[:, 0]], axis=1)
+    obcs = {0: ("noslip",), 1: ("noslip",), 2: ("noslip",), 3: ("function", lid)}
+    nat = BoxMesh(2, n, 1, 1, bcs=bcs, renumber=False)
+    om = oracle.BoxMesh(2, n, 1, 1, bcs=obcs, renumber=_match_numbering(nat, mesh, 2))
+    log = []
+    U_ref, it_ref, res_ref = oracle.newton_solve(
+        om, om.apply_nonzero_constraints(np.zeros(om.ndof)), oracle.scheme_params("steady", None, nu),
+        None, tol=1e-8, max_it=10, log=log,
+        lin=dict(rel=1e-9, abs_=1e-9, max_iters=5000, ilu_atol=1e-12, ilu_fill=1))
+    assert len(its) == it_ref and res_ref < 1e-8
+    for k, (k_ref, _) in zip(its, log):
+        assert abs(k - k_ref) <= 2
+    U = s.present_solution
+    assert np.linalg.norm(U - U_ref) <= 1e-7 * np.linalg.norm(U_ref)
+    s.close()
+
+
 def test_gmres_no_convergence_and_state_errors(oracle):
     from softx_2020_200_b200 import GlsnsError, NoConvergence
     mesh = oracle.BoxMesh(2, 8, 1, 1)
