@@ -292,6 +292,8 @@ glsns_status glsns_ilu_apply(glsns_context *ctx, const double *r, double *z);
    [2n..3n) / [3n..4n) = lower / upper: per resident warp w, at [8w..8w+7), the clock
    cycles it spent per pipeline stage and its item count (see tools/trsv_trace.py);
    [4n..5n) / [5n..6n) = lower / upper: when each row's totals reached the solver's mailbox;
+   [6n..8n), [8n..10n) likewise: when the helper began the last item of the row's group and
+   when it had all the inputs (t_publish is [10 n]);
    row_warp (may be NULL) = resident warp each row was scheduled on in the two
    sweeps (bit 30: solved behind its predecessor on the same warp, -1: diagonal row). */
 glsns_status glsns_ilu_apply_trace(glsns_context *ctx, const double *r, double *z,

@@ -14,7 +14,8 @@ LIB = os.path.join(HERE, "libglsns.so")
 SOURCES = ["api.cu", "assembly.cu", "sparse.cu", "trsv.cu", "krylov.cu", "comm.cu", "host_mesh.cpp", "host_solver.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC,-fopenmp,-O3", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-fPIC,-fopenmp,-O3", "-ccbin", "/usr/bin/g++"] + \
+    os.environ.get("GLSNS_NVCC_FLAGS", "").split()   # e.g. -DGLSNS_TRSV_ITEM=96 (tuning experiments)
 
 
 def _stale(target, deps):

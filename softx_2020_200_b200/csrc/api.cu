@@ -781,15 +781,15 @@ glsns_ilu_apply_trace(glsns_context *ctx, const double *r, double *z, uint64_t *
     return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "null pointer");
   const int64_t                 n = ctx->n_owned;
   glsns::DevBuf<unsigned long long> tr;
-  GLSNS_TRY(dev_alloc(ctx, tr, (size_t)6 * n));
-  cudaMemsetAsync(tr.p, 0, sizeof(unsigned long long) * 6 * n, ctx->stream);
+  GLSNS_TRY(dev_alloc(ctx, tr, (size_t)10 * n));
+  cudaMemsetAsync(tr.p, 0, sizeof(unsigned long long) * 10 * n, ctx->stream);
   GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->tvec.p, r, sizeof(double) * n, cudaMemcpyHostToDevice,
                                   ctx->stream));
   glsns_status s = launch_ilu_apply(ctx, ctx->tvec.p, ctx->zg.p, tr.p);
   if (s == GLSNS_OK)
     {
       cudaMemcpyAsync(z, ctx->zg.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
-      cudaMemcpyAsync(t_publish, tr.p, sizeof(uint64_t) * 6 * n, cudaMemcpyDeviceToHost,
+      cudaMemcpyAsync(t_publish, tr.p, sizeof(uint64_t) * 10 * n, cudaMemcpyDeviceToHost,
                       ctx->stream);
       s = check_counters(ctx, "ILU apply");
     }

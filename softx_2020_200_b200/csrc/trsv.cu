@@ -26,7 +26,7 @@
 //     are resident — hence the cooperative launch, which refuses instead of hanging.
 //   * STREAMS.  After every factorisation the factor entries are re-packed, per
 //     sweep, into one contiguous byte stream per warp in exactly the order that warp
-//     consumes them: per item (<= 128 entries of one group) a 16-byte header, the
+//     consumes them: per item (<= 64 entries of one group) a 16-byte header, the
 //     inverted diagonal, the in-group triangle, the window couplings, the column
 //     indices and the values.  The solve then reads HBM strictly sequentially, and
 //     one lane moves a whole item into the warp's shared-memory ring with a single
@@ -54,7 +54,10 @@ namespace glsns
     constexpr long long          SPIN_LIMIT = 1ll << 21; // a bug guard (seconds), never reached in a correct run
 
     constexpr int TRSV_G = 4;          // rows per group
-    constexpr int TS_CH  = 128;        // entries per item
+#ifndef GLSNS_TRSV_ITEM
+#define GLSNS_TRSV_ITEM 64
+#endif
+    constexpr int TS_CH  = GLSNS_TRSV_ITEM; // entries per item (a multiple of 32)
     constexpr int TS_U   = TS_CH / 32; // entries per lane and item
     constexpr int TS_WIN = 16;         // rows of the chain kept in the window
     constexpr int TS_BG  = 4;          // groups per block (the solver's unit)
@@ -310,12 +313,12 @@ namespace glsns
     //     block (kept in a tiny shared-memory window) and M, G the block's recurrence
     //     solved ahead of time; publish.  The chain advances 16 rows per step.
     constexpr int TS_MBOX  = 8;  // mailbox entries (blocks) per team
-    constexpr int TS_HSLOT = TS_OFF_COL0 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 4624
+    constexpr int TS_HSLOT = TS_OFF_COL0 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 2320 (64-entry items)
     constexpr int TS_SSLOT = TS_OFF_C + 256 * TS_BR;                        // 4112
     // team area: windows 4 x 128 | mailbox 8 x 128 | solved counter 16 | barriers
-    constexpr int TS_TEAM_AREA = 1792;
+    constexpr int TS_TEAM_AREA = 2048;
     static_assert(TS_MBOX == 8 && TS_NWIN == 4 &&
-                    128 * TS_NWIN + 128 * TS_MBOX + 16 + 8 * 5 * TS_NSLOT <= TS_TEAM_AREA,
+                    128 * TS_NWIN + 128 * TS_MBOX + 16 + 8 * 12 * TS_NSLOT <= TS_TEAM_AREA,
                   "team area");
 
     template <bool UPPER>
@@ -585,6 +588,9 @@ namespace glsns
             const int            flags = h.y, m = flags & 31, cp = pad4(flags >> 16);
             const double        *sval  = reinterpret_cast<const double *>(S + TS_OFF_COL0 + 4 * cp);
             long long            spins = 0;
+            unsigned long long   t_rs = 0, t_det = 0; // debugging aid (trace)
+            if (trace)
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_rs));
             for (;;)
               {
 #pragma unroll
@@ -631,6 +637,8 @@ namespace glsns
                     break;
                   }
               }
+            if (trace)
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_det));
             if (flags & IT_LAST)
               {
                 // the group is complete: fold in the right-hand side, total over the
@@ -678,6 +686,8 @@ namespace glsns
                         unsigned long long tns;
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
                         trace[4 * trace_n + h.x + (lane >> 3)] = tns;
+                        trace[6 * trace_n + h.x + (lane >> 3)] = t_rs;  // began the group's last item
+                        trace[8 * trace_n + h.x + (lane >> 3)] = t_det; // had all its inputs
                       }
                   }
 #pragma unroll
@@ -730,7 +740,12 @@ namespace glsns
 
     struct TrsvConfig
     {
-      int teams = 3, helpers = 3; // per SM
+      // per SM.  Helpers are the servers of a team's queue of groups: tools/trsv_trace.py shows
+      // the critical group waiting for its helper to get to it, not for its inputs, so many
+      // helpers per solver (and small items, which make their rings small) win: 3 x (1+3)
+      // with 128-entry items 10.8 ms per application at 64^3 cells, 2 x (1+5) 8.75 ms,
+      // 2 x (1+6) with 96-entry items 8.51 ms, 2 x (1+7) with 64-entry items 8.33 ms.
+      int teams = 2, helpers = 7;
     };
 
     size_t
@@ -748,7 +763,7 @@ namespace glsns
           t.teams = atoi(getenv("GLSNS_TRSV_TEAMS"));
         if (getenv("GLSNS_TRSV_HELPERS"))
           t.helpers = atoi(getenv("GLSNS_TRSV_HELPERS"));
-        t.helpers = std::max(1, std::min(4, t.helpers));
+        t.helpers = std::max(1, std::min(11, t.helpers));
         t.teams   = std::max(1, std::min(16 / (t.helpers + 1), t.teams));
         while (t.teams > 1 && t.teams * team_smem_bytes(t.helpers) > (size_t)TS_SMEM_MAX)
           --t.teams;
@@ -1249,7 +1264,7 @@ namespace glsns
         DevBuf<unsigned long long> tr;
         GLSNS_TRY(dev_alloc(ctx, r, (size_t)n));
         GLSNS_TRY(dev_alloc(ctx, z, (size_t)n));
-        GLSNS_TRY(dev_alloc(ctx, tr, (size_t)6 * n));
+        GLSNS_TRY(dev_alloc(ctx, tr, (size_t)10 * n));
         GLSNS_TRY(dev_alloc(ctx, ctx->ytmp, (size_t)n));
         GLSNS_TRY(dev_alloc(ctx, ctx->dinv, (size_t)n));
         GLSNS_CUDA(ctx, cudaMemsetAsync(r.p, 0, sizeof(double) * n, ctx->stream));
@@ -1276,7 +1291,7 @@ namespace glsns
         glsns_status                    st    = time_apply(t_cur);
         for (int round = 0; round < rounds && st == GLSNS_OK; ++round)
           {
-            GLSNS_CUDA(ctx, cudaMemsetAsync(tr.p, 0, sizeof(unsigned long long) * 6 * n, ctx->stream));
+            GLSNS_CUDA(ctx, cudaMemsetAsync(tr.p, 0, sizeof(unsigned long long) * 10 * n, ctx->stream));
             if ((st = launch_ilu_apply(ctx, r.p, z.p, tr.p)) != GLSNS_OK ||
                 (st = check_counters(ctx, "ILU apply (schedule tuning)")) != GLSNS_OK)
               break;

@@ -245,12 +245,14 @@ class GLSHotPath:
         """(z, t_lower, t_upper, warp_lower, warp_upper): publish times in ns per row and sweep."""
         r = np.ascontiguousarray(r, dtype=np.float64)
         n = self.n_owned
-        z, t, w = np.empty(n), np.zeros(6 * n, dtype=np.uint64), np.zeros(2 * n, dtype=np.int32)
+        z, t, w = np.empty(n), np.zeros(10 * n, dtype=np.uint64), np.zeros(2 * n, dtype=np.int32)
         self._check(self._L.glsns_ilu_apply_trace(
             self._ctx, _ptr(r, c_double_p), _ptr(z, c_double_p),
             t.ctypes.data_as(C.POINTER(C.c_uint64)), _ptr(w, c_i32_p)))
         self.last_trace_polls = (t[2 * n:3 * n], t[3 * n:4 * n])
-        self.last_trace_posts = (t[4 * n:5 * n], t[5 * n:])  # when a row's totals reached the mailbox
+        self.last_trace_posts = (t[4 * n:5 * n], t[5 * n:6 * n])  # when a row's totals reached the mailbox
+        self.last_trace_begin = (t[6 * n:7 * n], t[7 * n:8 * n])  # when its helper began the group's last item
+        self.last_trace_inputs = (t[8 * n:9 * n], t[9 * n:])      # ... and had all its inputs
         return z, t[:n], t[n:2 * n], w[:n], w[n:]
 
     def ilu_levels(self):

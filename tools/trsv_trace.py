@@ -24,7 +24,9 @@ if len(sys.argv) > 2:  # raw trace for offline analysis: ns offsets from the fir
         t = t.astype(np.int64); return np.where(t > 0, t - ref, -1).astype(np.int32)
     r0l, r0u = int(tl[wl >= 0].min()), int(tu[wu >= 0].min())
     np.savez_compressed(sys.argv[2], tl=rel(tl, r0l), tu=rel(tu, r0u), pl=rel(hp.last_trace_posts[0], r0l),
-                        pu=rel(hp.last_trace_posts[1], r0u), wl=wl, wu=wu)
+                        pu=rel(hp.last_trace_posts[1], r0u), wl=wl, wu=wu,
+                        bl=rel(hp.last_trace_begin[0], r0l), bu=rel(hp.last_trace_begin[1], r0u),
+                        il=rel(hp.last_trace_inputs[0], r0l), iu=rel(hp.last_trace_inputs[1], r0u))
 pct = lambda v: [float(np.percentile(v, p)) for p in (10, 50, 90)] + [len(v)] if len(v) else None
 out = {"n": n}
 for name, t, tp, w, upper in (("lower", tl, hp.last_trace_posts[0], wl, False),
