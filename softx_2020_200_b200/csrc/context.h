@@ -230,6 +230,8 @@ namespace glsns
   glsns_status launch_spmv(glsns_context *ctx, const double *x, double *y);
   glsns_status ilu_analyse(glsns_context *ctx, const int64_t *rowptr, const int32_t *col);
   glsns_status ilu_install_fill(glsns_context *ctx, int32_t fill);
+  void         iluk_symbolic_host(int64_t n, const int64_t *rowptr, const int32_t *col, int fill,
+                                  std::vector<int64_t> &prow, std::vector<int32_t> &pcol);
   glsns_status matrix_values_to_host(glsns_context *ctx, const double *dev_padded, double *host_base);
   glsns_status matrix_values_from_host(glsns_context *ctx, const double *host_base);
   glsns_status launch_ilu_factor(glsns_context *ctx, double atol, double rtol);

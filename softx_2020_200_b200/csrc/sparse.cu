@@ -957,4 +957,29 @@ namespace glsns
     return check_counters(ctx, "ILU(0) factorisation");
   }
 
+  void
+  iluk_symbolic_host(const int64_t n, const int64_t *rowptr, const int32_t *col, const int fill,
+                     std::vector<int64_t> &prow, std::vector<int32_t> &pcol)
+  {
+    iluk_symbolic(n, rowptr, col, fill, prow, pcol);
+  }
 } // namespace glsns
+
+// Host-only entry point (no device needed): the level-of-fill pattern glsns_setup_ilu installs
+// for `ilu preconditioner fill` = fill, for tests of the symbolic phase.  Returns the number of
+// entries; out_row_ptr [n+1] and out_col_idx [returned count] may be NULL to query the size.
+extern "C" int64_t
+glsnsh_iluk_pattern(int64_t n, const int64_t *row_ptr, const int32_t *col_idx, int32_t fill,
+                    int64_t *out_row_ptr, int32_t *out_col_idx)
+{
+  if (n < 0 || !row_ptr || (row_ptr[n] && !col_idx) || fill < 0 || fill > 200)
+    return -1;
+  std::vector<int64_t> prow;
+  std::vector<int32_t> pcol;
+  glsns::iluk_symbolic_host(n, row_ptr, col_idx, fill, prow, pcol);
+  if (out_row_ptr)
+    memcpy(out_row_ptr, prow.data(), sizeof(int64_t) * (size_t)(n + 1));
+  if (out_col_idx)
+    memcpy(out_col_idx, pcol.data(), sizeof(int32_t) * pcol.size());
+  return (int64_t)pcol.size();
+}

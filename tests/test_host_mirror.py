@@ -165,3 +165,28 @@ def test_cavity_boundary_conditions_first_listed_wins():
     lid_edge = (np.abs(xyz[:, 1] - 1) < 1e-12) & (np.abs(np.abs(xyz[:, 0]) - 1) < 1e-12)
     assert np.all(val[lid_edge] == 0.0)          # walls are listed before the lid
     assert np.all(con[comp == 3] == 0)           # pressure is never constrained
+
+
+@pytest.mark.parametrize("dim,n,pu,pp,fill", [(2, 8, 1, 1, 1), (2, 8, 1, 1, 4), (2, 4, 2, 2, 2),
+                                               (3, 3, 1, 1, 1), (3, 2, 2, 2, 1), (2, 6, 2, 1, 0)])
+def test_level_of_fill_pattern_equals_the_oracle(oracle, dim, n, pu, pp, fill):
+    """The symbolic phase of `ilu preconditioner fill = k` (host code of libglsns.so, no device):
+    the pattern glsns_setup_ilu installs against the oracle's independent restatement of Ifpack's
+    level-of-fill graph."""
+    import ctypes as C
+    from softx_2020_200_b200 import _lib
+    L = _lib.lib()
+    L.glsnsh_iluk_pattern.restype = C.c_int64
+    L.glsnsh_iluk_pattern.argtypes = [C.c_int64, _lib.c_i64_p, _lib.c_i32_p, C.c_int32, _lib.c_i64_p,
+                                      _lib.c_i32_p]
+    mesh = oracle.BoxMesh(dim, n, pu, pp)
+    rp = np.ascontiguousarray(mesh.rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(mesh.col, dtype=np.int32)
+    p = lambda a, t: a.ctypes.data_as(t)
+    nnz = L.glsnsh_iluk_pattern(mesh.ndof, p(rp, _lib.c_i64_p), p(col, _lib.c_i32_p), fill, None, None)
+    orp, ocol = np.empty(mesh.ndof + 1, dtype=np.int64), np.empty(nnz, dtype=np.int32)
+    assert L.glsnsh_iluk_pattern(mesh.ndof, p(rp, _lib.c_i64_p), p(col, _lib.c_i32_p), fill,
+                                 p(orp, _lib.c_i64_p), p(ocol, _lib.c_i32_p)) == nnz
+    pm, _ = oracle.iluk_pattern(mesh, fill)
+    assert np.array_equal(orp, pm.rowptr) and np.array_equal(ocol, pm.col)
+    assert L.glsnsh_iluk_pattern(mesh.ndof, p(rp, _lib.c_i64_p), p(col, _lib.c_i32_p), -1, None, None) == -1
