@@ -1,38 +1,46 @@
-// ILU(0) application z = U^-1 L^-1 r: the two triangular solves of every GMRES
+// ILU application z = U^-1 L^-1 r: the two triangular solves of every Krylov
 // iteration (what Ifpack_ILU::ApplyInverse does behind TrilinosWrappers::
 // PreconditionILU, reference call site source/solvers/gls_navier_stokes.cc:1276-1279).
 //
 // The solves keep the host's row ordering exactly (the preconditioner, and with it
 // the GMRES iteration count, must be the reference's), so the parallelism is what
 // the dependency DAG of that ordering offers.  Under Cuthill-McKee that DAG is
-// deep and narrow (3D Q2-Q2, 32^3 cells: 2742 levels of ~100 mesh nodes each) and
+// deep and narrow (3D Q2-Q2, 64^3 cells: 5558 levels of ~390 mesh nodes each) and
 // ~90 % of its critical edges join a node to the node numbered just before it.  A
 // level-synchronous or row-per-warp solve pays one L2 store->load hop (0.36 us on
 // B200, tools/hop_latency.cu) plus a warp reduction per level; this kernel is built
 // to take HBM, the hop and most instructions off that critical path:
 //
 //   * GROUPS.  Up to 4 consecutive rows with identical column patterns (the dim+1
-//     dofs of a mesh node) are solved together: one index stream, a 4x4 triangle.
-//   * CHAINS.  The host schedules the groups on the resident warps level by level
-//     (trsv_analyse): a group whose predecessor in the numbering is one of its
-//     dependencies goes to the warp that solves that predecessor, right behind it.
-//     The solutions of the last 16 rows of the chain stay in the warp's registers
-//     (one per lane, a shift register over the row distance), so the entries that
-//     couple a group to its recent predecessors never wait for L2; only the
-//     dependencies on other chains travel through L2, and most of those have
-//     several levels of slack.  Every warp's list is sorted by level, which makes the
-//     waiting deadlock free (the blocked group of lowest level would wait on a group
-//     of lower level that is some warp's current or earlier item) provided all warps
-//     are resident — hence the cooperative launch, which refuses instead of hanging.
+//     dofs of a mesh node) share one index stream.
+//   * BLOCKS.  Up to 4 consecutive linked groups (<= 16 rows) are the unit of the
+//     recurrence.  Everything a block needs from outside was numbered before its
+//     first row, so solving its rows in one step cannot dead-lock; its own triangle T
+//     and its couplings F to the 16 chain rows before it are packed SOLVED after every
+//     factorisation (M = T^-1, G = T^-1 F), so a block is one 16 x 32 product
+//     out = -(M totals + G w) and the chain advances 16 rows per step.
+//   * CHAINS.  The host schedules the blocks on the resident TEAMS level by level
+//     (trsv_analyse): a block whose predecessor in the numbering is one of its
+//     dependencies goes to the team that solves that predecessor, right behind it,
+//     and reads the last 16 rows of the chain from a window in shared memory instead
+//     of through L2; only the dependencies on other chains travel through L2.  Every
+//     team's list is sorted by a key that grows along every dependency (the block
+//     level, or, after the profile-guided pass, the time its inputs were published in
+//     a traced run), which makes the waiting dead-lock free (the blocked block with
+//     the smallest key waits on a block with a smaller one, which is some team's
+//     current or earlier item) provided all teams are resident -- hence the
+//     cooperative launch, which refuses instead of hanging.
+//   * TEAMS.  1 solver warp (the recurrence and nothing else) + K helper warps (they
+//     stream the groups' factor entries, gather the solution entries, reduce, and
+//     post the totals in the block's mailbox entry); 2 teams x (1 + 7) warps per SM.
 //   * STREAMS.  After every factorisation the factor entries are re-packed, per
 //     sweep, into one contiguous byte stream per warp in exactly the order that warp
-//     consumes them: per item (<= 64 entries of one group) a 16-byte header, the
-//     inverted diagonal, the in-group triangle, the window couplings, the column
-//     indices and the values.  The solve then reads HBM strictly sequentially, and
-//     one lane moves a whole item into the warp's shared-memory ring with a single
-//     bulk copy (cp.async.bulk, completion on an mbarrier) several items ahead of
-//     the one being solved: ~220 KB x 148 SMs of factor data in flight, ~5 issue
-//     slots per item instead of ~150 for per-entry copies.
+//     consumes them: per helper item (<= 64 entries of one group) a 16-byte header,
+//     the column indices and the values of the group's rows; per solver item (one
+//     block) the header and the solved recurrence.  The solve then reads HBM strictly
+//     sequentially, and one lane moves a whole item into the warp's shared-memory
+//     ring with a single bulk copy (cp.async.bulk, completion on an mbarrier) several
+//     items ahead of the one being solved.
 //   * The solution vector itself carries readiness: it is pre-filled with an
 //     all-ones NaN pattern and a consumer re-reads an entry until it has been
 //     overwritten (no flags, no fences).
