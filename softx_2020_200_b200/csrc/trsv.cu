@@ -1319,12 +1319,19 @@ namespace glsns
             std::swap(keep_l, ctx->trsv_l), std::swap(keep_u, ctx->trsv_u);
             std::vector<int32_t> rw_l = ctx->trsv_row_warp_l, rw_u = ctx->trsv_row_warp_u;
             int32_t              dummy;
-            if ((st = schedule(false, ctx->trsv_l, dummy, when.data())) != GLSNS_OK ||
-                (st = schedule(true, ctx->trsv_u, dummy, when.data() + n)) != GLSNS_OK)
-              break;
-            float t_new = 0;
-            if ((st = time_apply(t_new)) != GLSNS_OK)
-              break;
+            float                t_new = 1e30f;
+            // a candidate that cannot be built (no memory for a second set of streams) or does
+            // not run is simply not taken: the schedule in use stays
+            const bool cand_ok = schedule(false, ctx->trsv_l, dummy, when.data()) == GLSNS_OK &&
+                                 schedule(true, ctx->trsv_u, dummy, when.data() + n) == GLSNS_OK &&
+                                 time_apply(t_new) == GLSNS_OK;
+            if (!cand_ok)
+              {
+                cudaStreamSynchronize(ctx->stream);
+                cudaGetLastError();
+                cudaMemsetAsync(ctx->counters.p, 0, 2 * sizeof(int32_t), ctx->stream);
+                t_new = 1e30f;
+              }
             if (getenv("GLSNS_TRSV_DEBUG"))
               fprintf(stderr, "trsv_analyse: tuning round %d: %.3f ms -> %.3f ms\n", round, t_cur, t_new);
             if (t_new < t_cur)
