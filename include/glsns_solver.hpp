@@ -230,6 +230,35 @@ namespace glsns
       }
     };
 
+    // `initial conditions` (include/solvers/initial_conditions.h:36-121).  The function `uvwp` is
+    // evaluated on the host (deal.II's ParsedFunction); the solver takes its values.
+    enum class InitialConditionType
+    {
+      none,
+      L2projection,
+      viscous,
+      nodal
+    };
+    struct InitialConditions
+    {
+      InitialConditionType type      = InitialConditionType::nodal;
+      double               viscosity = 1;
+      void
+      parse_parameters(const ParameterFile &prm)
+      {
+        const std::string op = prm.get("initial conditions", "type", "nodal");
+        if (op == "L2projection")
+          type = InitialConditionType::L2projection;
+        else if (op == "viscous")
+          type = InitialConditionType::viscous;
+        else if (op == "nodal")
+          type = InitialConditionType::nodal;
+        else // Patterns::Selection("L2projection|viscous|nodal") rejects anything else
+          throw std::runtime_error("initial conditions: type must be one of <L2projection|viscous|nodal>");
+        viscosity = prm.get_double("initial conditions", "viscosity", 1);
+      }
+    };
+
     // `FEM`, `physical properties`, `velocity source` (parameters.cc:169-210, 803-831)
     struct FEM
     {
@@ -611,9 +640,11 @@ namespace glsns
     Parameters::FEM                fem_parameters;
     Parameters::PhysicalProperties physical_properties;
     Parameters::VelocitySource     velocitySource;
+    Parameters::InitialConditions  initial_condition;
     void
     parse(const ParameterFile &prm)
     {
+      initial_condition.parse_parameters(prm);
       non_linear_solver.parse_parameters(prm);
       linear_solver.parse_parameters(prm);
       fem_parameters.parse_parameters(prm);
@@ -637,15 +668,7 @@ namespace glsns
       check(glsns_create(cuda_device, &ctx), "glsns_create");
       check(glsns_set_fe(ctx, &fe), "glsns_set_fe");
       check(glsns_set_mesh(ctx, &mesh), "glsns_set_mesh");
-      const double omega[3] = {nsparam.velocitySource.omega_x, nsparam.velocitySource.omega_y,
-                               nsparam.velocitySource.omega_z};
-      check(glsns_set_physics(ctx, nsparam.physical_properties.viscosity,
-                              nsparam.velocitySource.type ==
-                                  Parameters::VelocitySource::VelocitySourceType::srf ?
-                                GLSNS_SOURCE_SRF :
-                                GLSNS_SOURCE_NONE,
-                              omega),
-            "glsns_set_physics");
+      set_physics();
       check(glsns_set_forcing(ctx, forcing_at_q), "glsns_set_forcing");
       constrained.assign(mesh.constrained, mesh.constrained + mesh.n_dofs);
       if (mesh.constraint_values)
@@ -713,6 +736,55 @@ namespace glsns
             "get present_solution");
     }
 
+    // set_nodal_values (source/solvers/navier_stokes_base.cc:926-944): VectorTools::interpolate
+    // of the initial-condition function (done by the host: `initial_nodal`, [n_dofs]), then
+    // nonzero_constraints.distribute, present_solution = newton_update.
+    void
+    set_nodal_values(const double *initial_nodal)
+    {
+      for (int64_t i = 0; i < n_dofs; ++i)
+        present_solution[i] =
+          (constrained[i] && !constraint_values.empty()) ? constraint_values[i] :
+          constrained[i]                                  ? 0.0 :
+                                                            initial_nodal[i];
+      for (int64_t i = 0; i < n_owned; ++i)
+        newton_update[i] = present_solution[i];
+    }
+
+    // set_initial_condition(initial_condition_type, restart = false)
+    // (gls_navier_stokes.cc:784-828); finish_time_step() / postprocess() stay with the caller,
+    // restart (read_checkpoint) is out of scope.
+    void
+    set_initial_condition(const Parameters::InitialConditionType initial_condition_type,
+                          const double *initial_nodal, const double *initial_at_q)
+    {
+      if (initial_condition_type == Parameters::InitialConditionType::L2projection)
+        set_initial_condition_L2projection(initial_at_q);
+      else if (initial_condition_type == Parameters::InitialConditionType::nodal)
+        set_nodal_values(initial_nodal);
+      else if (initial_condition_type == Parameters::InitialConditionType::viscous)
+        { // a steady solve at the artificial viscosity of the `initial conditions` subsection
+          set_nodal_values(initial_nodal);
+          const double viscosity                = nsparam.physical_properties.viscosity;
+          nsparam.physical_properties.viscosity = nsparam.initial_condition.viscosity;
+          set_physics();
+          try
+            {
+              PhysicsSolver<Vector>::solve_non_linear_system(TimeSteppingMethod::steady, false, true);
+            }
+          catch (...)
+            {
+              nsparam.physical_properties.viscosity = viscosity;
+              set_physics();
+              throw;
+            }
+          nsparam.physical_properties.viscosity = viscosity;
+          set_physics();
+        }
+      else
+        throw std::runtime_error("GLSNS - Initial condition could not be set"); // :825
+    }
+
     // calculate_CFL(dof_handler, present_solution, fem_parameters, time_step, communicator)
     // (source/solvers/postprocessing_cfl.cc:34-87; called from navier_stokes_base.cc:436-441)
     double
@@ -739,8 +811,28 @@ namespace glsns
     {
       return ctx;
     }
+    const NavierStokesSolverParameters &
+    parameters() const
+    {
+      return nsparam;
+    }
 
   private:
+    // viscosity and velocity source of nsparam -> the device context
+    void
+    set_physics()
+    {
+      const double omega[3] = {nsparam.velocitySource.omega_x, nsparam.velocitySource.omega_y,
+                               nsparam.velocitySource.omega_z};
+      check(glsns_set_physics(ctx, nsparam.physical_properties.viscosity,
+                              nsparam.velocitySource.type ==
+                                  Parameters::VelocitySource::VelocitySourceType::srf ?
+                                GLSNS_SOURCE_SRF :
+                                GLSNS_SOURCE_NONE,
+                              omega),
+            "glsns_set_physics");
+    }
+
     void
     check(glsns_status s, const char *what) const
     {

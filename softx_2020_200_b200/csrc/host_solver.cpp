@@ -78,7 +78,7 @@ glsnsh_newton_toy(int use_skip_newton, int skip_iterations, double *x_out)
   return solver.n_matrix;
 }
 
-// Parse a .prm text; out[0..8] = non-linear {tolerance, max iterations, skip iterations, solver},
+// Parse a .prm text; out[0..17] (18 doubles) = non-linear {tolerance, max iterations, skip iterations, solver},
 // linear {relative, minimum, max iters, fill, atol}; returns 0 or 1 (+ message in err).
 int
 glsnsh_parse_prm(const char *text, double *out, char *err, int err_len)
@@ -95,6 +95,7 @@ glsnsh_parse_prm(const char *text, double *out, char *err, int err_len)
       out[10] = (int)p.linear_solver.solver, out[11] = p.physical_properties.viscosity;
       out[12] = p.fem_parameters.velocity_order, out[13] = p.fem_parameters.pressure_order;
       out[14] = (int)p.velocitySource.type, out[15] = p.velocitySource.omega_z;
+      out[16] = (int)p.initial_condition.type, out[17] = p.initial_condition.viscosity;
       return 0;
     }
   catch (const std::exception &e)
@@ -203,6 +204,33 @@ glsnsh_solver_set_initial_condition_l2(void *handle, const double *initial_at_q)
   try
     {
       h->solver->set_initial_condition_L2projection(initial_at_q);
+      return 0;
+    }
+  catch (const glsns::NoConvergence &e)
+    {
+      h->error = e.what();
+      return 3;
+    }
+  catch (const std::exception &e)
+    {
+      h->error = e.what();
+      return 1;
+    }
+}
+
+// set_initial_condition(type): type < 0 takes the `initial conditions` subsection's, otherwise
+// Parameters::InitialConditionType (0 none, 1 L2projection, 2 viscous, 3 nodal).
+int
+glsnsh_solver_set_initial_condition(void *handle, int type, const double *initial_nodal,
+                                    const double *initial_at_q)
+{
+  SolverHandle *h = (SolverHandle *)handle;
+  try
+    {
+      h->solver->set_initial_condition(
+        type < 0 ? h->solver->parameters().initial_condition.type :
+                   static_cast<glsns::Parameters::InitialConditionType>(type),
+        initial_nodal, initial_at_q);
       return 0;
     }
   catch (const glsns::NoConvergence &e)

@@ -31,6 +31,9 @@ def _bind(L):
     L.glsnsh_solver_solve_non_linear_system.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.glsnsh_solver_set_initial_condition_l2.restype = C.c_int
     L.glsnsh_solver_set_initial_condition_l2.argtypes = [C.c_void_p, _lib.c_double_p]
+    L.glsnsh_solver_set_initial_condition.restype = C.c_int
+    L.glsnsh_solver_set_initial_condition.argtypes = [C.c_void_p, C.c_int, _lib.c_double_p,
+                                                      _lib.c_double_p]
     L.glsnsh_solver_calculate_cfl.restype = C.c_int
     L.glsnsh_solver_calculate_cfl.argtypes = [C.c_void_p, _lib.c_double_p, C.c_double, _lib.c_double_p]
     L.glsnsh_solver_log.restype = C.c_char_p
@@ -86,6 +89,22 @@ class GLSNavierStokesSolver:
         a = np.ascontiguousarray(initial_at_q, dtype=np.float64)
         assert a.size == self.mesh.n_cells * self.mesh.n_q * (self.mesh.dim + 1)
         rc = self._L.glsnsh_solver_set_initial_condition_l2(self._h, a.ctypes.data_as(_lib.c_double_p))
+        if rc == 3:
+            raise NoConvergence(self._L.glsnsh_solver_error(self._h).decode(), {})
+        if rc:
+            raise RuntimeError(self._L.glsnsh_solver_error(self._h).decode())
+
+    def set_initial_condition(self, initial_nodal=None, initial_at_q=None, type=None):
+        """set_initial_condition (gls_navier_stokes.cc:784-828) with the `initial conditions` type of
+        the .prm (or `type`: "L2projection" | "viscous" | "nodal"); initial_nodal [n_dofs]: the
+        interpolated initial-condition function, initial_at_q [n_cells, n_q, dim+1]: its values at
+        the quadrature points (L2projection only)."""
+        t = -1 if type is None else {"none": 0, "L2projection": 1, "viscous": 2, "nodal": 3}[type]
+        a = None if initial_nodal is None else np.ascontiguousarray(initial_nodal, dtype=np.float64)
+        q = None if initial_at_q is None else np.ascontiguousarray(initial_at_q, dtype=np.float64)
+        rc = self._L.glsnsh_solver_set_initial_condition(
+            self._h, t, None if a is None else a.ctypes.data_as(_lib.c_double_p),
+            None if q is None else q.ctypes.data_as(_lib.c_double_p))
         if rc == 3:
             raise NoConvergence(self._L.glsnsh_solver_error(self._h).decode(), {})
         if rc:

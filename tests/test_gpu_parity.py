@@ -449,6 +449,46 @@ def test_example_01_cavity_prm_as_shipped(oracle, nu, n):
     s.close()
 
 
+def test_set_initial_condition_viscous_and_nodal_through_the_cpp_mirror(oracle):
+    """set_initial_condition (gls_navier_stokes.cc:784-828) with `initial conditions: type = viscous`
+    (a steady solve at the subsection's artificial viscosity, :811-822, the physical viscosity
+    restored afterwards) and `nodal` (set_nodal_values, navier_stokes_base.cc:926-944) on the 2D
+    cavity, against the oracle's Newton solves."""
+    from softx_2020_200_b200.mesh import BoxMesh
+    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.test_host_mirror import _match_numbering
+    n, nu, nu_ic = 16, 0.02, 1.0
+    bcs = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (3, "function", (1.0, 0.0))]
+    mesh = BoxMesh(2, n, 1, 1, bcs=bcs)
+    prm = CAVITY_PRM % nu + "subsection initial conditions\n set type = viscous\n set viscosity = %g\nend\n" % nu_ic
+    s = GLSNavierStokesSolver(mesh, prm, None)
+    s.set_initial_condition(initial_nodal=np.zeros(mesh.n_dofs))        # type from the .prm
+    lid = lambda x: np.stack([np.ones(len(x)), 0 * x[:, 0]], axis=1)
+    obcs = {0: ("noslip",), 1: ("noslip",), 2: ("noslip",), 3: ("function", lid)}
+    nat = BoxMesh(2, n, 1, 1, bcs=bcs, renumber=False)
+    om = oracle.BoxMesh(2, n, 1, 1, bcs=obcs, renumber=_match_numbering(nat, mesh, 2))
+    lin = dict(rel=1e-9, abs_=1e-9, max_iters=5000, ilu_atol=1e-12, ilu_fill=1)
+    U0 = om.apply_nonzero_constraints(np.zeros(om.ndof))
+    U_ic, _, _ = oracle.newton_solve(om, U0, oracle.scheme_params("steady", None, nu_ic), None,
+                                     tol=1e-8, max_it=10, lin=lin)
+    assert np.linalg.norm(s.present_solution - U_ic) <= 1e-7 * np.linalg.norm(U_ic)
+    # the physical viscosity is back: the steady solve from that start matches the oracle's at nu
+    s.solve_non_linear_system("steady", False, True)
+    U_ref, _, res = oracle.newton_solve(om, U_ic, oracle.scheme_params("steady", None, nu), None,
+                                        tol=1e-8, max_it=10, lin=lin)
+    assert res < 1e-8
+    assert np.linalg.norm(s.present_solution - U_ref) <= 1e-6 * np.linalg.norm(U_ref)
+    # nodal: the interpolated values with the non-zero constraints distributed
+    vals = np.random.default_rng(3).uniform(-1, 1, mesh.n_dofs)
+    s.set_initial_condition(initial_nodal=vals, type="nodal")
+    con = mesh.array("constrained") != 0
+    expect = np.where(con, mesh.array("constraint_values"), vals)
+    assert np.array_equal(s.present_solution, expect)
+    with pytest.raises(RuntimeError, match="Initial condition could not be set"):
+        s.set_initial_condition(initial_nodal=vals, type="none")
+    s.close()
+
+
 def test_gmres_no_convergence_and_state_errors(oracle):
     from softx_2020_200_b200 import GlsnsError, NoConvergence
     mesh = oracle.BoxMesh(2, 8, 1, 1)

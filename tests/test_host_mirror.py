@@ -50,7 +50,7 @@ def test_newton_drivers_on_the_reference_fake_backend(skip, skip_iterations):
 def _parse(text):
     from softx_2020_200_b200 import _lib
     L = _lib.lib()
-    out = (C.c_double * 16)()
+    out = (C.c_double * 18)()
     err = C.create_string_buffer(256)
     rc = L.glsnsh_parse_prm(text.encode(), out, err, 256)
     return rc, list(out), err.value.decode()
@@ -63,6 +63,7 @@ def test_prm_defaults_match_the_reference():
     assert v[:4] == [1e-6, 10, 1, 0]                      # tolerance, max it, skip it, newton
     assert v[4:11] == [1e-3, 1e-8, 1000, 0, 1e-8, 1.0, 0]  # rel, abs, max iters, fill, atol, rtol, gmres
     assert v[11:16] == [1.0, 1, 1, 0, 0.0]
+    assert v[16:18] == [3, 1.0]                            # initial conditions: nodal, viscosity 1
 
 
 def test_prm_reads_the_shipped_cavity_file_syntax():
@@ -106,6 +107,13 @@ end
     assert rc == 1 and "invalid iterative solver type" in err
     rc, _, err = _parse("subsection non-linear solver\n set verbosity = loud\nend\n")
     assert rc == 1 and "Invalid verbosity level" in err
+    # include/solvers/initial_conditions.h:69-121 (as in taylor-green-vortex_gls_*.prm)
+    rc, v, _ = _parse("subsection initial conditions\n set type = L2projection\n set viscosity = 0.1\nend\n")
+    assert rc == 0 and v[16:18] == [1, 0.1]
+    rc, v, _ = _parse("subsection initial conditions\n set type = viscous\nend\n")
+    assert rc == 0 and v[16:18] == [2, 1.0]
+    rc, _, err = _parse("subsection initial conditions\n set type = random\nend\n")
+    assert rc == 1 and "L2projection|viscous|nodal" in err
 
 
 def _match_numbering(A, B, dim):
