@@ -6,7 +6,10 @@ cpu_baseline / ``--impl reference`` legs may import this module.  The product pa
 
 Parity status: PINNED against the reference's golden files (tests/test_oracle_golden.py):
 ``tests/solvers/restart_01.output`` (GMRES iterations 8/6/10, true residuals, L2 error) and
-``applications_tests/gls_navier_stokes_3d/mms3d_gls.output`` (3D Q1-Q1 MMS errors).
+``applications_tests/gls_navier_stokes_3d/mms3d_gls.output`` (3D Q1-Q1 MMS errors),
+``applications_tests/gls_navier_stokes_2d/taylor-green-vortex_gls_{sdirk3,sdirk2,bdf1}.mpirun=2.output``
+(periodic Taylor-Green vortex: CFL, enstrophy, kinetic energy and L2 error of every step, which pin the
+transient terms, the L2 projection, calculate_CFL and the SDIRK stage logic).
 
 What is restated here (numpy) and in gls_oracle.c (the heavy loops), with the reference file:line:
 
@@ -26,6 +29,10 @@ What is restated here (numpy) and in gls_oracle.c (the heavy loops), with the re
 * assemble_L2_projection (:829-914) + set_initial_condition(L2projection) (:795-803)
                                                 -> assemble_l2_projection, l2_projection
 * calculate_CFL (source/solvers/postprocessing_cfl.cc:34-87)                     -> calculate_cfl
+* NavierStokesBase::iterate, SDIRK stages (source/solvers/navier_stokes_base.cc:461-505) -> sdirk_step
+* calculate_kinetic_energy / calculate_enstrophy (source/solvers/postprocessing_*.cc)  -> kinetic_energy,
+  enstrophy
+* periodic boundary conditions (type = periodic): BoxMesh(periodic=...)
 * NewtonNonLinearSolver::solve (include/core/newton_non_linear_solver.h:76-139) -> newton_solve
 * calculate_L2_error (source/solvers/navier_stokes_base.cc:255-380)              -> l2_error
 * bdf_coefficients (source/core/bdf.cc:46-75), sdirk_coefficients (source/core/sdirk.cc:11-44)
@@ -200,9 +207,16 @@ class BoxMesh:
     face (colorize=false, boundary id 0). First listed bc wins on shared edges/corners, as
     VectorTools::interpolate_boundary_values does not overwrite existing constraint lines.
     renumber: "cm" (Cuthill–McKee, gls_navier_stokes.cc:70), "none", or an explicit new-index array.
+    periodic: directions d whose faces 2d / 2d+1 carry `type = periodic` (boundary_conditions.h,
+    DoFTools::make_periodicity_constraints in navier_stokes_base.cc): the dofs of the hi face are
+    identified with those of the lo face.  Here: the cells refer to the lo-face dofs directly (the
+    same global system as resolving x_hi = x_lo in distribute_local_to_global); the hi-face dofs
+    stay in the numbering (deal.II counts them) as constrained rows with a unit diagonal
+    (``periodic_slave`` / ``periodic_master``).  Use an even n (the 2^dim cell colouring).
     """
 
-    def __init__(self, dim, n, pu, pp, lo=-1.0, hi=1.0, bcs=None, renumber="cm", nq1=None):
+    def __init__(self, dim, n, pu, pp, lo=-1.0, hi=1.0, bcs=None, renumber="cm", nq1=None,
+                 periodic=()):
         assert pu % pp == 0
         self.dim, self.ncd, self.pu, self.pp = dim, n, pu, pp
         self.lo, self.hi = float(lo), float(hi)
@@ -240,6 +254,21 @@ class BoxMesh:
         cd = [self.vel_dof[un, c] for c in range(dim)] + [self.p_dof[pn]]
         cell_dofs = np.concatenate(cd, axis=1)
         assert cell_dofs.min() >= 0
+        # periodic identification (provisional numbering)
+        master_node = np.arange(nnode)
+        for d in periodic:
+            assert n % 2 == 0
+            mi = self.node_idx[master_node].copy()
+            mi[mi[:, d] == gu - 1, d] = 0
+            master_node = (mi * stride).sum(axis=1)
+        master_of = np.arange(self.ndof)
+        if len(periodic):
+            sl = np.nonzero(master_node != np.arange(nnode))[0]
+            for c in range(dim):
+                master_of[self.vel_dof[sl, c]] = self.vel_dof[master_node[sl], c]
+            slp = sl[has_p[sl]]
+            master_of[self.p_dof[slp]] = self.p_dof[master_node[slp]]
+            cell_dofs = master_of[cell_dofs]
         # dof meta
         comp = np.zeros(self.ndof, dtype=np.int32)
         dof_node = np.zeros(self.ndof, dtype=np.int64)
@@ -268,6 +297,9 @@ class BoxMesh:
                 new = constrained[d_] == 0
                 constrained[d_[new]] = 1
                 cvalue[d_[new]] = vals[new, c]
+        slave = master_of != np.arange(self.ndof)
+        constrained[slave] = 1
+        cvalue[slave] = 0.0
         # renumbering
         if isinstance(renumber, str) and renumber == "cm":
             new_of_old = self._cuthill_mckee(cell_dofs)
@@ -283,6 +315,8 @@ class BoxMesh:
         self.dof_coords = coords[dof_node[inv]]
         self.constrained = np.ascontiguousarray(constrained[inv])
         self.constraint_value = cvalue[inv]
+        self.periodic_slave = np.nonzero(slave[inv])[0]                  # new ids
+        self.periodic_master = new_of_old[master_of[inv[self.periodic_slave]]]
         # geometry (affine Cartesian cells)
         self.cell_invJ = np.ascontiguousarray(
             np.broadcast_to(np.eye(dim) / self.hx, (self.ncell, dim, dim)))
@@ -348,6 +382,21 @@ class BoxMesh:
         """Forcing values at the quadrature points (gls_navier_stokes.cc:364-369)."""
         f = fn(self.qpoints.reshape(-1, self.dim))
         return np.ascontiguousarray(f[:, :self.dim].reshape(self.ncell, self.fe.nq, self.dim))
+
+    def distribute_periodic(self, U):
+        """x_hi = x_lo on the periodic faces (AffineConstraints::distribute for those lines)."""
+        U = U.copy()
+        U[self.periodic_slave] = U[self.periodic_master]
+        return U
+
+    def unit_diagonal_on_periodic_slaves(self, val):
+        """Rows of the identified hi-face dofs: no cell refers to them, give them a unit diagonal
+        (deal.II's constrained rows carry a positive diagonal as well; nothing couples to them)."""
+        if self.periodic_slave.size:
+            rs = self.rowptr[self.periodic_slave]
+            assert np.all(self.rowptr[self.periodic_slave + 1] - rs == 1)
+            val[rs] = 1.0
+        return val
 
     def apply_nonzero_constraints(self, U):
         """PhysicsSolver::apply_constraints -> nonzero_constraints.distribute
@@ -443,11 +492,15 @@ def assemble(mesh, U, params, assemble_matrix=True, force=None, U1=None, U2=None
         lb = np.zeros((mesh.ncell, n)) if return_local else None
         L.glso_assemble(*common, _p(lM, c_double_p), _p(lb, c_double_p))
         if return_local:
+            if assemble_matrix and getattr(mesh, "periodic_slave", np.zeros(0)).size:
+                mesh.unit_diagonal_on_periodic_slaves(val)
             return val, rhs, lM, lb
     else:
         ptr, order, ncolor = mesh.color_lists()
         L.glso_set_num_threads(C.c_int(threads))
         L.glso_assemble_mt(*common, _p(ptr, c_i32_p), _p(order, c_i32_p), C.c_int(ncolor))
+    if assemble_matrix and getattr(mesh, "periodic_slave", np.zeros(0)).size:
+        mesh.unit_diagonal_on_periodic_slaves(val)
     return val, rhs
 
 
@@ -668,6 +721,8 @@ def assemble_l2_projection(mesh, initial):
                 else:
                     val[rs + np.searchsorted(mesh.col[rs:re], dofs[j])] += local[i, j]
             rhs[gi] += r
+    if getattr(mesh, "periodic_slave", np.zeros(0)).size:
+        mesh.unit_diagonal_on_periodic_slaves(val)
     return val, rhs
 
 
@@ -679,7 +734,10 @@ def l2_projection(mesh, initial, ilu_atol=1e-8, rel=1e-15, abs_=1e-15):
     tol = max(rel * float(np.linalg.norm(rhs)), abs_)
     lu, dp = ilu0(mesh, val, ilu_atol, 1.0)
     x, it, res, ok, _ = gmres(mesh, val, lu, dp, rhs, tol, 1000, 30)
-    return mesh.apply_nonzero_constraints(x), it, ok
+    x = mesh.apply_nonzero_constraints(x)
+    if getattr(mesh, "periodic_slave", np.zeros(0)).size:
+        x = mesh.distribute_periodic(x)
+    return x, it, ok
 
 
 def calculate_cfl(mesh, U, time_step):
@@ -735,6 +793,53 @@ def newton_solve(mesh, U0, params, force=None, tol=1e-6, max_it=10, lin=None, hi
         last_res = current_res
         it += 1
     return present, it, current_res
+
+
+def sdirk_step(mesh, order, U_m1, dt, nu, force=None, tol=1e-6, max_it=10, lin=None):
+    """One time step of `method = sdirk2 | sdirk3` as NavierStokesBase::iterate runs it
+    (source/solvers/navier_stokes_base.cc:461-505): stage k solves with method sdirk<order>_k from
+    the previous stage's result, the stage results become solution_m2 / solution_m3; solution_m1 is
+    the solution of the previous time step.  Returns the solution at the end of the step."""
+    dts = [dt] * 4
+    hist = [U_m1, None, None]
+    U = U_m1
+    for k in range(1, order + 1):
+        pr = scheme_params("sdirk%d_%d" % (order, k), dts, nu)
+        U, _, _ = newton_solve(mesh, U, pr, force, tol=tol, max_it=max_it, lin=lin, hist=tuple(hist))
+        if k < order:
+            hist[k] = U
+    return U
+
+
+def kinetic_energy(mesh, U):
+    """calculate_kinetic_energy (source/solvers/postprocessing_kinetic_energy.cc:34-84):
+    sum_q 0.5 |u_h|^2 JxW / volume on QGauss(fe.degree + 1)."""
+    dim, fe = mesh.dim, FETables(mesh.dim, mesh.pu, mesh.pp, max(mesh.pu, mesh.pp) + 1)
+    JxW = mesh.cell_detJ[:, None] * fe.wq[None, :]
+    Uc, n_su = U[mesh.cell_dofs], fe.n_su
+    ke = 0.0
+    for c in range(dim):
+        uh = Uc[:, c * n_su:(c + 1) * n_su] @ fe.Nu.T
+        ke += 0.5 * float((uh * uh * JxW).sum())
+    return ke / float(JxW.sum())
+
+
+def enstrophy(mesh, U):
+    """calculate_enstrophy (source/solvers/postprocessing_enstrophy.cc:34-93): sum_q 0.5 |curl u_h|^2
+    JxW / volume on QGauss(fe.degree + 1)."""
+    dim, fe = mesh.dim, FETables(mesh.dim, mesh.pu, mesh.pp, max(mesh.pu, mesh.pp) + 1)
+    JxW = mesh.cell_detJ[:, None] * fe.wq[None, :]
+    Uc, n_su = U[mesh.cell_dofs], fe.n_su
+    # real-space gradients: d/dx_d = sum_r dxi_r/dx_d d/dxi_r, cell_invJ[c][r][d] = dxi_r/dx_d
+    gN = np.einsum("qar,crd->cqad", fe.dNu, mesh.cell_invJ)               # [cell][q][a][d]
+    g = np.stack([np.einsum("ca,cqad->cqd", Uc[:, c * n_su:(c + 1) * n_su], gN) for c in range(dim)],
+                 axis=2)                                                  # [cell][q][comp][d]
+    pairs = [(1, 0)] if dim == 2 else [(2, 1), (0, 2), (1, 0)]
+    en = 0.0
+    for i, j in pairs:                                                    # (du_i/dx_j - du_j/dx_i)
+        w = g[:, :, i, j] - g[:, :, j, i]
+        en += 0.5 * float((w * w * JxW).sum())
+    return en / float(JxW.sum())
 
 
 def l2_error(mesh, U, exact):

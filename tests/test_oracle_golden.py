@@ -182,3 +182,74 @@ def test_oracle_l2_projection_and_cfl(oracle, dim, n, pu, pp):
     meas = mesh.cell_measure[0]
     h = (np.sqrt(4 * meas / np.pi) if dim == 2 else (6 * meas / np.pi) ** (1 / 3)) / max(pu, pp)
     assert abs(oracle.calculate_cfl(mesh, V, 0.01) - np.linalg.norm(vel) * 0.01 / h) <= 1e-14
+
+
+# ---- Taylor-Green vortex: the reference's transient goldens -----------------------------------
+TWO_PI = 6.28318530718      # `set grid arguments = 0 : 6.28318530718 : true`
+
+
+def _taylor_green(t, nu=1.0):
+    """initial conditions / analytical solution of taylor-green-vortex_gls_*.prm (:33-36, :44-48)."""
+    def f(x):
+        e = np.exp(-2 * nu * t)
+        return np.stack([e * np.cos(x[:, 0]) * np.sin(x[:, 1]), -e * np.sin(x[:, 0]) * np.cos(x[:, 1]),
+                         -0.25 * (np.cos(2 * x[:, 0]) + np.cos(2 * x[:, 1]))], axis=1)
+    return f
+
+
+TG_LIN = dict(rel=1e-4, abs_=1e-9, max_iters=5000, ilu_atol=1e-5)   # linear solver :108-116 (ILU(0)
+# here instead of the file's fill 1 on 2 ranks: only the path to the Newton-converged state differs)
+
+
+@pytest.mark.parametrize("order", [3, 2])
+def test_taylor_green_vortex_sdirk_output(oracle, order):
+    """applications_tests/gls_navier_stokes_2d/taylor-green-vortex_gls_sdirk{3,2}.mpirun=2.output:
+    4096 periodic Q2-Q1 cells, 37507 dofs, L2-projected initial condition, ONE sdirk step of 0.1.
+    Pins, digit for digit as printed: calculate_CFL of the projected field (1.80106), enstrophy and
+    kinetic energy before (0.5, 0.25) and after the step, and the velocity L2 error to the three
+    digits the solver tolerances leave stable (tightening GMRES / Newton moves the 4th:
+    1.38187e-4 ... 1.38256e-4 around the reference's 1.38223e-4)."""
+    g = REF["taylor_green_vortex_sdirk%d" % order]
+    mesh = oracle.BoxMesh(2, 64, 2, 1, lo=0.0, hi=TWO_PI, bcs={}, periodic=(0, 1))
+    assert (mesh.ncell, mesh.ndof) == (g["cells"], g["dofs"])
+    U0, _, ok = oracle.l2_projection(mesh, _taylor_green(0.0), ilu_atol=1e-5)
+    assert ok
+    assert "%.6g" % oracle.enstrophy(mesh, U0) == g["enstrophy_0"]
+    assert "%.6g" % oracle.kinetic_energy(mesh, U0) == g["kinetic_energy_0"]
+    assert "%.6g" % oracle.calculate_cfl(mesh, U0, 0.1) == g["cfl"][0]
+    U1 = oracle.sdirk_step(mesh, order, U0, 0.1, 1.0, None, tol=1e-6, max_it=5, lin=TG_LIN)
+    assert "%.6g" % oracle.enstrophy(mesh, U1) == g["enstrophy"][0]
+    assert "%.6g" % oracle.kinetic_energy(mesh, U1) == g["kinetic_energy"][0]
+    err = oracle.l2_error(mesh, U1, _taylor_green(0.1))[0]
+    assert abs(err - float(g["l2_error_velocity"][0])) <= 5e-4 * err
+
+
+def test_taylor_green_vortex_bdf1_output(oracle):
+    """taylor-green-vortex_gls_bdf1.mpirun=2.output: 1024 periodic Q1-Q1 cells, 3267 dofs, 100 BDF1
+    steps of 0.01.  Every printed CFL number, enstrophy, kinetic energy and velocity L2 error of the
+    100 steps, as printed (6 significant digits; the error table's 5)."""
+    g = REF["taylor_green_vortex_bdf1"]
+    mesh = oracle.BoxMesh(2, 32, 1, 1, lo=0.0, hi=TWO_PI, bcs={}, periodic=(0, 1))
+    assert (mesh.ncell, mesh.ndof) == (g["cells"], g["dofs"])
+    U, _, ok = oracle.l2_projection(mesh, _taylor_green(0.0), ilu_atol=1e-5)
+    assert ok
+    assert "%.6g" % oracle.enstrophy(mesh, U) == g["enstrophy_0"]
+    assert "%.6g" % oracle.kinetic_energy(mesh, U) == g["kinetic_energy_0"]
+    pr = oracle.scheme_params("bdf1", [0.01] * 4, 1.0)
+    exact = {k: 0 for k in ("cfl", "enstrophy", "kinetic_energy", "l2_error_velocity", "error_table")}
+    for k in range(100):
+        cfl = oracle.calculate_cfl(mesh, U, 0.01)
+        U, _, _ = oracle.newton_solve(mesh, U, pr, None, tol=1e-6, max_it=5, lin=TG_LIN,
+                                      hist=(U, None, None))
+        vals = dict(cfl=cfl, enstrophy=oracle.enstrophy(mesh, U),
+                    kinetic_energy=oracle.kinetic_energy(mesh, U),
+                    l2_error_velocity=oracle.l2_error(mesh, U, _taylor_green(0.01 * (k + 1)))[0])
+        for name, v in vals.items():
+            ref = float(g[name][k])
+            assert abs(v - ref) <= 2e-5 * abs(ref), (name, k, v, ref)
+            exact[name] += "%.6g" % v == g[name][k]
+        t, e = g["error_table"][k]
+        assert t == "%.4f" % (0.01 * (k + 1))
+        exact["error_table"] += "%.4e" % vals["l2_error_velocity"] == e
+    # digit for digit, up to the rare last-digit flip that the solver tolerances allow
+    assert all(c >= 95 for c in exact.values()), exact
