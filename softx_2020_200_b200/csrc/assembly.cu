@@ -745,6 +745,19 @@ namespace glsns
         *out = sh[0];
     }
 
+    // Constrained rows that no cell contributed to get a unit diagonal.  A Dirichlet row always
+    // receives |local(i,i)| > 0 from its cells; a row stays empty when the host has identified its
+    // dof with another one in the cell -> dof table (periodic faces: the cells refer to the master
+    // dofs, the slave rows are only carried along), and ILU needs a pivot there.
+    __global__ void __launch_bounds__(256)
+    unit_diagonal_on_empty_constrained_rows(const int64_t n, const uint8_t *__restrict__ constrained,
+                                            const int64_t *__restrict__ diag_pos, double *val)
+    {
+      const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (i < n && constrained[i] && val[diag_pos[i]] == 0.0)
+        val[diag_pos[i]] = 1.0;
+    }
+
     size_t
     assembly_smem_bytes(int dim, int n_su, int n_sp, int nq)
     {
@@ -810,6 +823,13 @@ namespace glsns
         kern<<<n_in, 256, smem, ctx->stream>>>(A);
         ctx->kernel_launches++;
       }
+    if (assemble_matrix && ctx->n_owned)
+      {
+        unit_diagonal_on_empty_constrained_rows<<<(unsigned)((ctx->n_owned + 255) / 256), 256, 0,
+                                                  ctx->stream>>>(ctx->n_owned, ctx->constrained.p,
+                                                                 ctx->diag_pos.p, ctx->val.p);
+        ctx->kernel_launches++;
+      }
     GLSNS_CUDA(ctx, cudaGetLastError());
     return GLSNS_OK;
   }
@@ -840,6 +860,13 @@ namespace glsns
           continue;
         A.cell_list = ctx->color_cells.p + ctx->color_ptr[c];
         kern<<<n_in, 256, smem, ctx->stream>>>(A);
+        ctx->kernel_launches++;
+      }
+    if (ctx->n_owned)
+      {
+        unit_diagonal_on_empty_constrained_rows<<<(unsigned)((ctx->n_owned + 255) / 256), 256, 0,
+                                                  ctx->stream>>>(ctx->n_owned, ctx->constrained.p,
+                                                                 ctx->diag_pos.p, ctx->val.p);
         ctx->kernel_launches++;
       }
     GLSNS_CUDA(ctx, cudaGetLastError());

@@ -489,6 +489,56 @@ def test_set_initial_condition_viscous_and_nodal_through_the_cpp_mirror(oracle):
     s.close()
 
 
+def test_taylor_green_vortex_bdf1_golden_on_gpu(oracle):
+    """The reference's own transient golden through the CUDA path:
+    applications_tests/gls_navier_stokes_2d/taylor-green-vortex_gls_bdf1.mpirun=2.output (1024
+    periodic Q1-Q1 cells, 3267 dofs, nu = 1, BDF1 steps of 0.01).  Initial condition by
+    glsns_assemble_l2_projection + GMRES, then 30 Newton-converged BDF1 steps; the CFL number of
+    every step comes from glsns_calculate_cfl, enstrophy / kinetic energy / velocity L2 error from
+    the host post-processors on the downloaded solution: all as printed by the reference (6
+    significant digits; 2e-5 relative where the solver tolerances flip the last one).  Periodic
+    faces: the host identifies the dofs in the cell -> dof table (oracle BoxMesh(periodic=...))."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                           "reference_golden.json")) as f:
+        g = json.load(f)["taylor_green_vortex_bdf1"]
+
+    def tg(t):
+        def f(x):
+            e = np.exp(-2.0 * t)
+            return np.stack([e * np.cos(x[:, 0]) * np.sin(x[:, 1]), -e * np.sin(x[:, 0]) * np.cos(x[:, 1]),
+                             -0.25 * (np.cos(2 * x[:, 0]) + np.cos(2 * x[:, 1]))], axis=1)
+        return f
+    mesh = oracle.BoxMesh(2, 32, 1, 1, lo=0.0, hi=6.28318530718, bcs={}, periodic=(0, 1))
+    assert (mesh.ncell, mesh.ndof) == (g["cells"], g["dofs"])
+    hp = hotpath_from_oracle_mesh(mesh, 1.0, None)
+    hp.assemble_l2_projection(tg(0.0)(mesh.qpoints.reshape(-1, 2)))
+    hp.solve_linear_system(relative_residual=1e-14, minimum_residual=1e-14, ilu_atol=1e-5,
+                           download=False)
+    hp.distribute_constraints("newton_update")
+    U = hp.get_vector("newton_update")
+    assert "%.6g" % oracle.enstrophy(mesh, U) == g["enstrophy_0"]
+    assert "%.6g" % oracle.kinetic_energy(mesh, U) == g["kinetic_energy_0"]
+    lin = dict(relative_residual=1e-4, minimum_residual=1e-9, max_iterations=5000, ilu_atol=1e-5)
+    centre = oracle.shape_at_centre(2, 1)
+    exact = 0
+    for k in range(30):
+        hp.set_vector("solution_m1", U)
+        hp.set_vector("present_solution", U)
+        vals = {"cfl": hp.calculate_cfl("present_solution", centre, 1, 0.01)}
+        U, _, res = _newton_gpu(hp, mesh, U, "bdf1", [0.01] * 4, tol=1e-6, max_it=5, lin=lin)
+        assert res < 1e-6
+        vals.update(enstrophy=oracle.enstrophy(mesh, U), kinetic_energy=oracle.kinetic_energy(mesh, U),
+                    l2_error_velocity=oracle.l2_error(mesh, U, tg(0.01 * (k + 1)))[0])
+        for name, v in vals.items():
+            ref = float(g[name][k])
+            assert abs(v - ref) <= 2e-5 * abs(ref), (name, k, v, ref)
+            exact += "%.6g" % v == g[name][k]
+    assert exact >= 0.95 * 4 * 30, exact
+    hp.close()
+
+
 def test_gmres_no_convergence_and_state_errors(oracle):
     from softx_2020_200_b200 import GlsnsError, NoConvergence
     mesh = oracle.BoxMesh(2, 8, 1, 1)
