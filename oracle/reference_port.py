@@ -212,22 +212,30 @@ class BoxMesh:
     identified with those of the lo face.  Here: the cells refer to the lo-face dofs directly (the
     same global system as resolving x_hi = x_lo in distribute_local_to_global); the hi-face dofs
     stay in the numbering (deal.II counts them) as constrained rows with a unit diagonal
-    (``periodic_slave`` / ``periodic_master``).  Use an even n (the 2^dim cell colouring).
+    (``periodic_slave`` / ``periodic_master``).
+    n, lo, hi: scalars (hyper_cube) or one value per direction (a structured rectangle / box).
     """
 
     def __init__(self, dim, n, pu, pp, lo=-1.0, hi=1.0, bcs=None, renumber="cm", nq1=None,
                  periodic=()):
         assert pu % pp == 0
         self.dim, self.ncd, self.pu, self.pp = dim, n, pu, pp
-        self.lo, self.hi = float(lo), float(hi)
+        # per-direction cell counts and extents (scalars = the same in every direction:
+        # hyper_cube; sequences: subdivided_hyper_rectangle-like boxes)
+        nd = np.array([n] * dim if np.isscalar(n) else list(n), dtype=np.int64)
+        lov = np.array([lo] * dim if np.isscalar(lo) else list(lo), dtype=np.float64)
+        hiv = np.array([hi] * dim if np.isscalar(hi) else list(hi), dtype=np.float64)
+        self.nd = nd
+        self.lo, self.hi = (float(lo), float(hi)) if np.isscalar(lo) and np.isscalar(hi) else (lov, hiv)
         self.fe = FETables(dim, pu, pp, nq1)
         fe = self.fe
-        self.hx = (self.hi - self.lo) / n
-        gu = pu * n + 1                      # velocity node grid size per direction
+        hxv = (hiv - lov) / nd
+        self.hx = float(hxv[0]) if np.allclose(hxv, hxv[0]) else hxv
+        guv = pu * nd + 1                    # velocity node grid size per direction
         ratio = pu // pp
-        self.gu = gu
-        nnode = gu ** dim
-        idx = np.indices((gu,) * dim).reshape(dim, -1)[::-1]   # idx[d] = index along d, x fastest
+        self.gu = int(guv[0]) if np.all(guv == guv[0]) else guv
+        nnode = int(np.prod(guv))
+        idx = np.indices(tuple(int(g) for g in guv[::-1])).reshape(dim, -1)[::-1]  # idx[d] along d, x fastest
         # numpy's indices with C order makes the LAST axis fastest; reverse so axis 0 = x fastest
         self.node_idx = idx.T.copy()                              # [nnode, dim]
         has_p = np.all(self.node_idx % ratio == 0, axis=1)
@@ -237,10 +245,10 @@ class BoxMesh:
         self.vel_dof = first[:-1, None] + np.arange(dim)[None, :]     # [nnode, dim] provisional ids
         self.p_dof = np.where(has_p, first[:-1] + dim, -1)
         # cells
-        cidx = np.indices((n,) * dim).reshape(dim, -1)[::-1].T        # [ncell, dim], x fastest
+        cidx = np.indices(tuple(int(v) for v in nd[::-1])).reshape(dim, -1)[::-1].T   # [ncell, dim], x fastest
         self.ncell = cidx.shape[0]
         self.cell_idx = cidx
-        stride = gu ** np.arange(dim)
+        stride = np.concatenate([[1], np.cumprod(guv[:-1])])
 
         def local_nodes(p):
             n1 = p + 1
@@ -257,9 +265,8 @@ class BoxMesh:
         # periodic identification (provisional numbering)
         master_node = np.arange(nnode)
         for d in periodic:
-            assert n % 2 == 0
             mi = self.node_idx[master_node].copy()
-            mi[mi[:, d] == gu - 1, d] = 0
+            mi[mi[:, d] == guv[d] - 1, d] = 0
             master_node = (mi * stride).sum(axis=1)
         master_of = np.arange(self.ndof)
         if len(periodic):
@@ -277,7 +284,7 @@ class BoxMesh:
             dof_node[self.vel_dof[:, c]] = np.arange(nnode)
         comp[self.p_dof[has_p]] = dim
         dof_node[self.p_dof[has_p]] = np.arange(nnode)[has_p]
-        coords = self.lo + self.node_idx * (self.hx / pu)
+        coords = lov + self.node_idx * (hxv / pu)
         # constraints
         constrained = np.zeros(self.ndof, dtype=np.uint8)
         cvalue = np.zeros(self.ndof)
@@ -285,10 +292,10 @@ class BoxMesh:
             bcs = {None: ("noslip",)}
         for face, bc in bcs.items():
             if face is None:
-                on = np.any((self.node_idx == 0) | (self.node_idx == gu - 1), axis=1)
+                on = np.any((self.node_idx == 0) | (self.node_idx == guv - 1), axis=1)
             else:
                 d, side = face // 2, face % 2
-                on = self.node_idx[:, d] == (gu - 1 if side else 0)
+                on = self.node_idx[:, d] == (guv[d] - 1 if side else 0)
             nodes = np.nonzero(on)[0]
             vals = np.zeros((nodes.size, dim)) if bc[0] == "noslip" else np.asarray(
                 bc[1](coords[nodes]), dtype=np.float64)
@@ -319,12 +326,23 @@ class BoxMesh:
         self.periodic_master = new_of_old[master_of[inv[self.periodic_slave]]]
         # geometry (affine Cartesian cells)
         self.cell_invJ = np.ascontiguousarray(
-            np.broadcast_to(np.eye(dim) / self.hx, (self.ncell, dim, dim)))
-        self.cell_detJ = np.full(self.ncell, self.hx ** dim)
-        self.cell_measure = np.full(self.ncell, self.hx ** dim)
+            np.broadcast_to(np.eye(dim) / self.hx if np.isscalar(self.hx) else np.diag(1.0 / hxv),
+                            (self.ncell, dim, dim)))
+        # (hx ** dim for cubes: the committed fixtures were made with exactly this expression)
+        vol = self.hx ** dim if np.isscalar(self.hx) else float(np.prod(hxv))
+        self.cell_detJ = np.full(self.ncell, vol)
+        self.cell_measure = np.full(self.ncell, vol)
         self.qpoints = np.ascontiguousarray(
-            self.lo + (cidx[:, None, :] + fe.xq[None, :, :]) * self.hx)     # [ncell, nq, dim]
-        self.cell_color = (cidx % 2 * (2 ** np.arange(dim))).sum(axis=1).astype(np.int32)
+            lov + (cidx[:, None, :] + fe.xq[None, :, :]) * hxv)             # [ncell, nq, dim]
+        # colours: no two cells of a colour share a dof.  Parity per direction; across a periodic
+        # wrap with an odd cell count the last cell of the direction takes a third colour.
+        per_dir = cidx % 2
+        radix = 2
+        for d in periodic:
+            if nd[d] % 2:
+                per_dir[cidx[:, d] == nd[d] - 1, d] = 2
+                radix = 3
+        self.cell_color = (per_dir * (radix ** np.arange(dim))).sum(axis=1).astype(np.int32)
         self.rowptr, self.col = self._sparsity()
 
     def _cuthill_mckee(self, cell_dofs):
@@ -847,7 +865,7 @@ def l2_error(mesh, U, exact):
     exact(x[:, dim]) -> [:, dim+1]. Returns (err_u, err_p)."""
     dim = mesh.dim
     fe = FETables(dim, mesh.pu, mesh.pp, mesh.fe.nq1 + 1)
-    xq = mesh.lo + (mesh.cell_idx[:, None, :] + fe.xq[None, :, :]) * mesh.hx
+    xq = mesh.lo + (mesh.cell_idx[:, None, :] + fe.xq[None, :, :]) * mesh.hx   # (scalars or [dim] arrays)
     ex = exact(xq.reshape(-1, dim)).reshape(mesh.ncell, fe.nq, dim + 1)
     JxW = mesh.cell_detJ[:, None] * fe.wq[None, :]
     n_su = fe.n_su

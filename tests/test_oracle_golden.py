@@ -253,3 +253,27 @@ def test_taylor_green_vortex_bdf1_output(oracle):
         exact["error_table"] += "%.4e" % vals["l2_error_velocity"] == e
     # digit for digit, up to the rare last-digit flip that the solver tolerances allow
     assert all(c >= 95 for c in exact.values()), exact
+
+
+def test_poiseuille_gls_output(oracle):
+    """applications_tests/gls_navier_stokes_2d/poiseuille_gls.output:24-26: plane Poiseuille flow
+    driven by the source term (1, 0) in the x-periodic channel [0,10] x [0,1] (2d_channel.msh is the
+    structured 49 x 9 mesh, refined uniformly twice), Q1-Q1, nu = 1: cells, dofs (deal.II counts the
+    periodic duplicates) and the velocity error against u = y (1 - y) / 2, as printed.  The exact
+    pressure is 0: the printed pressure errors are solver noise (1e-9), ours must be too."""
+    g = REF["poiseuille_gls"]
+
+    def exact(x):
+        return np.stack([0.5 * x[:, 1] * (1 - x[:, 1]), 0 * x[:, 0], 0 * x[:, 0]], axis=1)
+    force = lambda x: np.stack([np.ones(len(x)), 0 * x[:, 0], 0 * x[:, 0]], axis=1)
+    lin = dict(rel=1e-4, abs_=1e-9, max_iters=5000, ilu_atol=1e-5)          # poiseuille_gls.prm:108-116
+    for k in range(3):
+        mesh = oracle.BoxMesh(2, (49 * 2 ** k, 9 * 2 ** k), 1, 1, lo=(0.0, 0.0), hi=(10.0, 1.0),
+                              bcs={2: ("noslip",), 3: ("noslip",)}, periodic=(0,))
+        assert (mesh.ncell, mesh.ndof) == (g["cells"][k], g["dofs"][k])
+        U, _, res = oracle.newton_solve(mesh, mesh.apply_nonzero_constraints(np.zeros(mesh.ndof)),
+                                        oracle.scheme_params("steady", None, 1.0),
+                                        mesh.evaluate_force(force), tol=1e-6, max_it=3, lin=lin)
+        eu, ep = oracle.l2_error(mesh, U, exact)
+        assert "%.4e" % eu == g["error_velocity"][k]
+        assert ep < 1e-6
