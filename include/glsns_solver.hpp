@@ -631,6 +631,102 @@ namespace glsns
   }
 
   // ------------------------------------------------------------------------------------------
+  // Time-stepping glue of NavierStokesBase around solve_non_linear_system (the caller of the hot
+  // path in a transient run, source/solvers/navier_stokes_base.cc:428-590), for any solver that
+  // has present_solution, solution_m1..m3, time_steps_vector and solve_non_linear_system.
+  // ------------------------------------------------------------------------------------------
+  inline bool
+  is_bdf(const TimeSteppingMethod method)
+  {
+    return method == TimeSteppingMethod::bdf1 || method == TimeSteppingMethod::bdf2 ||
+           method == TimeSteppingMethod::bdf3;
+  }
+
+  // SimulationControl::add_time_step (source/core/simulation_control.cc:29-38): the vector that
+  // get_time_steps_vector() hands to the assembly, newest first
+  inline void
+  add_time_step(std::vector<double> &time_steps_vector, const double dt)
+  {
+    for (size_t i = time_steps_vector.size() - 1; i > 0; --i)
+      time_steps_vector[i] = time_steps_vector[i - 1];
+    time_steps_vector[0] = dt;
+  }
+
+  // NavierStokesBase::iterate (navier_stokes_base.cc:461-505): the SDIRK stages of one time step
+  // (stage results become solution_m2 / solution_m3), or one solve for steady / BDF
+  template <class Solver>
+  void
+  iterate(Solver &s, const TimeSteppingMethod method)
+  {
+    if (method == TimeSteppingMethod::sdirk2)
+      {
+        s.solve_non_linear_system(TimeSteppingMethod::sdirk2_1, false, false);
+        s.solution_m2 = s.present_solution;
+        s.solve_non_linear_system(TimeSteppingMethod::sdirk2_2, false, false);
+      }
+    else if (method == TimeSteppingMethod::sdirk3)
+      {
+        s.solve_non_linear_system(TimeSteppingMethod::sdirk3_1, false, false);
+        s.solution_m2 = s.present_solution;
+        s.solve_non_linear_system(TimeSteppingMethod::sdirk3_2, false, false);
+        s.solution_m3 = s.present_solution;
+        s.solve_non_linear_system(TimeSteppingMethod::sdirk3_3, false, false);
+      }
+    else
+      s.solve_non_linear_system(method, false, false);
+  }
+
+  // NavierStokesBase::first_iteration (navier_stokes_base.cc:511-590): BDF2 / BDF3 start with
+  // Euler steps of dt * startup_timestep_scaling (`startup time scaling`, default 0.4) and finish
+  // the step with the rest; `dt` has already been added to time_steps_vector by integrate().
+  template <class Solver>
+  void
+  first_iteration(Solver &s, const TimeSteppingMethod method, const double dt,
+                  const double startup_timestep_scaling)
+  {
+    if (!is_bdf(method) || method == TimeSteppingMethod::bdf1)
+      iterate(s, method);
+    else if (method == TimeSteppingMethod::bdf2)
+      {
+        add_time_step(s.time_steps_vector, dt * startup_timestep_scaling);
+        s.solve_non_linear_system(TimeSteppingMethod::bdf1, false, true);
+        s.solution_m2 = s.solution_m1;
+        s.solution_m1 = s.present_solution;
+        add_time_step(s.time_steps_vector, dt * (1. - startup_timestep_scaling));
+        s.solve_non_linear_system(TimeSteppingMethod::bdf2, false, true);
+      }
+    else // bdf3
+      {
+        const double time_step = dt * startup_timestep_scaling;
+        add_time_step(s.time_steps_vector, time_step);
+        s.solve_non_linear_system(TimeSteppingMethod::bdf1, false, true);
+        s.solution_m2 = s.solution_m1;
+        s.solution_m1 = s.present_solution;
+        add_time_step(s.time_steps_vector, time_step);
+        s.solve_non_linear_system(TimeSteppingMethod::bdf1, false, true);
+        s.solution_m3 = s.solution_m2;
+        s.solution_m2 = s.solution_m1;
+        s.solution_m1 = s.present_solution;
+        add_time_step(s.time_steps_vector, dt * (1. - 2. * startup_timestep_scaling));
+        s.solve_non_linear_system(TimeSteppingMethod::bdf3, false, true);
+      }
+  }
+
+  // NavierStokesBase::finish_time_step (navier_stokes_base.cc:428-442), the vectors (the CFL number
+  // of the new solution is GLSNavierStokesSolver::calculate_CFL; checkpoints stay with the host)
+  template <class Solver>
+  void
+  finish_time_step(Solver &s, const TimeSteppingMethod method)
+  {
+    if (method != TimeSteppingMethod::steady)
+      {
+        s.solution_m3 = s.solution_m2;
+        s.solution_m2 = s.solution_m1;
+        s.solution_m1 = s.present_solution;
+      }
+  }
+
+  // ------------------------------------------------------------------------------------------
   // GLSNavierStokesSolver: the three overrides forwarded to the device through the C ABI
   // ------------------------------------------------------------------------------------------
   struct NavierStokesSolverParameters

@@ -51,6 +51,28 @@ namespace
     int    n_matrix = 0;
   };
 
+  // records what the time-stepping glue asks of a solver: (method, first, renew, time_steps[0..2],
+  // tags of m1, m2, m3 at the time of the call); "solving" gives present_solution a fresh tag
+  struct RecordingSolver
+  {
+    glsns::Vector       present_solution, solution_m1, solution_m2, solution_m3;
+    std::vector<double> time_steps_vector = {0, 0, 0, 0};
+    std::vector<double> log;
+    int                 next_tag = 1;
+    RecordingSolver()
+    {
+      present_solution.reinit(1), solution_m1.reinit(1), solution_m2.reinit(1), solution_m3.reinit(1);
+    }
+    void
+    solve_non_linear_system(const glsns::TimeSteppingMethod m, const bool first, const bool renew)
+    {
+      log.insert(log.end(), {(double)(int)m, (double)first, (double)renew, time_steps_vector[0],
+                             time_steps_vector[1], time_steps_vector[2], solution_m1[0],
+                             solution_m2[0], solution_m3[0]});
+      present_solution[0] = next_tag++;
+    }
+  };
+
   struct SolverHandle
   {
     glsns::GLSNavierStokesSolver *solver = nullptr;
@@ -76,6 +98,31 @@ glsnsh_newton_toy(int use_skip_newton, int skip_iterations, double *x_out)
   solver.solve_non_linear_system(glsns::TimeSteppingMethod::steady, true, true);
   x_out[0] = solver.present_solution[0], x_out[1] = solver.present_solution[1];
   return solver.n_matrix;
+}
+
+// The time-stepping glue on the recording solver: n_steps time steps of size dt with `method`
+// (TimeSteppingMethod value), the first one through first_iteration.  out receives 9 doubles per
+// solve_non_linear_system call (see RecordingSolver); returns the number of calls.
+int
+glsnsh_time_stepping_trace(int method, int n_steps, double dt, double startup_scaling, double *out,
+                           int out_len)
+{
+  RecordingSolver                s;
+  const glsns::TimeSteppingMethod m = static_cast<glsns::TimeSteppingMethod>(method);
+  glsns::finish_time_step(s, m); // after set_initial_condition (tag 0 = the initial condition)
+  for (int k = 0; k < n_steps; ++k)
+    {
+      glsns::add_time_step(s.time_steps_vector, dt); // SimulationControlTransient::integrate
+      if (k == 0)
+        glsns::first_iteration(s, m, dt, startup_scaling);
+      else
+        glsns::iterate(s, m);
+      glsns::finish_time_step(s, m);
+    }
+  const int n = (int)s.log.size();
+  for (int i = 0; i < n && i < out_len; ++i)
+    out[i] = s.log[i];
+  return n / 9;
 }
 
 // Parse a .prm text; out[0..17] (18 doubles) = non-linear {tolerance, max iterations, skip iterations, solver},

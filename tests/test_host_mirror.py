@@ -198,3 +198,48 @@ def test_level_of_fill_pattern_equals_the_oracle(oracle, dim, n, pu, pp, fill):
     pm, _ = oracle.iluk_pattern(mesh, fill)
     assert np.array_equal(orp, pm.rowptr) and np.array_equal(ocol, pm.col)
     assert L.glsnsh_iluk_pattern(mesh.ndof, p(rp, _lib.c_i64_p), p(col, _lib.c_i32_p), -1, None, None) == -1
+
+
+def _time_stepping(method, n_steps, dt=0.1, scaling=0.4):
+    from softx_2020_200_b200 import _lib
+    L = _lib.lib()
+    L.glsnsh_time_stepping_trace.restype = C.c_int
+    L.glsnsh_time_stepping_trace.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double,
+                                             C.POINTER(C.c_double), C.c_int]
+    out = (C.c_double * 900)()
+    n = L.glsnsh_time_stepping_trace(_lib.SCHEMES[method], n_steps, dt, scaling, out, 900)
+    names = {v: k for k, v in _lib.SCHEMES.items()}
+    return [(names[int(out[9 * i])], bool(out[9 * i + 1]), bool(out[9 * i + 2]),
+             tuple(round(out[9 * i + j], 12) for j in (3, 4, 5)),
+             tuple(int(out[9 * i + j]) for j in (6, 7, 8))) for i in range(n)]
+
+
+def test_time_stepping_glue_of_navier_stokes_base():
+    """NavierStokesBase::first_iteration / iterate / finish_time_step
+    (source/solvers/navier_stokes_base.cc:428-590) of the mirror on a recording solver: which
+    method each solve runs with, the time-step vector it sees (newest first) and which earlier
+    solutions sit in solution_m1 / m2 / m3 (tag 0 = the initial condition, tag k = result of the
+    k-th solve)."""
+    # sdirk3: three stage solves per step, stage results in m2 / m3, m1 = previous step
+    calls = _time_stepping("sdirk3", 2)
+    assert [c[0] for c in calls] == ["sdirk3_1", "sdirk3_2", "sdirk3_3"] * 2
+    assert [c[4] for c in calls[:3]] == [(0, 0, 0), (0, 1, 0), (0, 1, 2)]
+    assert [c[4][0] for c in calls[3:]] == [3, 3, 3] and calls[5][4] == (3, 4, 5)
+    assert all(c[1:3] == (False, False) and c[3][0] == 0.1 for c in calls)
+    # sdirk2
+    calls = _time_stepping("sdirk2", 1)
+    assert [c[0] for c in calls] == ["sdirk2_1", "sdirk2_2"] and calls[1][4][:2] == (0, 1)
+    # bdf1 / steady: one solve per step
+    assert [c[0] for c in _time_stepping("bdf1", 3)] == ["bdf1"] * 3
+    assert [c[4][0] for c in _time_stepping("bdf1", 3)] == [0, 1, 2]
+    # bdf2 starts with an Euler step of 0.4 dt and completes the step with a bdf2 solve of 0.6 dt
+    calls = _time_stepping("bdf2", 2)
+    assert [c[0] for c in calls] == ["bdf1", "bdf2", "bdf2"]
+    assert calls[0][3][0] == 0.04 and calls[1][3][:2] == (0.06, 0.04) and calls[2][3][:2] == (0.1, 0.06)
+    assert calls[0][2] and calls[1][2] and not calls[2][2]          # start-up solves renew the matrix
+    assert calls[1][4][:2] == (1, 0) and calls[2][4][:2] == (2, 1)
+    # bdf3: two Euler steps of 0.4 dt, then a bdf3 solve of 0.2 dt
+    calls = _time_stepping("bdf3", 2)
+    assert [c[0] for c in calls] == ["bdf1", "bdf1", "bdf3", "bdf3"]
+    assert [c[3][0] for c in calls] == [0.04, 0.04, 0.02, 0.1]
+    assert calls[2][4] == (2, 1, 0) and calls[3][4] == (3, 2, 1)
