@@ -1,5 +1,5 @@
 """ILU-apply kernel check + timing on the 3D Q2-Q2 cavity (run under gpurun).
-    [GLSNS_TRSV_WARPS=w GLSNS_TRSV_NSLOT=s] python tools/trsv_sweep.py N [check]
+    [GLSNS_TRSV_TEAMS=t GLSNS_TRSV_HELPERS=k GLSNS_TRSV_TUNE=r] python tools/trsv_sweep.py N [check]
 `check` compares the device triangular solves with the CPU oracle's on the device's own factors."""
 import json, os, sys, types
 sys.path.insert(0, ".")
@@ -12,7 +12,7 @@ check = len(sys.argv) > 2 and sys.argv[2] == "check"
 CAVITY = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (4, "noslip"), (5, "noslip"), (3, "function", (1, 0, 0))]
 m = BoxMesh(3, n, 2, 2, bcs=CAVITY); hp = GLSHotPath(0); m.attach(hp); hp.set_physics(0.005)
 U0 = m.initial_state(); hp.set_vector("evaluation_point", U0); hp.assemble(True); hp.setup_ilu(0, 1e-12, 1.0)
-out = dict(n=n, warps=os.environ.get("GLSNS_TRSV_WARPS"), nslot=os.environ.get("GLSNS_TRSV_NSLOT"),
+out = dict(n=n, teams=os.environ.get("GLSNS_TRSV_TEAMS"), helpers=os.environ.get("GLSNS_TRSV_HELPERS"),
            levels=hp.ilu_levels())
 if check:
     from oracle import reference_port as R
