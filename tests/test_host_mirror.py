@@ -160,6 +160,30 @@ def test_box_mesh_equals_the_oracle_mesh(oracle, dim, n, pu, pp):
         assert len(np.unique(d)) == d.size
 
 
+@pytest.mark.parametrize("dim,n,lo,hi,pu,pp", [(2, (5, 3), (0.0, 0.0), (10.0, 1.0), 1, 1),
+                                                (2, (3, 4), (-1.0, 0.5), (2.0, 1.5), 2, 1),
+                                                (3, (2, 3, 4), (0.0, 0.0, 0.0), (1.0, 2.0, 0.5), 2, 2)])
+def test_anisotropic_box_mesh_equals_the_oracle_mesh(oracle, dim, n, lo, hi, pu, pp):
+    """Boxes with different cell counts and extents per direction (subdivided_hyper_rectangle-like;
+    the channel of poiseuille_gls.prm is one): the C++ stand-in against the numpy restatement."""
+    from softx_2020_200_b200.mesh import BoxMesh
+    A = BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, renumber=False, with_q_points=True)
+    O = oracle.BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, renumber="none")
+    assert A.n_dofs == O.ndof and A.n_cells == O.ncell
+    for name, ref in [("cell_dofs", O.cell_dofs.ravel()), ("row_ptr", O.rowptr), ("col_idx", O.col),
+                      ("constrained", O.constrained), ("dof_component", O.dof_comp)]:
+        assert np.array_equal(A.array(name), ref), name
+    for name, ref in [("inv_jacobian", O.cell_invJ), ("det_jacobian", O.cell_detJ),
+                      ("cell_measure", O.cell_measure), ("q_points", O.qpoints),
+                      ("dof_coords", O.dof_coords)]:
+        assert np.allclose(A.array(name), ref.ravel(), rtol=0, atol=2e-14), name
+    B = BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, renumber=True)
+    O2 = oracle.BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, renumber=_match_numbering(A, B, dim))
+    for name, ref in [("cell_dofs", O2.cell_dofs.ravel()), ("row_ptr", O2.rowptr),
+                      ("col_idx", O2.col), ("constrained", O2.constrained)]:
+        assert np.array_equal(B.array(name), ref), name
+
+
 def test_cavity_boundary_conditions_first_listed_wins():
     from softx_2020_200_b200.mesh import BoxMesh
     bcs = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (4, "noslip"), (5, "noslip"),
