@@ -34,6 +34,7 @@ namespace
     // dofs
     int64_t              n_dofs = 0, n_owned = 0, n_cells = 0, n_global = 0, owned_begin = 0;
     std::vector<int32_t> cell_dofs, col, color_ptr, color_cells, dof_comp;
+    std::vector<int32_t> periodic_slave, periodic_master; // dofs identified by make_periodic
     std::vector<int64_t> rowptr, cell_ids, local_to_global;
     std::vector<uint8_t> constrained;
     std::vector<double>  cvalues, inv_jac, det_jac, measure, q_points, dof_coords;
@@ -489,6 +490,136 @@ glsnsh_mesh_create(int dim, const int *n_cells_dir, int pu, int pp, const double
   return (glsnsh_mesh *)M;
 }
 
+// `type = periodic` boundary pairs (boundary_conditions.h; DoFTools::make_periodicity_constraints
+// in setup_dofs): bit d of dir_mask identifies the dofs of face 2d+1 with those of face 2d.  The
+// cells then refer to the lo-face dofs directly -- the same global system as resolving x_hi = x_lo
+// in distribute_local_to_global -- while the hi-face dofs stay in the numbering (deal.II counts
+// them too) as constrained rows no cell touches (the device assembly gives those a unit diagonal).
+// Cell colours and the sparsity pattern are rebuilt.  Serial meshes only; returns 0 or 1 (+ error).
+int
+glsnsh_mesh_make_periodic(glsnsh_mesh *m, int dir_mask)
+{
+  HostMesh *M = (HostMesh *)m;
+  if (!M->error.empty())
+    return 1;
+  if (M->n_owned != M->n_dofs || !M->periodic_slave.empty())
+    {
+      M->error = "make_periodic: serial, not yet periodic meshes only";
+      return 1;
+    }
+  const int dim = M->dim, pu = M->pu;
+  int       gu[3] = {1, 1, 1};
+  double    hn[3] = {1, 1, 1};
+  for (int d = 0; d < dim; ++d)
+    gu[d] = pu * M->ncd[d] + 1, hn[d] = (M->hi[d] - M->lo[d]) / M->ncd[d] / pu;
+  const int64_t nnode = (int64_t)gu[0] * gu[1] * gu[2];
+  // dof of (node, component)
+  std::vector<int32_t> dof_at((size_t)nnode * (dim + 1), -1);
+  std::vector<int64_t> node_of(M->n_dofs);
+  for (int64_t g = 0; g < M->n_dofs; ++g)
+    {
+      int64_t v = 0, stride = 1;
+      for (int d = 0; d < dim; ++d)
+        {
+          const int i = (int)llround((M->dof_coords[(size_t)g * dim + d] - M->lo[d]) / hn[d]);
+          v += stride * i, stride *= gu[d];
+        }
+      node_of[g]                                     = v;
+      dof_at[(size_t)v * (dim + 1) + M->dof_comp[g]] = (int32_t)g;
+    }
+  std::vector<int32_t> master_of(M->n_dofs);
+  for (int64_t g = 0; g < M->n_dofs; ++g)
+    {
+      int64_t v = node_of[g], stride = 1, mv = v;
+      for (int d = 0; d < dim; ++d)
+        {
+          const int i = (int)((v / stride) % gu[d]);
+          if (((dir_mask >> d) & 1) && i == gu[d] - 1)
+            mv -= stride * i;
+          stride *= gu[d];
+        }
+      master_of[g] = dof_at[(size_t)mv * (dim + 1) + M->dof_comp[g]];
+      if (master_of[g] != (int32_t)g)
+        {
+          M->periodic_slave.push_back((int32_t)g), M->periodic_master.push_back(master_of[g]);
+          M->constrained[g] = 1, M->cvalues[g] = 0.0;
+        }
+    }
+  for (int32_t &g : M->cell_dofs)
+    g = master_of[g];
+  // colours: parity per direction; across a periodic wrap with an odd cell count the last cell
+  // of the direction takes a third colour
+  int radix = 2;
+  for (int d = 0; d < dim; ++d)
+    if (((dir_mask >> d) & 1) && (M->ncd[d] & 1))
+      radix = 3;
+  int ncolor = 1;
+  for (int d = 0; d < dim; ++d)
+    ncolor *= radix;
+  std::vector<int32_t> color(M->n_cells);
+  for (int64_t c = 0; c < M->n_cells; ++c)
+    {
+      const int ci[3] = {(int)(c % M->ncd[0]), (int)((c / M->ncd[0]) % M->ncd[1]),
+                         dim == 3 ? (int)(c / ((int64_t)M->ncd[0] * M->ncd[1])) : 0};
+      int       col = 0, mul = 1;
+      for (int d = 0; d < dim; ++d)
+        {
+          int k = ci[d] & 1;
+          if (((dir_mask >> d) & 1) && (M->ncd[d] & 1) && ci[d] == M->ncd[d] - 1)
+            k = 2;
+          col += mul * k, mul *= radix;
+        }
+      color[c] = col;
+    }
+  M->color_ptr.assign(ncolor + 1, 0);
+  for (int64_t c = 0; c < M->n_cells; ++c)
+    M->color_ptr[color[c] + 1]++;
+  for (int k = 0; k < ncolor; ++k)
+    M->color_ptr[k + 1] += M->color_ptr[k];
+  {
+    std::vector<int32_t> pos(M->color_ptr.begin(), M->color_ptr.end() - 1);
+    for (int64_t c = 0; c < M->n_cells; ++c)
+      M->color_cells[pos[color[c]]++] = (int32_t)c;
+  }
+  // sparsity from the cell -> dof table: couplings between unconstrained dofs of a cell + diagonal
+  std::vector<int64_t> cptr(M->n_dofs + 1, 0);
+  for (int32_t g : M->cell_dofs)
+    cptr[g + 1]++;
+  for (int64_t g = 0; g < M->n_dofs; ++g)
+    cptr[g + 1] += cptr[g];
+  std::vector<int32_t> cells_of((size_t)cptr[M->n_dofs]);
+  {
+    std::vector<int64_t> pos(cptr.begin(), cptr.end() - 1);
+    for (int64_t c = 0; c < M->n_cells; ++c)
+      for (int k = 0; k < M->n_loc; ++k)
+        cells_of[(size_t)pos[M->cell_dofs[(size_t)c * M->n_loc + k]]++] = (int32_t)c;
+  }
+  std::vector<std::vector<int32_t>> rows((size_t)M->n_dofs);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t r = 0; r < M->n_dofs; ++r)
+    {
+      std::vector<int32_t> &out = rows[(size_t)r];
+      out.push_back((int32_t)r);
+      if (!M->constrained[r])
+        for (int64_t t = cptr[r]; t < cptr[r + 1]; ++t)
+          {
+            const int32_t *cd = M->cell_dofs.data() + (size_t)cells_of[(size_t)t] * M->n_loc;
+            for (int k = 0; k < M->n_loc; ++k)
+              if (!M->constrained[cd[k]])
+                out.push_back(cd[k]);
+          }
+      std::sort(out.begin(), out.end());
+      out.erase(std::unique(out.begin(), out.end()), out.end());
+    }
+  M->rowptr.assign(M->n_dofs + 1, 0);
+  for (int64_t r = 0; r < M->n_dofs; ++r)
+    M->rowptr[r + 1] = M->rowptr[r] + (int64_t)rows[(size_t)r].size();
+  M->col.resize((size_t)M->rowptr[M->n_dofs]);
+  for (int64_t r = 0; r < M->n_dofs; ++r)
+    std::copy(rows[(size_t)r].begin(), rows[(size_t)r].end(), M->col.begin() + M->rowptr[r]);
+  return 0;
+}
+
 // The rank-local view of a (serial) mesh: contiguous blocks of the global dof order
 // balanced by nonzeros, local numbering owned-first then ghosts by global id (which
 // groups them by owner), every cell that touches an owned row.
@@ -717,6 +848,8 @@ glsnsh_mesh_array(const glsnsh_mesh *m, const char *name, int64_t *count)
   ARR("dof_coords", dof_coords)
   ARR("local_to_global", local_to_global)
   ARR("cell_ids", cell_ids)
+  ARR("periodic_slave", periodic_slave)
+  ARR("periodic_master", periodic_master)
   ARR("neighbor_rank", neighbor_rank)
   ARR("send_ptr", send_ptr)
   ARR("send_idx", send_idx)

@@ -309,6 +309,38 @@ glsnsh_solver_calculate_cfl(void *handle, const double *shape_u_at_centre, doubl
     }
 }
 
+// NavierStokesBase's time-stepping glue on the device-backed solver (navier_stokes_base.cc:428-590):
+// what = 0 integrate (add_time_step(dt)), 1 first_iteration, 2 iterate, 3 finish_time_step.
+// Returns 0 ok, 3 NoConvergence, 1 any other exception.
+int
+glsnsh_solver_time_step(void *handle, int what, int method, double dt, double startup_scaling)
+{
+  SolverHandle *h = (SolverHandle *)handle;
+  try
+    {
+      const glsns::TimeSteppingMethod m = static_cast<glsns::TimeSteppingMethod>(method);
+      if (what == 0)
+        glsns::add_time_step(h->solver->time_steps_vector, dt);
+      else if (what == 1)
+        glsns::first_iteration(*h->solver, m, dt, startup_scaling);
+      else if (what == 2)
+        glsns::iterate(*h->solver, m);
+      else
+        glsns::finish_time_step(*h->solver, m);
+      return 0;
+    }
+  catch (const glsns::NoConvergence &e)
+    {
+      h->error = e.what();
+      return 3;
+    }
+  catch (const std::exception &e)
+    {
+      h->error = e.what();
+      return 1;
+    }
+}
+
 // everything the solver wrote to pcout so far
 const char *
 glsnsh_solver_log(void *handle)

@@ -13,7 +13,8 @@ _DTYPES = {"cell_dofs": np.int32, "col_idx": np.int32, "row_ptr": np.int64, "con
            "constraint_values": np.float64, "inv_jacobian": np.float64, "det_jacobian": np.float64,
            "cell_measure": np.float64, "q_points": np.float64, "color_ptr": np.int32,
            "color_cells": np.int32, "dof_component": np.int32, "dof_coords": np.float64,
-           "local_to_global": np.int64, "cell_ids": np.int64, "neighbor_rank": np.int32,
+           "local_to_global": np.int64, "cell_ids": np.int64, "periodic_slave": np.int32,
+           "periodic_master": np.int32, "neighbor_rank": np.int32,
            "send_ptr": np.int64, "send_idx": np.int32, "recv_ptr": np.int64, "shape_u": np.float64,
            "grad_u": np.float64, "hess_u": np.float64, "shape_p": np.float64, "grad_p": np.float64,
            "weights": np.float64, "unit_q_points": np.float64}
@@ -28,6 +29,8 @@ def _bind(L):
     L.glsnsh_mesh_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
                                      _lib.c_double_p, _lib.c_double_p, C.c_int, C.POINTER(C.c_int),
                                      _lib.c_double_p, C.POINTER(C.c_int), C.c_int, C.c_int]
+    L.glsnsh_mesh_make_periodic.restype = C.c_int
+    L.glsnsh_mesh_make_periodic.argtypes = [C.c_void_p, C.c_int]
     L.glsnsh_mesh_partition.restype = C.c_void_p
     L.glsnsh_mesh_partition.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.glsnsh_mesh_destroy.restype = None
@@ -49,11 +52,13 @@ class BoxMesh:
     bcs: list of (face_id, "noslip") or (face_id, "function", (ux, uy[, uz])) in the order the
     reference creates the constraints (first listed wins on shared edges); face ids as deal.II's
     colorize=true (0 x=lo, 1 x=hi, 2 y=lo, 3 y=hi, 4 z=lo, 5 z=hi). bcs=None: no-slip everywhere
-    (boundary id 0 of an uncolorized hyper_cube).
+    (boundary id 0 of an uncolorized hyper_cube); bcs=[] : no Dirichlet boundary at all.
+    periodic: directions d whose faces 2d / 2d+1 are a `type = periodic` pair (the dofs of the hi
+    face are identified with those of the lo face, see glsnsh_mesh_make_periodic).
     """
 
     def __init__(self, dim, n, pu, pp, lo=-1.0, hi=1.0, bcs=None, renumber=True, nq1=0,
-                 with_q_points=False, _handle=None):
+                 with_q_points=False, periodic=(), _handle=None):
         self._L = _lib.lib()
         _bind(self._L)
         if _handle is not None:
@@ -83,6 +88,8 @@ class BoxMesh:
             self._h = self._L.glsnsh_mesh_create(dim, nd, pu, pp, lo3, hi3, nq1, types, vals,
                                                  (C.c_int * 6)(*order), 1 if renumber else 0,
                                                  1 if with_q_points else 0)
+            if len(periodic):
+                self._L.glsnsh_mesh_make_periodic(self._h, sum(1 << d for d in periodic))
         err = self._L.glsnsh_mesh_error(self._h).decode()
         if err:
             raise ValueError(err)

@@ -34,6 +34,8 @@ def _bind(L):
     L.glsnsh_solver_set_initial_condition.restype = C.c_int
     L.glsnsh_solver_set_initial_condition.argtypes = [C.c_void_p, C.c_int, _lib.c_double_p,
                                                       _lib.c_double_p]
+    L.glsnsh_solver_time_step.restype = C.c_int
+    L.glsnsh_solver_time_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
     L.glsnsh_solver_calculate_cfl.restype = C.c_int
     L.glsnsh_solver_calculate_cfl.argtypes = [C.c_void_p, _lib.c_double_p, C.c_double, _lib.c_double_p]
     L.glsnsh_solver_log.restype = C.c_char_p
@@ -109,6 +111,26 @@ class GLSNavierStokesSolver:
             raise NoConvergence(self._L.glsnsh_solver_error(self._h).decode(), {})
         if rc:
             raise RuntimeError(self._L.glsnsh_solver_error(self._h).decode())
+
+    def _time_step(self, what, method, dt=0.0, startup_scaling=0.4):
+        rc = self._L.glsnsh_solver_time_step(self._h, what, METHODS[method], dt, startup_scaling)
+        if rc == 3:
+            raise NoConvergence(self._L.glsnsh_solver_error(self._h).decode(), {})
+        if rc:
+            raise RuntimeError(self._L.glsnsh_solver_error(self._h).decode())
+
+    def advance(self, method, dt, first=False, startup_scaling=0.4):
+        """One transient iteration as NavierStokesBase::solve runs it (navier_stokes_base.cc:428-590):
+        integrate() adds dt to the time-step vector, first_iteration() / iterate() solve the stage(s)
+        (method: "bdf1" | "bdf2" | "bdf3" | "sdirk2" | "sdirk3" | "steady"), finish_time_step() shifts
+        solution_m1..m3."""
+        self._time_step(0, method, dt)
+        self._time_step(1 if first else 2, method, dt, startup_scaling)
+        self._time_step(3, method)
+
+    def finish_time_step(self, method):
+        """After set_initial_condition: solution_m1 = present_solution (navier_stokes_base.cc:428-435)."""
+        self._time_step(3, method)
 
     def calculate_cfl(self, shape_u_at_centre, time_step):
         """calculate_CFL (postprocessing_cfl.cc:34-87) of present_solution."""

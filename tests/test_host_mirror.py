@@ -184,6 +184,41 @@ def test_anisotropic_box_mesh_equals_the_oracle_mesh(oracle, dim, n, lo, hi, pu,
         assert np.array_equal(B.array(name), ref), name
 
 
+@pytest.mark.parametrize("dim,n,lo,hi,pu,pp,periodic,walls", [
+    (2, 4, 0.0, 6.28318530718, 1, 1, (0, 1), ()),           # taylor-green-vortex_gls_bdf1.prm
+    (2, 4, 0.0, 6.28318530718, 2, 1, (0, 1), ()),           # taylor-green-vortex_gls_sdirk*.prm
+    (2, (5, 3), (0.0, 0.0), (10.0, 1.0), 1, 1, (0,), (2, 3)),  # poiseuille_gls.prm (odd count)
+    (3, (2, 3, 2), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), 2, 2, (2,), (0, 1, 2, 3))])
+def test_periodic_box_mesh_equals_the_oracle_mesh(oracle, dim, n, lo, hi, pu, pp, periodic, walls):
+    """`type = periodic` boundary pairs in the C++ stand-in (glsnsh_mesh_make_periodic) against the
+    numpy restatement: identified cell -> dof table, slave dofs as constrained rows, sparsity; the
+    colouring stays conflict free across the wrap (odd cell counts take a third colour)."""
+    from softx_2020_200_b200.mesh import BoxMesh
+    bcs = [(f, "noslip") for f in walls]
+    obcs = {f: ("noslip",) for f in walls}
+    A = BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, bcs=bcs, renumber=False, periodic=periodic)
+    O = oracle.BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, bcs=obcs, renumber="none", periodic=periodic)
+    assert A.n_dofs == O.ndof and A.n_cells == O.ncell
+    for name, ref in [("cell_dofs", O.cell_dofs.ravel()), ("row_ptr", O.rowptr), ("col_idx", O.col),
+                      ("constrained", O.constrained), ("periodic_slave", O.periodic_slave),
+                      ("periodic_master", O.periodic_master)]:
+        assert np.array_equal(A.array(name), ref), name
+    assert np.all(A.array("constraint_values")[A.array("periodic_slave")] == 0)
+    B = BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, bcs=bcs, renumber=True, periodic=periodic)
+    nat = BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, bcs=bcs, renumber=False)
+    full = BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, bcs=bcs, renumber=True)
+    O2 = oracle.BoxMesh(dim, n, pu, pp, lo=lo, hi=hi, bcs=obcs, renumber=_match_numbering(nat, full, dim),
+                        periodic=periodic)
+    for name, ref in [("cell_dofs", O2.cell_dofs.ravel()), ("row_ptr", O2.rowptr), ("col_idx", O2.col),
+                      ("constrained", O2.constrained)]:
+        assert np.array_equal(B.array(name), ref), name
+    ptr, cells, cd = B.array("color_ptr"), B.array("color_cells"), B.array("cell_dofs").reshape(B.n_cells, -1)
+    assert ptr[-1] == B.n_cells
+    for c in range(len(ptr) - 1):
+        d = cd[cells[ptr[c]:ptr[c + 1]]].ravel()
+        assert len(np.unique(d)) == d.size
+
+
 def test_cavity_boundary_conditions_first_listed_wins():
     from softx_2020_200_b200.mesh import BoxMesh
     bcs = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (4, "noslip"), (5, "noslip"),
