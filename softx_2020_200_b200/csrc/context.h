@@ -43,6 +43,8 @@ namespace glsns
     int32_t nlow;  // offset of the in-group block inside the row
     int32_t fmask; // group descriptor: bit d = couples to the chain row at distance d;
                    // helper item: where the totals go (block position << 4 | row offset)
+    int32_t fmask2; // group descriptor: the same for the distances 32 ...
+    int32_t pad_;
   };
 
   // One sweep (lower or upper) of the ILU application in stream form (trsv.cu).

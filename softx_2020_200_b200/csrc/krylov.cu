@@ -239,11 +239,10 @@ namespace glsns
     const int64_t n = std::max<int64_t>(ctx->n_owned, 1);
     if (restart < 1 || restart > 60)
       return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "GMRES restart must be in 1..60");
-    if (ctx->krylov_m != restart || !ctx->V.p)
-      {
-        GLSNS_TRY(dev_alloc(ctx, ctx->V, (size_t)n * (restart + 1)));
-        ctx->krylov_m = restart;
-      }
+    // (dev_alloc is a no-op when the size is unchanged; the basis must follow n_owned when a
+    // second glsns_set_mesh -- after refinement -- changes it, not only the restart length)
+    GLSNS_TRY(dev_alloc(ctx, ctx->V, (size_t)n * (restart + 1)));
+    ctx->krylov_m = restart;
     GLSNS_TRY(dev_alloc(ctx, ctx->w, (size_t)n));
     GLSNS_TRY(dev_alloc(ctx, ctx->tvec, (size_t)n));
     GLSNS_TRY(dev_alloc(ctx, ctx->ytmp, (size_t)n));

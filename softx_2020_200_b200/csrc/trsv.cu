@@ -16,14 +16,19 @@
 //   * BLOCKS.  Up to 4 consecutive linked groups (<= 16 rows) are the unit of the
 //     recurrence.  Everything a block needs from outside was numbered before its
 //     first row, so solving its rows in one step cannot dead-lock; its own triangle T
-//     and its couplings F to the 16 chain rows before it are packed SOLVED after every
-//     factorisation (M = T^-1, G = T^-1 F), so a block is one 16 x 32 product
-//     out = -(M totals + G w) and the chain advances 16 rows per step.
+//     and its couplings F to the 48 chain rows before it are packed SOLVED after every
+//     factorisation (M = T^-1, G = T^-1 F), so a block is one 16 x 64 product
+//     out = -(M totals + G w) and the chain advances 16 rows per step.  (48 rows, not
+//     16: a block couples to the last two or three blocks of its chain, and what is not
+//     in the window goes through L2 and a helper -- with a 16-row window the helpers'
+//     totals arrived 0.8 us after the chain predecessor in the median block, which tripled
+//     the chain step: 8.66 -> 7.89 ms per application at 64^3 cells.)
 //   * CHAINS.  The host schedules the blocks on the resident TEAMS level by level
 //     (trsv_analyse): a block whose predecessor in the numbering is one of its
 //     dependencies goes to the team that solves that predecessor, right behind it,
-//     and reads the last 16 rows of the chain from a window in shared memory instead
-//     of through L2; only the dependencies on other chains travel through L2.  Every
+//     and reads the last 48 rows of the chain from a window in shared memory (the chain's
+//     last 64 rows, by row number modulo 64) instead of through L2; only the dependencies
+//     on other chains travel through L2.  Every
 //     team's list is sorted by a key that grows along every dependency (the block
 //     level, or, after the profile-guided pass, the time its inputs were published in
 //     a traced run), which makes the waiting dead-lock free (the blocked block with
@@ -67,16 +72,23 @@ namespace glsns
 #endif
     constexpr int TS_CH  = GLSNS_TRSV_ITEM; // entries per item (a multiple of 32)
     constexpr int TS_U   = TS_CH / 32; // entries per lane and item
-    constexpr int TS_WIN = 16;         // rows of the chain kept in the window
+#ifndef GLSNS_TRSV_WIN
+#define GLSNS_TRSV_WIN 48
+#endif
+    constexpr int TS_WIN  = GLSNS_TRSV_WIN; // rows of the chain behind a block that its recurrence couples to
+    constexpr int TS_HIST = 64;        // rows of a chain kept in its shared-memory window
     constexpr int TS_BG  = 4;          // groups per block (the solver's unit)
     constexpr int TS_BR  = 16;         // rows per block
-    static_assert(TS_BR == TRSV_G * TS_BG && TS_BR == TS_WIN, "block = window = 16 rows");
+    constexpr int TS_WH  = TS_WIN / 2; // window rows per lane of a row's lane pair
+    constexpr int TS_NC  = TS_WH + 8;  // coefficients per lane: TS_WH of G, 8 of M
+    static_assert(TS_BR == TRSV_G * TS_BG && TS_WIN % 8 == 0 && TS_WIN >= 16 && TS_WIN + TS_BR <= TS_HIST,
+                  "blocks of 16 rows; the window and the block being written share the history");
     // item blob (bytes, 16-byte aligned), first 16 bytes = header
     //   helper item: r0 | flags | block position in the team's list << 4 | row offset in the
     //                block | bytes/16 of the blob NSLOT items ahead;
     //                then col 4*pad4(entries) | val 8*m*pad4(entries)
     //   solver item (one per block): r0 | flags | - | bytes/16 of the blob NSLOT items ahead;
-    //                then the block's solved recurrence, 16 x 2R doubles (R = rows padded to 4)
+    //                then the block's solved recurrence, TS_NC x 2R doubles (R = rows padded to 4)
     constexpr int TS_OFF_COL0 = 16;
     constexpr int TS_OFF_C    = 16;
     constexpr int TS_NSLOT     = 4; // ring slots of every warp (helper and solver)
@@ -101,7 +113,7 @@ namespace glsns
     blob_bytes(int flags)
     {
       const int m = flags & 31, c = pad4(flags >> 16);
-      return (flags & IT_SOLVER) ? TS_OFF_C + 256 * pad4(m) : TS_OFF_COL0 + 4 * c + 8 * m * c;
+      return (flags & IT_SOLVER) ? TS_OFF_C + 16 * TS_NC * pad4(m) : TS_OFF_COL0 + 4 * c + 8 * m * c;
     }
     // per-warp entry of the stream directory (64 bytes)
     struct TrsvWarpDir
@@ -209,13 +221,13 @@ namespace glsns
 
     // values (after every factorisation)
     template <bool UPPER>
-    __global__ void __launch_bounds__(256)
+    __global__ void __launch_bounds__(128)
     trsv_pack_values_kernel(const int64_t n_items, const TrsvItem *__restrict__ items,
                             const TrsvItem *__restrict__ gdesc,
                             const int64_t *__restrict__ blob_off, const double *__restrict__ lu,
                             unsigned char *__restrict__ stream)
     {
-      __shared__ double TF[8][2 * TS_BR * TS_BR]; // per warp: T [16][16], F [16][16]
+      __shared__ double TF[4][TS_BR * TS_BR + TS_BR * TS_WIN]; // per warp: T [16][16], F [16][TS_WIN]
       const int64_t it   = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       const int     lane = threadIdx.x & 31;
       if (it >= n_items)
@@ -241,70 +253,76 @@ namespace glsns
       // 16 x 16 triangle costs a few ulps times its condition number; Ifpack substitutes).
       double *T = TF[(threadIdx.x >> 5)], *F = T + TS_BR * TS_BR;
       for (int k = lane; k < TS_BR * TS_BR; k += 32)
-        {
-          T[k] = (k / TS_BR == k % TS_BR) ? 1.0 : 0.0;
-          F[k] = 0.0;
-        }
+        T[k] = (k / TS_BR == k % TS_BR) ? 1.0 : 0.0;
+      for (int k = lane; k < TS_BR * TS_WIN; k += 32)
+        F[k] = 0.0;
       __syncwarp();
       const int r0b = d.r0;
       for (int q = 0; q < d.len; ++q)
         {
           const TrsvItem gq = gdesc[d.rs0 + q];
           const int      mg = gq.flags & 31, off = gq.r0 - r0b;
-          const unsigned fm = (unsigned)gq.fmask;
+          const unsigned long long fm =
+            (unsigned long long)(unsigned)gq.fmask | ((unsigned long long)(unsigned)gq.fmask2 << 32);
           for (int a = 0; a < mg; ++a)
             {
               const double *row = lu + gq.rs0 + (int64_t)a * gq.len;
               if (lane < mg && (UPPER ? lane >= a : lane < a))
                 T[(off + a) * TS_BR + off + lane] = row[gq.nlow + lane];
-              if (lane < TS_WIN && (fm & (1u << lane)))
-                {
-                  const int    before = __popc(fm & ((1u << lane) - 1u));
-                  const double v      = row[UPPER ? gq.nlow + mg + before : gq.nlow - 1 - before];
-                  const int    tr     = UPPER ? gq.r0 + mg + lane : gq.r0 - 1 - lane; // coupled row
-                  if (UPPER ? tr < r0b + m : tr >= r0b)
-                    T[(off + a) * TS_BR + tr - r0b] = v;
-                  else
-                    F[(off + a) * TS_BR + (UPPER ? tr - (r0b + m) : r0b - 1 - tr)] = v;
-                }
+              for (int dd = lane; dd < TS_WIN; dd += 32)
+                if (fm & (1ull << dd))
+                  {
+                    const int    before = __popcll(fm & ((1ull << dd) - 1ull));
+                    const double v      = row[UPPER ? gq.nlow + mg + before : gq.nlow - 1 - before];
+                    const int    tr     = UPPER ? gq.r0 + mg + dd : gq.r0 - 1 - dd; // coupled row
+                    if (UPPER ? tr < r0b + m : tr >= r0b)
+                      T[(off + a) * TS_BR + tr - r0b] = v;
+                    else
+                      F[(off + a) * TS_WIN + (UPPER ? tr - (r0b + m) : r0b - 1 - tr)] = v;
+                  }
             }
         }
       __syncwarp();
-      // lane c < 16 solves for column c of M, lane c >= 16 for column c - 16 of G
-      double y[TS_BR];
-      if (UPPER)
-        {
-#pragma unroll
-          for (int a = TS_BR - 1; a >= 0; --a)
-            {
-              double v = lane < TS_BR ? (lane == a ? 1.0 : 0.0) : F[a * TS_BR + lane - TS_BR];
-#pragma unroll
-              for (int b = TS_BR - 1; b > a; --b)
-                v -= T[a * TS_BR + b] * y[b];
-              y[a] = v / T[a * TS_BR + a];
-            }
-        }
-      else
-        {
-#pragma unroll
-          for (int a = 0; a < TS_BR; ++a)
-            {
-              double v = lane < TS_BR ? (lane == a ? 1.0 : 0.0) : F[a * TS_BR + lane - TS_BR];
-#pragma unroll
-              for (int b = 0; b < a; ++b)
-                v -= T[a * TS_BR + b] * y[b];
-              y[a] = v;
-            }
-        }
-      // layout the solver reads without bank conflicts: C[jj][2 a + hh], jj < 8: G[a][8 hh + jj],
-      // jj >= 8: M[a][8 hh + jj - 8]
+      // one column per lane and pass: columns 0 .. 15 are those of M, 16 .. 16 + TS_WIN - 1 of G.
+      // Layout the solver reads without bank conflicts: C[jj][2 a + hh]; jj < TS_WH:
+      // G[a][TS_WH hh + jj] (the chain row at distance TS_WH hh + jj), jj >= TS_WH:
+      // M[a][8 hh + jj - TS_WH]
       const int R2 = 2 * pad4(m);
       double   *C  = reinterpret_cast<double *>(B + TS_OFF_C);
-      const int cc = lane & 15, hh = cc >> 3, jj = (cc & 7) + (lane < TS_BR ? 8 : 0);
+      for (int c = lane; c < TS_BR + TS_WIN; c += 32)
+        {
+          double y[TS_BR];
+          if (UPPER)
+            {
 #pragma unroll
-      for (int a = 0; a < TS_BR; ++a)
-        if (2 * a < R2)
-          C[jj * R2 + 2 * a + hh] = y[a];
+              for (int a = TS_BR - 1; a >= 0; --a)
+                {
+                  double v = c < TS_BR ? (c == a ? 1.0 : 0.0) : F[a * TS_WIN + c - TS_BR];
+#pragma unroll
+                  for (int b = TS_BR - 1; b > a; --b)
+                    v -= T[a * TS_BR + b] * y[b];
+                  y[a] = v / T[a * TS_BR + a];
+                }
+            }
+          else
+            {
+#pragma unroll
+              for (int a = 0; a < TS_BR; ++a)
+                {
+                  double v = c < TS_BR ? (c == a ? 1.0 : 0.0) : F[a * TS_WIN + c - TS_BR];
+#pragma unroll
+                  for (int b = 0; b < a; ++b)
+                    v -= T[a * TS_BR + b] * y[b];
+                  y[a] = v;
+                }
+            }
+          const int hh = c < TS_BR ? c >> 3 : (c - TS_BR) / TS_WH;
+          const int jj = c < TS_BR ? TS_WH + (c & 7) : (c - TS_BR) % TS_WH;
+#pragma unroll
+          for (int a = 0; a < TS_BR; ++a)
+            if (2 * a < R2)
+              C[jj * R2 + 2 * a + hh] = y[a];
+        }
     }
 
     // ---- the solve ---------------------------------------------------------------
@@ -322,11 +340,12 @@ namespace glsns
     //     solved ahead of time; publish.  The chain advances 16 rows per step.
     constexpr int TS_MBOX  = 8;  // mailbox entries (blocks) per team
     constexpr int TS_HSLOT = TS_OFF_COL0 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 2320 (64-entry items)
-    constexpr int TS_SSLOT = TS_OFF_C + 256 * TS_BR;                        // 4112
-    // team area: windows 4 x 128 | mailbox 8 x 128 | solved counter 16 | barriers
-    constexpr int TS_TEAM_AREA = 2048;
+    constexpr int TS_SSLOT = TS_OFF_C + 16 * TS_NC * TS_BR;                 // 8208 (48-row window)
+    // team area: windows 4 x 512 | mailbox 8 x 128 | solved counter 16 | barriers
+    constexpr int TS_OFF_MBOX  = 8 * TS_HIST * TS_NWIN;
+    constexpr int TS_TEAM_AREA = TS_OFF_MBOX + 1536;
     static_assert(TS_MBOX == 8 && TS_NWIN == 4 &&
-                    128 * TS_NWIN + 128 * TS_MBOX + 16 + 8 * 12 * TS_NSLOT <= TS_TEAM_AREA,
+                    TS_OFF_MBOX + 128 * TS_MBOX + 16 + 8 * 12 * TS_NSLOT <= TS_TEAM_AREA,
                   "team area");
 
     template <bool UPPER>
@@ -346,11 +365,11 @@ namespace glsns
       const size_t  team_smem = (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_NSLOT * TS_SSLOT + TS_TEAM_AREA;
       unsigned char *T0   = smem_all + (size_t)team_in_cta * team_smem;
       unsigned char *area = T0 + (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_NSLOT * TS_SSLOT;
-      double        *wsm_all = reinterpret_cast<double *>(area);         // [TS_NWIN][16] chain windows by row & 15
-      double        *mbox = reinterpret_cast<double *>(area + 128 * TS_NWIN); // [TS_MBOX][16], all-ones = empty
-      volatile int  *done = reinterpret_cast<volatile int *>(area + 128 * TS_NWIN + 128 * TS_MBOX); // blocks solved
+      double        *wsm_all = reinterpret_cast<double *>(area);         // [TS_NWIN][64] chain windows by row & 63
+      double        *mbox = reinterpret_cast<double *>(area + TS_OFF_MBOX); // [TS_MBOX][16], all-ones = empty
+      volatile int  *done = reinterpret_cast<volatile int *>(area + TS_OFF_MBOX + 128 * TS_MBOX); // blocks solved
       unsigned long long *bars_all =
-        reinterpret_cast<unsigned long long *>(area + 128 * TS_NWIN + 128 * TS_MBOX + 16);
+        reinterpret_cast<unsigned long long *>(area + TS_OFF_MBOX + 128 * TS_MBOX + 16);
       const TrsvWarpDir  *D        = dir + team * (K + 1) + role;
       const int64_t       n_items  = D->n_items;
       unsigned long long  policy;
@@ -359,7 +378,8 @@ namespace glsns
       // visible to the helpers by the one CTA barrier of the kernel
       if (role == 0)
         {
-          wsm_all[lane] = wsm_all[lane + 32] = 0.0; // TS_NWIN * 16 = 64 entries
+          for (int k = lane; k < TS_NWIN * TS_HIST; k += 32)
+            wsm_all[k] = 0.0;
 #pragma unroll
           for (int k = 0; k < TS_MBOX * TS_BR / 32; ++k)
             reinterpret_cast<unsigned long long *>(mbox)[lane + 32 * k] = SENTINEL;
@@ -419,29 +439,31 @@ namespace glsns
               const unsigned char *S  = ring + (size_t)slot * TS_SSLOT;
               const int4           h  = *reinterpret_cast<const int4 *>(S);
               const int            r0 = h.x, m = h.y & 31, R2 = 2 * pad4(m);
-              double              *wsm = wsm_all + 16 * ((h.y >> 12) & (TS_NWIN - 1));
+              double              *wsm = wsm_all + TS_HIST * ((h.y >> 12) & (TS_NWIN - 1));
               const double        *C   = reinterpret_cast<const double *>(S + TS_OFF_C) + lane;
               const bool           on  = lane < R2;
-              double               cg[8], cm[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                {
-                  cg[j] = on ? C[j * R2] : 0.0;
-                  cm[j] = on ? C[(j + 8) * R2] : 0.0;
-                }
-              // the window part first: it is what the chain waits for
+              // the window part first: it is what the chain waits for (lane (a, hh) takes the
+              // chain rows at distance TS_WH hh ... TS_WH hh + TS_WH - 1 from the block)
               double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
               {
-                const int wb = UPPER ? r0 + m + 8 * hh : r0 - 1 - 8 * hh;
+                double cg[TS_WH];
 #pragma unroll
-                for (int j = 0; j < 8; j += 4)
+                for (int j = 0; j < TS_WH; ++j)
+                  cg[j] = on ? C[j * R2] : 0.0;
+                const int wb = UPPER ? r0 + m + TS_WH * hh : r0 - 1 - TS_WH * hh;
+#pragma unroll
+                for (int j = 0; j < TS_WH; j += 4)
                   {
-                    p0 += cg[j] * wsm[(UPPER ? wb + j : wb - j) & 15];
-                    p1 += cg[j + 1] * wsm[(UPPER ? wb + j + 1 : wb - j - 1) & 15];
-                    p2 += cg[j + 2] * wsm[(UPPER ? wb + j + 2 : wb - j - 2) & 15];
-                    p3 += cg[j + 3] * wsm[(UPPER ? wb + j + 3 : wb - j - 3) & 15];
+                    p0 += cg[j] * wsm[(UPPER ? wb + j : wb - j) & (TS_HIST - 1)];
+                    p1 += cg[j + 1] * wsm[(UPPER ? wb + j + 1 : wb - j - 1) & (TS_HIST - 1)];
+                    p2 += cg[j + 2] * wsm[(UPPER ? wb + j + 2 : wb - j - 2) & (TS_HIST - 1)];
+                    p3 += cg[j + 3] * wsm[(UPPER ? wb + j + 3 : wb - j - 3) & (TS_HIST - 1)];
                   }
               }
+              double cm[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                cm[j] = on ? C[(j + TS_WH) * R2] : 0.0;
               TS_TICK(1)
               // totals of everything else (minus the right-hand side), from the helpers: a
               // mailbox entry carries its own readiness (all-ones pattern = empty)
@@ -483,7 +505,7 @@ namespace glsns
                   const double v = -p;
                   st_result(x + r0 + a, v);
                   if (!(h.y & IT_GUEST))
-                    wsm[(r0 + a) & 15] = v;
+                    wsm[(r0 + a) & (TS_HIST - 1)] = v;
                   if (trace) // debugging aid (glsns_ilu_apply_trace): when was the row published
                     {
                       unsigned long long tns;
@@ -867,7 +889,8 @@ namespace glsns
     const int32_t max_block     = std::max(1, std::min(TS_BG, getenv("GLSNS_TRSV_BLOCK") ? atoi(getenv("GLSNS_TRSV_BLOCK")) : TS_BG));
     const int     K      = cfg.helpers;
 
-    std::vector<int32_t> glev(ng), fmask(ng), cnt(ng), e_off(ng), order(ng), blk_of(ng);
+    std::vector<int32_t> glev(ng), cnt(ng), e_off(ng), order(ng), blk_of(ng);
+    std::vector<uint64_t> fmask(ng);
     std::vector<uint8_t> link(ng);
 
     // One sweep: levels, blocks, chain links, level-ordered schedule on NW teams, item lists.
@@ -907,7 +930,7 @@ namespace glsns
             {
               const int64_t gap = upper ? grp_ptr[p] - (grp_ptr[g] + grp_m[g]) :
                                           grp_ptr[g] - (grp_ptr[p] + grp_m[p]);
-              if (gap < TS_WIN - 1)
+              if (gap < TS_BR - 1)
                 {
                   if (!upper)
                     for (int64_t k = ke - 1; k >= kb; --k)
@@ -1101,7 +1124,7 @@ namespace glsns
               const int32_t r0 = grp_ptr[g], m = grp_m[g];
               int64_t       kb, ke;
               range(g, kb, ke);
-              uint32_t fm = 0;
+              uint64_t fm = 0;
               int32_t  nf = 0;
               if (!upper)
                 for (int64_t k = ke - 1; k >= kb; --k)
@@ -1109,7 +1132,7 @@ namespace glsns
                     const int32_t d = r0 - 1 - col[k];
                     if (d >= TS_WIN || col[k] < edge || grp_of[col[k]] < 0)
                       break;
-                    fm |= 1u << d;
+                    fm |= 1ull << d;
                     ++nf;
                   }
               else
@@ -1118,10 +1141,10 @@ namespace glsns
                     const int32_t d = col[k] - (r0 + m);
                     if (d >= TS_WIN || col[k] >= edge || grp_of[col[k]] < 0)
                       break;
-                    fm |= 1u << d;
+                    fm |= 1ull << d;
                     ++nf;
                   }
-              fmask[g] = (int32_t)fm;
+              fmask[g] = fm;
               e_off[g] = (int32_t)((upper ? kb + nf : kb) - rowptr[grp_ptr[g]]);
               cnt[g]   = (int32_t)(ke - kb - nf);
             }
@@ -1183,7 +1206,8 @@ namespace glsns
               {
                 TrsvItem &gd = gdesc[(size_t)n_gdesc++];
                 gd.rs0 = rowptr[i], gd.r0 = (int32_t)i, gd.len = len, gd.e_off = 0, gd.flags = m;
-                gd.nlow = (int32_t)(diag[i] - rowptr[i]), gd.fmask = fmask[g];
+                gd.nlow = (int32_t)(diag[i] - rowptr[i]);
+                gd.fmask = (int32_t)(uint32_t)fmask[g], gd.fmask2 = (int32_t)(uint32_t)(fmask[g] >> 32);
               }
               const int32_t nchunk = std::max(1, (cnt[g] + TS_CH - 1) / TS_CH);
               for (int32_t c = 0; c < nchunk; ++c)
@@ -1371,7 +1395,7 @@ namespace glsns
     if (ctx->trsv_l.n_items)
       {
         const int64_t nit = ctx->trsv_l.n_items;
-        trsv_pack_values_kernel<false><<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        trsv_pack_values_kernel<false><<<(unsigned)((nit * 32 + 127) / 128), 128, 0, ctx->stream>>>(
           nit, ctx->trsv_l.items.p, ctx->trsv_l.gdesc.p, ctx->trsv_l.blob_off.p, ctx->lu.p,
           ctx->trsv_l.stream.p);
         ctx->kernel_launches++;
@@ -1379,7 +1403,7 @@ namespace glsns
     if (ctx->trsv_u.n_items)
       {
         const int64_t nit = ctx->trsv_u.n_items;
-        trsv_pack_values_kernel<true><<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        trsv_pack_values_kernel<true><<<(unsigned)((nit * 32 + 127) / 128), 128, 0, ctx->stream>>>(
           nit, ctx->trsv_u.items.p, ctx->trsv_u.gdesc.p, ctx->trsv_u.blob_off.p, ctx->lu.p,
           ctx->trsv_u.stream.p);
         ctx->kernel_launches++;

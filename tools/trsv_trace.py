@@ -96,7 +96,7 @@ for name, t, tp, w, upper in (("lower", tl, hp.last_trace_posts[0], wl, False),
                           "cross_helper_part_us": th / 1e3, "cross_solver_part_us": tsol / 1e3}
     out[name] = o
 for name, pl in zip(("lower", "upper"), hp.last_trace_polls):
-    nw = min(len(pl) // 12, 148 * 3)
+    nw = min(len(pl) // 12, int(__import__('os').environ.get('GLSNS_TRACE_TEAMS', 296)))
     st = pl[:nw * 8].reshape(nw, 8).astype(np.float64)
     busy = st[st[:, 6] > 0]
     tot = busy[:, :5].sum(axis=0)
