@@ -33,7 +33,7 @@ NU = 0.005                                   # Re = 400 with U = 1, L = 2
 LIN = dict(relative_residual=1e-4, minimum_residual=1e-9, max_iterations=5000, restart=30,
            ilu_fill=0, ilu_atol=1e-12, ilu_rtol=1.0)   # examples/01-cavity/cavity.prm:88-94
 METRIC = "MDoF/s per Newton step (assembly+GMRES), 3D cavity Q2-Q2"
-CPU_SAMPLE_CELLS = 16
+CPU_SAMPLE_CELLS = 24     # 470 596 DoFs: about 10-15 s of CPU work per Newton step on 16 cores
 
 
 def peaks():
@@ -103,10 +103,12 @@ def cpu_newton_step_setup(n_cells, threads):
     return state
 
 
-def cpu_newton_step(st, U):
+def cpu_newton_step(st, U, structured=False):
+    """structured=False: the reference's literal q x j x i cell loop (gls_navier_stokes.cc:387-748),
+    "Mode A" of BASELINE.md section 3; True: the structured block form, the best-CPU "Mode B"."""
     import numpy as np
     R, mesh, pr = st["R"], st["mesh"], st["pr"]
-    val, rhs = R.assemble(mesh, U, pr, True, threads=st["threads"])
+    val, rhs = R.assemble(mesh, U, pr, True, threads=st["threads"], structured=structured)
     last = float(np.linalg.norm(rhs))
     tol = max(LIN["relative_residual"] * last, LIN["minimum_residual"])
     lu, dp = R.ilu0(mesh, val, LIN["ilu_atol"], LIN["ilu_rtol"], st["bp"])
@@ -116,7 +118,7 @@ def cpu_newton_step(st, U):
     alpha = 1.0
     while alpha > 1e-3:
         Un = mesh.apply_nonzero_constraints(U + alpha * dx)
-        _, r2 = R.assemble(mesh, Un, pr, False, threads=st["threads"])
+        _, r2 = R.assemble(mesh, Un, pr, False, threads=st["threads"], structured=structured)
         if float(np.linalg.norm(r2)) < 0.9 * last:
             break
         alpha *= 0.5
@@ -139,7 +141,8 @@ def run_reference(args):
     ndof = st["mesh"].ndof
     v = ndof / dt / 1e6
     sample = ("same cavity at n=%d (%d DoFs), Newton iteration 1, %d GMRES iterations, %d threads "
-              "= %d block-Jacobi ILU blocks" % (args.cpu_cells, ndof, its, threads, threads))
+              "= %d block-Jacobi ILU blocks, the reference's literal cell loop (Mode A)"
+              % (args.cpu_cells, ndof, its, threads, threads))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "MDoF/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -147,7 +150,11 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": "3D lid-driven cavity Q2-Q2 Re=400 steady, one Newton iteration "
                                "(CPU restatement of the reference path; Trilinos unavailable)",
-                   "cells_per_dir": args.cpu_cells, "n_dofs": ndof, "gmres_iterations": its},
+                   "cells_per_dir": args.cpu_cells, "n_dofs": ndof, "gmres_iterations": its,
+                   "ilu_blocks": threads,
+                   "same_config_as_gpu_arm": False,
+                   "note": "bounded sample: the GPU arm's default mesh (n=64) would take hours "
+                           "here; the GPU arm prints its own value at this size under same_config"},
         "cpu_baseline": {"value": v, "unit": "MDoF/s", "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "MDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -170,7 +177,7 @@ def newton_step_device(hp, U1_set):
         if hp.rhs_norm() < 0.9 * last:
             break
         alpha *= 0.5
-    return info["iterations"], trials
+    return info["iterations"], trials, info
 
 
 def newton_step_host(hp, U1, constrained, cvalues, pin):
@@ -204,11 +211,108 @@ def newton_step_host(hp, U1, constrained, cvalues, pin):
     return info["iterations"], h2d, d2h
 
 
+class GpuCase:
+    """The cavity at n cells per direction on this rank's GPU, set up through the C ABI, with the
+    linearisation point of the timed Newton step (the state after the first update from rest)."""
+
+    def __init__(self, n, world, rank, local_rank, dist, torch):
+        import numpy as np
+        from softx_2020_200_b200 import GLSHotPath
+        from softx_2020_200_b200.mesh import BoxMesh
+        self.n, self.world, self.dist, self.torch = n, world, dist, torch
+        t0 = time.perf_counter()
+        gmesh = BoxMesh(3, n, 2, 2, bcs=CAVITY)
+        self.n_global, self.nnz_global = gmesh.n_dofs, (int(gmesh.nnz) if world == 1 else None)
+        self.mesh = mesh = gmesh if world == 1 else gmesh.partition(world, rank)
+        self.hp = hp = GLSHotPath(local_rank)
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                uid = torch.from_numpy(GLSHotPath.comm_unique_id().copy())
+            uid = uid.cuda()
+            dist.broadcast(uid, 0)
+            hp.comm_init(world, rank, uid.cpu().numpy())
+        mesh.attach(hp)
+        hp.set_physics(NU)
+        self.setup_s = time.perf_counter() - t0
+        if world > 1:
+            gmesh.close()
+        self.constrained = mesh.array("constrained").astype(bool)
+        self.cvalues = mesh.array("constraint_values").copy()
+        U0 = mesh.initial_state()
+        hp.set_vector("present_solution", U0)
+        hp.set_vector("evaluation_point", U0)
+        self.its0, _, _ = newton_step_device(hp, lambda: None)
+        hp.accept_evaluation_point()
+        self.U1 = hp.get_vector("present_solution")
+        self.pins = {}
+
+    def reset(self):
+        self.hp.set_vector("present_solution", self.U1)
+        self.hp.set_vector("evaluation_point", self.U1)
+
+    def pin(self, name, size):
+        if name not in self.pins:
+            self.pins[name] = self.torch.empty(size, dtype=self.torch.float64, pin_memory=True)
+        return self.pins[name].numpy()
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_device(self, steps, warmup, clocks=None):
+        """K Newton steps with the state resident in HBM, timed by the library's CUDA-event phase
+        timers on its stream; max over ranks."""
+        hp = self.hp
+        for _ in range(warmup):
+            self.reset()
+            newton_step_device(hp, lambda: None)
+        self.barrier()
+        hp.reset_timers()
+        if clocks:
+            clocks.start()
+        wall0 = time.perf_counter()
+        its = trials = 0
+        info = None
+        for _ in range(steps):
+            self.reset()
+            its, trials, info = newton_step_device(hp, lambda: None)
+        self.barrier()
+        wall = time.perf_counter() - wall0
+        tm = hp.timers()
+        dev_ms = (tm["assemble_system_ms"] + tm["assemble_rhs_ms"] + tm["setup_ilu_ms"] +
+                  tm["solve_linear_system_ms"]) / steps
+        dev_ms = self.max_over_ranks(dev_ms)
+        return dict(ms=dev_ms, value=self.n_global / (dev_ms * 1e-3) / 1e6, wall_ms=wall / steps * 1e3,
+                    its=its, trials=trials, info=info, timers=tm)
+
+    def time_e2e(self, steps):
+        """The same steps through host buffers (pinned): H2D of every evaluation point, D2H of the
+        update and of every residual norm, inside the timed region; max over ranks."""
+        newton_step_host(self.hp, self.U1, self.constrained, self.cvalues, self.pin)   # warm-up
+        self.barrier()
+        e0 = time.perf_counter()
+        h2d = d2h = 0
+        for _ in range(steps):
+            _, h2d, d2h = newton_step_host(self.hp, self.U1, self.constrained, self.cvalues, self.pin)
+        self.barrier()
+        s = self.max_over_ranks((time.perf_counter() - e0) / steps)
+        return dict(value=self.n_global / s / 1e6, ms=s * 1e3, h2d=int(h2d), d2h=int(d2h))
+
+    def close(self):
+        self.hp.close()
+
+
 def run_ours(args):
-    import numpy as np
     import torch
-    from softx_2020_200_b200 import GLSHotPath
-    from softx_2020_200_b200.mesh import BoxMesh
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -221,90 +325,26 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    # ---- N > 1: parity of the partitioned path against the block-Jacobi oracle, before timing ----
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        from tests.multi_gpu_check import check as multi_gpu_check
+        parity = multi_gpu_check(args.parity_cells, world, rank, local_rank, dist)
+        if not parity["ok"]:
+            raise SystemExit("multi-GPU parity check failed: %r" % (parity,))
 
     n = args.cells
-    t0 = time.perf_counter()
-    gmesh = BoxMesh(3, n, 2, 2, bcs=CAVITY)
-    n_global = gmesh.n_dofs
-    mesh = gmesh if world == 1 else gmesh.partition(world, rank)
-    hp = GLSHotPath(local_rank)
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            uid = torch.from_numpy(GLSHotPath.comm_unique_id().copy())
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        hp.comm_init(world, rank, uid.cpu().numpy())
-    mesh.attach(hp)
-    hp.set_physics(NU)
-    t_setup = time.perf_counter() - t0
-    if world > 1:
-        gmesh.close()
-
-    constrained = mesh.array("constrained").astype(bool)
-    cvalues = mesh.array("constraint_values").copy()
-    U0 = mesh.initial_state()
-    # Newton iteration 0 from rest -> U1, the linearisation point of every timed step
-    hp.set_vector("present_solution", U0)
-    hp.set_vector("evaluation_point", U0)
-    its0, _ = newton_step_device(hp, lambda: None)
-    hp.accept_evaluation_point()
-    U1 = hp.get_vector("present_solution")
-
-    def reset():
-        hp.set_vector("present_solution", U1)
-        hp.set_vector("evaluation_point", U1)
-
-    pins = {}
-
-    def pin(name, size):
-        if name not in pins:
-            pins[name] = torch.empty(size, dtype=torch.float64, pin_memory=True)
-        return pins[name].numpy()
-
-    # ---- device-resident arm ----
-    for _ in range(max(args.warmup - 1, 0)):
-        reset()
-        newton_step_device(hp, lambda: None)
+    case = GpuCase(n, world, rank, local_rank, dist, torch)
+    hp, mesh = case.hp, case.mesh
     clocks = ClockSampler(local_rank)
-    barrier()
-    hp.reset_timers()
-    clocks.start()
-    wall0 = time.perf_counter()
-    its = trials = 0
-    for _ in range(args.steps):
-        reset()
-        its, trials = newton_step_device(hp, lambda: None)
-    barrier()
-    wall = time.perf_counter() - wall0
+    dev = case.time_device(args.steps, max(args.warmup - 1, 0), clocks)
     clk = clocks.stop()
-    tm = hp.timers()
-    dev_ms = (tm["assemble_system_ms"] + tm["assemble_rhs_ms"] + tm["setup_ilu_ms"] +
-              tm["solve_linear_system_ms"]) / args.steps
-    dev_ms = max_over_ranks(dev_ms)
-    value = n_global / (dev_ms * 1e-3) / 1e6
-
-    # ---- end-to-end arm: host buffers in, host buffers out ----
-    newton_step_host(hp, U1, constrained, cvalues, pin)              # warm-up
-    barrier()
-    e0 = time.perf_counter()
-    h2d = d2h = 0
-    for _ in range(args.steps):
-        _, h2d, d2h = newton_step_host(hp, U1, constrained, cvalues, pin)
-    barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - e0) / args.steps)
-    e2e = n_global / e2e_s / 1e6
+    tm, dev_ms, value, its, trials = dev["timers"], dev["ms"], dev["value"], dev["its"], dev["trials"]
+    info = dev["info"]
+    if not (info["true_residual"] <= info["tolerance"] * 1.01):
+        raise SystemExit("GMRES' logged residual %.3e exceeds its tolerance %.3e: the step is invalid"
+                         % (info["true_residual"], info["tolerance"]))
+    e2e = case.time_e2e(args.steps)
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the library stream ----
     hbm, hbm_src = peaks()
@@ -319,24 +359,50 @@ def run_ours(args):
               ("setup_ilu", "setup_ilu_ms"))}
     dom = "ilu_apply" if tm["trsv_ms"] >= tm["spmv_ms"] else "spmv"
     achieved = algo[dom] / (per[dom] * 1e-3) / 1e9
-    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    # (profiles/), only when it was taken on this very workload
-    traffic = None
+    # DRAM bytes per launch from the committed ncu --set full captures (profiles/traffic.json),
+    # only when they were taken on this very workload
+    cap = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             cap = json.load(f)
-        key = "%s@n%d" % (dom, n)
-        if world == 1 and key in cap:
-            traffic = cap[key]["dram_bytes_per_launch"]
-    except (OSError, ValueError, KeyError):
+    except (OSError, ValueError):
         pass
+
+    def traffic_of(kernel):
+        key = "%s@n%d" % (kernel, n)
+        return cap[key]["dram_bytes_per_launch"] if world == 1 and key in cap else None
+
+    def line(kernel):
+        t = traffic_of(kernel)
+        a = algo[kernel] / (per[kernel] * 1e-3) / 1e9
+        return {"achieved": a, "frac": a / hbm, "avg_launch_ms": per[kernel],
+                "share_of_step": share[kernel], "traffic": t,
+                "dram_frac": (t / (per[kernel] * 1e-3) / 1e9 / hbm) if t else None}
+
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": traffic, "peak_source": hbm_src,
+                "frac": achieved / hbm, "traffic": traffic_of(dom), "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": algo[dom], "avg_launch_ms": per[dom],
-                "share_of_step": share[dom],
-                "spmv": {"achieved": algo["spmv"] / (per["spmv"] * 1e-3) / 1e9,
-                         "frac": algo["spmv"] / (per["spmv"] * 1e-3) / 1e9 / hbm,
-                         "avg_launch_ms": per["spmv"], "share_of_step": share["spmv"]}}
+                "share_of_step": share[dom], "spmv": line("spmv"), "ilu_apply": line("ilu_apply")}
+    fp64 = cap.get("fp64_peak")
+    if fp64 and world == 1:
+        # assembly: algorithmic flops of the structured form (2.5e6 per Q2-Q2 hex
+        # for matrix + rhs) against the fp64 FMA peak measured on this pool (tools/fp64_peak.cu)
+        ms_asm = tm["assemble_system_ms"] / max(tm["assemble_system_calls"], 1)
+        tf = 2.5e6 * mesh.n_cells / (ms_asm * 1e-3) / 1e12
+        roofline["assembly"] = {"bound": "fp64", "achieved": tf, "peak": fp64["tflops"],
+                                "unit": "TFLOP/s", "frac": tf / fp64["tflops"], "avg_launch_ms": ms_asm,
+                                "peak_source": fp64.get("source")}
+
+    # ---- the GPU arm once more at the CPU sample size: a same-configuration ratio ----
+    same = None
+    if world == 1 and not args.no_cpu_baseline and args.cpu_cells != n:
+        small = GpuCase(args.cpu_cells, 1, 0, local_rank, None, torch)
+        sd = small.time_device(3, 1)
+        se = small.time_e2e(3)
+        same = {"cells_per_dir": args.cpu_cells, "n_dofs": small.n_global,
+                "gpu": {"value": sd["value"], "e2e": se["value"], "ms_per_step": sd["ms"],
+                        "gmres_iterations": sd["its"], "ilu_blocks": 1}}
+        small.close()
 
     if rank != 0:
         return
@@ -347,21 +413,25 @@ def run_ours(args):
         "config": {"workload": "3D lid-driven cavity Q2-Q2, Re=400 steady, one Newton iteration at "
                                "the state after the first Newton update from rest; GMRES(30)+ILU(0), "
                                "rel 1e-4 / abs 1e-9, ILU atol 1e-12",
-                   "cells_per_dir": n, "n_dofs": n_global, "nnz": int(gmesh.nnz) if world == 1 else None,
+                   "cells_per_dir": n, "n_dofs": case.n_global, "nnz": case.nnz_global,
                    "gmres_iterations": its, "line_search_trials": trials,
+                   "true_residual": info["true_residual"], "tolerance": info["tolerance"],
+                   "ilu_blocks": world,
                    "parallelism": "1 rank per GPU, contiguous row blocks, block-Jacobi ILU per rank"
                    if world > 1 else "1 GPU",
                    "cache": "inputs larger than L2 (matrix+factors %.1f GB)" % (20 * nnz / 1e9)},
         "gpu_launches": int(tm["kernel_launches"]),
-        "wall_ms_per_step": wall / args.steps * 1e3,
+        "wall_ms_per_step": dev["wall_ms"],
         "phases_ms_per_step": {k: tm[k] / args.steps for k in
                                ("assemble_system_ms", "assemble_rhs_ms", "setup_ilu_ms",
                                 "solve_linear_system_ms", "spmv_ms", "trsv_ms", "orthog_ms")},
-        "setup_s": t_setup, "first_newton_iteration_gmres_iterations": its0,
-        "e2e": {"value": e2e, "unit": "MDoF/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+        "setup_s": case.setup_s, "first_newton_iteration_gmres_iterations": case.its0,
+        "e2e": {"value": e2e["value"], "unit": "MDoF/s", "h2d_bytes_per_step": e2e["h2d"],
+                "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"]},
         "roofline": roofline, "clocks": clk,
     }
+    if parity is not None:
+        out["parity_check"] = parity
     # ---- CPU baseline on this box's host cores (bounded sample), rank 0, N = 1 only ----
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -369,14 +439,33 @@ def run_ours(args):
         c0 = time.perf_counter()
         _, cits = cpu_newton_step(st, st["U1"])
         cdt = time.perf_counter() - c0
+        ndof_c = st["mesh"].ndof
         out["cpu_baseline"] = {
-            "value": st["mesh"].ndof / cdt / 1e6, "unit": "MDoF/s", "cores": threads,
+            "value": ndof_c / cdt / 1e6, "unit": "MDoF/s", "cores": threads,
             "kind": "port",
             "sample": "same cavity at n=%d (%d DoFs), Newton iteration 1, %d GMRES iterations, %d "
-                      "threads = %d block-Jacobi ILU blocks, %.1f s" %
-                      (args.cpu_cells, st["mesh"].ndof, cits, threads, threads, cdt)}
+                      "threads = %d block-Jacobi ILU blocks, %.1f s; the reference's literal cell loop "
+                      "(Mode A)" % (args.cpu_cells, ndof_c, cits, threads, threads, cdt)}
+        c0 = time.perf_counter()
+        _, cits_b = cpu_newton_step(st, st["U1"], structured=True)
+        cdt_b = time.perf_counter() - c0
+        out["cpu_baseline_structured"] = {
+            "value": ndof_c / cdt_b / 1e6, "unit": "MDoF/s", "cores": threads, "kind": "port",
+            "sample": "as cpu_baseline with the structured (block-form) cell kernel instead of the "
+                      "reference's literal loop (Mode B, best CPU), %d GMRES iterations, %.1f s"
+                      % (cits_b, cdt_b)}
+        if same is not None:
+            same["cpu"] = {"value": ndof_c / cdt / 1e6, "gmres_iterations": cits,
+                           "ilu_blocks": threads, "cores": threads}
+            same["cpu_structured"] = {"value": ndof_c / cdt_b / 1e6}
+            same["ratio_e2e"] = same["gpu"]["e2e"] / same["cpu"]["value"]
+            same["ratio_e2e_vs_structured_cpu"] = same["gpu"]["e2e"] / same["cpu_structured"]["value"]
+            same["note"] = ("both arms on the same mesh and tolerances; the CPU arm runs one "
+                            "block-Jacobi ILU block per thread (what Ifpack with overlap 0 gives on "
+                            "that many MPI ranks), the GPU one block: the iteration counts differ")
+            out["same_config"] = same
     print(json.dumps(out))
-    hp.close()
+    case.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -391,6 +480,9 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=CPU_SAMPLE_CELLS)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--parity-cells", type=int, default=8,
+                    help="N > 1: mesh of the parity check against the oracle that precedes the timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

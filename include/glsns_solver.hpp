@@ -7,14 +7,16 @@
 //               FEM, PhysicalProperties, VelocitySource}   include/core/parameters.h,
 //                                                           source/core/parameters.cc
 //   PhysicsSolver<VectorType>                               include/core/physics_solver.h:38-158
-//   NonLinearSolver / NewtonNonLinearSolver                 include/core/newton_non_linear_solver.h:76-139
-//   SkipNewtonNonLinearSolver                               include/core/skip_newton_non_linear_solver.h:53-133
+//   NonLinearSolver (the abstract driver interface)         include/core/non_linear_solver.h
 //   GLSNavierStokesSolver::{assemble_matrix_and_rhs, assemble_rhs, solve_linear_system,
 //                           setup_ILU, solve_system_GMRES}  source/solvers/gls_navier_stokes.cc:916-1289
 //
 // A maintainer of the reference drops the three overrides of glsns::GLSNavierStokesSolver into
 // GLSNavierStokesSolver<dim> (INTEGRATION.md shows the diff); here VectorType is glsns::Vector, a
-// plain host vector with the handful of operations the Newton drivers use.
+// plain host vector with the handful of operations the Newton drivers use.  The Newton drivers
+// themselves (NewtonNonLinearSolver, SkipNewtonNonLinearSolver) and NavierStokesBase's
+// time-stepping glue are the reference's and are NOT part of this product: the tests drive this
+// class with a labelled transcription of them that lives under tests/mirror/.
 #ifndef GLSNS_SOLVER_HPP
 #define GLSNS_SOLVER_HPP
 
@@ -435,10 +437,13 @@ namespace glsns
   class PhysicsSolver
   {
   public:
-    explicit PhysicsSolver(NonLinearSolver<VectorType> *non_linear_solver)
+    // The Newton drivers (include/core/newton_non_linear_solver.h, skip_newton_non_linear_solver.h)
+    // are the reference's own and stay with it: the driver is handed in (the reference's
+    // constructor picks it from Parameters::NonLinearSolver, physics_solver.h:126-145) and
+    // owned, as there (physics_solver.h:54-57).
+    explicit PhysicsSolver(NonLinearSolver<VectorType> *non_linear_solver = nullptr)
       : non_linear_solver(non_linear_solver)
     {}
-    explicit PhysicsSolver(Parameters::NonLinearSolver non_linear_solver_parameters);
     virtual ~PhysicsSolver();
 
     virtual void
@@ -450,7 +455,12 @@ namespace glsns
 
     void
     solve_non_linear_system(const TimeSteppingMethod time_stepping_method,
-                            const bool first_iteration, const bool force_matrix_renewal);
+                            const bool first_iteration, const bool force_matrix_renewal)
+    {
+      if (!non_linear_solver)
+        throw std::runtime_error("PhysicsSolver: no non-linear solver attached");
+      non_linear_solver->solve(time_stepping_method, first_iteration, force_matrix_renewal);
+    }
 
     // nonzero_constraints.distribute(local_evaluation_point)
     virtual void
@@ -491,239 +501,10 @@ namespace glsns
     Parameters::NonLinearSolver params;
   };
 
-  // Newton with backtracking line search (newton_non_linear_solver.h:76-139)
-  template <typename VectorType>
-  class NewtonNonLinearSolver : public NonLinearSolver<VectorType>
-  {
-  public:
-    using NonLinearSolver<VectorType>::NonLinearSolver;
-    void
-    solve(const TimeSteppingMethod time_stepping_method, const bool is_initial_step,
-          const bool = true) override
-    {
-      double       current_res = 1.0, last_res = 1.0;
-      const bool   first_step      = is_initial_step;
-      unsigned int outer_iteration = 0;
-      auto        *solver          = this->physics_solver;
-      while ((current_res > this->params.tolerance) &&
-             outer_iteration < this->params.max_iterations)
-        {
-          solver->evaluation_point = solver->present_solution;
-          solver->assemble_matrix_and_rhs(time_stepping_method);
-          if (outer_iteration == 0)
-            {
-              current_res = solver->system_rhs.l2_norm();
-              last_res    = current_res;
-            }
-          if (this->params.verbosity != Parameters::Verbosity::quiet)
-            solver->pcout << "Newton iteration: " << outer_iteration
-                          << "  - Residual:  " << current_res << std::endl;
-          solver->solve_linear_system(first_step);
-          line_search(solver, time_stepping_method, current_res, last_res, this->params);
-          solver->present_solution = solver->evaluation_point;
-          last_res                 = current_res;
-          ++outer_iteration;
-        }
-    }
-
-    static void
-    line_search(PhysicsSolver<VectorType> *solver, const TimeSteppingMethod method,
-                double &current_res, const double last_res, const Parameters::NonLinearSolver &params)
-    {
-      for (double alpha = 1.0; alpha > 1e-3; alpha *= 0.5)
-        {
-          solver->local_evaluation_point = solver->present_solution;
-          solver->local_evaluation_point.add(alpha, solver->newton_update);
-          solver->apply_constraints();
-          solver->evaluation_point = solver->local_evaluation_point;
-          solver->assemble_rhs(method);
-          current_res = solver->system_rhs.l2_norm();
-          if (params.verbosity != Parameters::Verbosity::quiet)
-            solver->pcout << "\t\talpha = " << std::setw(6) << alpha << std::setw(0)
-                          << " res = " << std::setprecision(params.display_precision)
-                          << current_res << std::endl;
-          if (current_res < 0.9 * last_res || last_res < params.tolerance)
-            break;
-        }
-    }
-  };
-
-  // Same loop; Jacobian + preconditioner rebuilt every `skip iterations` calls
-  // (skip_newton_non_linear_solver.h:53-133)
-  template <typename VectorType>
-  class SkipNewtonNonLinearSolver : public NonLinearSolver<VectorType>
-  {
-  public:
-    using NonLinearSolver<VectorType>::NonLinearSolver;
-    void
-    solve(const TimeSteppingMethod time_stepping_method, const bool is_initial_step,
-          const bool force_matrix_renewal = true) override
-    {
-      double       current_res = 1.0, last_res = 1.0;
-      const bool   first_step      = is_initial_step;
-      unsigned int outer_iteration = 0;
-      bool assembly_needed = consecutive_iters == 0 || is_initial_step || force_matrix_renewal;
-      auto *solver         = this->physics_solver;
-      while ((current_res > this->params.tolerance) &&
-             outer_iteration < this->params.max_iterations)
-        {
-          solver->evaluation_point = solver->present_solution;
-          if (assembly_needed)
-            solver->assemble_matrix_and_rhs(time_stepping_method);
-          else if (outer_iteration == 0)
-            solver->assemble_rhs(time_stepping_method);
-          if (outer_iteration == 0)
-            {
-              current_res = solver->system_rhs.l2_norm();
-              last_res    = current_res;
-            }
-          if (this->params.verbosity != Parameters::Verbosity::quiet)
-            solver->pcout << "Newton iteration: " << outer_iteration
-                          << "  - Residual:  " << current_res << std::endl;
-          solver->solve_linear_system(first_step, assembly_needed);
-          NewtonNonLinearSolver<VectorType>::line_search(solver, time_stepping_method,
-                                                         current_res, last_res, this->params);
-          solver->present_solution = solver->evaluation_point;
-          last_res                 = current_res;
-          ++outer_iteration;
-          assembly_needed = false;
-        }
-      if (!force_matrix_renewal)
-        {
-          consecutive_iters++;
-          consecutive_iters = consecutive_iters % this->params.skip_iterations;
-        }
-    }
-
-  private:
-    unsigned int consecutive_iters = 0;
-  };
-
-  template <typename VectorType>
-  PhysicsSolver<VectorType>::PhysicsSolver(Parameters::NonLinearSolver p)
-  {
-    switch (p.solver)
-      {
-        case Parameters::NonLinearSolver::SolverType::newton:
-          non_linear_solver = new NewtonNonLinearSolver<VectorType>(this, p);
-          break;
-        case Parameters::NonLinearSolver::SolverType::skip_newton:
-          non_linear_solver = new SkipNewtonNonLinearSolver<VectorType>(this, p);
-          break;
-        default:
-          break;
-      }
-  }
-
   template <typename VectorType>
   PhysicsSolver<VectorType>::~PhysicsSolver()
   {
     delete non_linear_solver;
-  }
-
-  template <typename VectorType>
-  void
-  PhysicsSolver<VectorType>::solve_non_linear_system(const TimeSteppingMethod method,
-                                                     const bool first_iteration,
-                                                     const bool force_matrix_renewal)
-  {
-    this->non_linear_solver->solve(method, first_iteration, force_matrix_renewal);
-  }
-
-  // ------------------------------------------------------------------------------------------
-  // Time-stepping glue of NavierStokesBase around solve_non_linear_system (the caller of the hot
-  // path in a transient run, source/solvers/navier_stokes_base.cc:428-590), for any solver that
-  // has present_solution, solution_m1..m3, time_steps_vector and solve_non_linear_system.
-  // ------------------------------------------------------------------------------------------
-  inline bool
-  is_bdf(const TimeSteppingMethod method)
-  {
-    return method == TimeSteppingMethod::bdf1 || method == TimeSteppingMethod::bdf2 ||
-           method == TimeSteppingMethod::bdf3;
-  }
-
-  // SimulationControl::add_time_step (source/core/simulation_control.cc:29-38): the vector that
-  // get_time_steps_vector() hands to the assembly, newest first
-  inline void
-  add_time_step(std::vector<double> &time_steps_vector, const double dt)
-  {
-    for (size_t i = time_steps_vector.size() - 1; i > 0; --i)
-      time_steps_vector[i] = time_steps_vector[i - 1];
-    time_steps_vector[0] = dt;
-  }
-
-  // NavierStokesBase::iterate (navier_stokes_base.cc:461-505): the SDIRK stages of one time step
-  // (stage results become solution_m2 / solution_m3), or one solve for steady / BDF
-  template <class Solver>
-  void
-  iterate(Solver &s, const TimeSteppingMethod method)
-  {
-    if (method == TimeSteppingMethod::sdirk2)
-      {
-        s.solve_non_linear_system(TimeSteppingMethod::sdirk2_1, false, false);
-        s.solution_m2 = s.present_solution;
-        s.solve_non_linear_system(TimeSteppingMethod::sdirk2_2, false, false);
-      }
-    else if (method == TimeSteppingMethod::sdirk3)
-      {
-        s.solve_non_linear_system(TimeSteppingMethod::sdirk3_1, false, false);
-        s.solution_m2 = s.present_solution;
-        s.solve_non_linear_system(TimeSteppingMethod::sdirk3_2, false, false);
-        s.solution_m3 = s.present_solution;
-        s.solve_non_linear_system(TimeSteppingMethod::sdirk3_3, false, false);
-      }
-    else
-      s.solve_non_linear_system(method, false, false);
-  }
-
-  // NavierStokesBase::first_iteration (navier_stokes_base.cc:511-590): BDF2 / BDF3 start with
-  // Euler steps of dt * startup_timestep_scaling (`startup time scaling`, default 0.4) and finish
-  // the step with the rest; `dt` has already been added to time_steps_vector by integrate().
-  template <class Solver>
-  void
-  first_iteration(Solver &s, const TimeSteppingMethod method, const double dt,
-                  const double startup_timestep_scaling)
-  {
-    if (!is_bdf(method) || method == TimeSteppingMethod::bdf1)
-      iterate(s, method);
-    else if (method == TimeSteppingMethod::bdf2)
-      {
-        add_time_step(s.time_steps_vector, dt * startup_timestep_scaling);
-        s.solve_non_linear_system(TimeSteppingMethod::bdf1, false, true);
-        s.solution_m2 = s.solution_m1;
-        s.solution_m1 = s.present_solution;
-        add_time_step(s.time_steps_vector, dt * (1. - startup_timestep_scaling));
-        s.solve_non_linear_system(TimeSteppingMethod::bdf2, false, true);
-      }
-    else // bdf3
-      {
-        const double time_step = dt * startup_timestep_scaling;
-        add_time_step(s.time_steps_vector, time_step);
-        s.solve_non_linear_system(TimeSteppingMethod::bdf1, false, true);
-        s.solution_m2 = s.solution_m1;
-        s.solution_m1 = s.present_solution;
-        add_time_step(s.time_steps_vector, time_step);
-        s.solve_non_linear_system(TimeSteppingMethod::bdf1, false, true);
-        s.solution_m3 = s.solution_m2;
-        s.solution_m2 = s.solution_m1;
-        s.solution_m1 = s.present_solution;
-        add_time_step(s.time_steps_vector, dt * (1. - 2. * startup_timestep_scaling));
-        s.solve_non_linear_system(TimeSteppingMethod::bdf3, false, true);
-      }
-  }
-
-  // NavierStokesBase::finish_time_step (navier_stokes_base.cc:428-442), the vectors (the CFL number
-  // of the new solution is GLSNavierStokesSolver::calculate_CFL; checkpoints stay with the host)
-  template <class Solver>
-  void
-  finish_time_step(Solver &s, const TimeSteppingMethod method)
-  {
-    if (method != TimeSteppingMethod::steady)
-      {
-        s.solution_m3 = s.solution_m2;
-        s.solution_m2 = s.solution_m1;
-        s.solution_m1 = s.present_solution;
-      }
   }
 
   // ------------------------------------------------------------------------------------------
@@ -756,7 +537,7 @@ namespace glsns
     GLSNavierStokesSolver(const NavierStokesSolverParameters &nsparam, const glsns_fe_desc &fe,
                           const glsns_mesh_desc &mesh, const double *forcing_at_q = nullptr,
                           int cuda_device = 0)
-      : PhysicsSolver<Vector>(nsparam.non_linear_solver)
+      : PhysicsSolver<Vector>(nullptr)
       , nsparam(nsparam)
       , n_dofs(mesh.n_dofs)
       , n_owned(mesh.n_owned)

@@ -386,6 +386,227 @@ cell_literal(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
     }
 }
 
+/* ---- structured cell kernel ("Mode B" of BASELINE.md section 3) ------------------
+ * The same local matrix and right-hand side as cell_literal, computed the way a tuned CPU
+ * code would: every velocity shape function is N_a e_c, so the n x n matrix is a
+ * (dim+1) x (dim+1) grid of scalar n_s x n_s blocks built from the per-point features
+ * {N, grad N, lap N, u.grad N} (derived from
+ * source/solvers/gls_navier_stokes.cc:525-606, :628-748).  About ten times fewer flops than
+ * the literal q x j x i loop.  Not the reference's arithmetic order: it is the honest
+ * best-CPU baseline of bench.py, and tests/test_oracle_golden.py checks it against
+ * cell_literal to rounding.  Needs n_su == n_sp or not: pressure has its own tables. */
+static void
+cell_structured(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
+                int64_t cell, const double *U, const double *U1, const double *U2,
+                const double *U3, int assemble_matrix, double *M, double *b,
+                double *scratch)
+{
+  const int dim = fe->dim, n_su = fe->n_su, n_sp = fe->n_sp, nq = fe->nq;
+  const int n   = dim * n_su + n_sp;
+  const int32_t *dofs = cs->cell_dofs + cell * n;
+  const double  *iJ   = cs->cell_invJ + cell * dim * dim;
+  const double   nu   = pr->viscosity;
+  const double   c0   = pr->transient ? pr->coefs[0] : 0.0;
+  double *N   = scratch;             /* [n_su]       */
+  double *dN  = N + n_su;            /* [n_su][MAXD] */
+  double *lap = dN + n_su * MAXD;    /* [n_su]       */
+  double *adv = lap + n_su;          /* [n_su]       */
+  double *L   = adv + n_su;          /* [n_su]       */
+  double *Np  = L + n_su;            /* [n_sp]       */
+  double *dNp = Np + n_sp;           /* [n_sp][MAXD] */
+  if (assemble_matrix)
+    memset(M, 0, sizeof(double) * n * n);
+  memset(b, 0, sizeof(double) * n);
+  double h;
+  if (dim == 2)
+    h = sqrt(4. * cs->cell_measure[cell] / M_PI) / fe->vel_degree;
+  else
+    h = pow(6 * cs->cell_measure[cell] / M_PI, 1. / 3.) / fe->vel_degree;
+  double W[MAXD][MAXD] = {{0}};
+  if (pr->srf)
+    {
+      const double *om = pr->omega;
+      if (dim == 2)
+        W[0][1] = -2 * om[2], W[1][0] = 2 * om[2];
+      else
+        {
+          W[0][1] = -2 * om[2], W[0][2] = 2 * om[1], W[1][0] = 2 * om[2];
+          W[1][2] = -2 * om[0], W[2][0] = -2 * om[1], W[2][1] = 2 * om[0];
+        }
+    }
+  for (int q = 0; q < nq; ++q)
+    {
+      for (int a = 0; a < n_su; ++a)
+        {
+          const double *gr = fe->dNu + ((size_t)q * n_su + a) * dim;
+          const double *hr = fe->d2Nu + ((size_t)q * n_su + a) * dim * dim;
+          double        l  = 0;
+          for (int d = 0; d < dim; ++d)
+            {
+              double g = 0;
+              for (int r = 0; r < dim; ++r)
+                g += gr[r] * iJ[r * dim + d];
+              dN[a * MAXD + d] = g;
+              for (int r = 0; r < dim; ++r)
+                for (int t = 0; t < dim; ++t)
+                  l += hr[r * dim + t] * iJ[r * dim + d] * iJ[t * dim + d];
+            }
+          lap[a] = l;
+          N[a]   = fe->Nu[(size_t)q * n_su + a];
+        }
+      for (int a = 0; a < n_sp; ++a)
+        {
+          const double *gr = fe->dNp + ((size_t)q * n_sp + a) * dim;
+          Np[a]            = fe->Np[(size_t)q * n_sp + a];
+          for (int d = 0; d < dim; ++d)
+            {
+              double g = 0;
+              for (int r = 0; r < dim; ++r)
+                g += gr[r] * iJ[r * dim + d];
+              dNp[a * MAXD + d] = g;
+            }
+        }
+      double u[MAXD] = {0, 0, 0}, G[MAXD][MAXD] = {{0}}, lap_u[MAXD] = {0, 0, 0};
+      double p = 0, gp[MAXD] = {0, 0, 0}, udot[MAXD] = {0, 0, 0};
+      for (int c = 0; c < dim; ++c)
+        for (int a = 0; a < n_su; ++a)
+          {
+            const int32_t g = dofs[c * n_su + a];
+            const double  v = U[g];
+            u[c] += v * N[a];
+            lap_u[c] += v * lap[a];
+            for (int d = 0; d < dim; ++d)
+              G[c][d] += v * dN[a * MAXD + d];
+            if (pr->transient)
+              udot[c] += (pr->coefs[0] * v + (U1 ? pr->coefs[1] * U1[g] : 0.0) +
+                          (U2 ? pr->coefs[2] * U2[g] : 0.0) + (U3 ? pr->coefs[3] * U3[g] : 0.0)) *
+                         N[a];
+          }
+      for (int a = 0; a < n_sp; ++a)
+        {
+          const double v = U[dofs[dim * n_su + a]];
+          p += v * Np[a];
+          for (int d = 0; d < dim; ++d)
+            gp[d] += v * dNp[a * MAXD + d];
+        }
+      double unorm = 0, div_u = 0;
+      for (int c = 0; c < dim; ++c)
+        unorm += u[c] * u[c], div_u += G[c][c];
+      const double u_mag = fmax(sqrt(unorm), 1e-12);
+      const double JxW   = cs->cell_detJ[cell] * fe->wq[q];
+      const double tau =
+        !pr->transient ?
+          1. / sqrt(pow(2. * u_mag / h, 2) + 9 * pow(4 * nu / (h * h), 2)) :
+          1. / sqrt(pow(pr->sdt, 2) + pow(2. * u_mag / h, 2) + 9 * pow(4 * nu / (h * h), 2));
+      double force[MAXD] = {0, 0, 0}, R[MAXD], Gu[MAXD], body[MAXD] = {0, 0, 0};
+      if (cs->force)
+        for (int c = 0; c < dim; ++c)
+          force[c] = cs->force[((size_t)cell * nq + q) * dim + c];
+      if (pr->srf)
+        { /* Coriolis + centrifugal (:443-467) */
+          const double *x = cs->qpoints + ((size_t)cell * nq + q) * dim, *om = pr->omega;
+          double        cen[MAXD] = {0, 0, 0};
+          if (dim == 2)
+            cen[0] = -om[2] * om[2] * x[0], cen[1] = -om[2] * om[2] * x[1];
+          else
+            {
+              const double t[3] = {om[1] * x[2] - om[2] * x[1], om[2] * x[0] - om[0] * x[2],
+                                   om[0] * x[1] - om[1] * x[0]};
+              cen[0] = om[1] * t[2] - om[2] * t[1];
+              cen[1] = om[2] * t[0] - om[0] * t[2];
+              cen[2] = om[0] * t[1] - om[1] * t[0];
+            }
+          for (int c = 0; c < dim; ++c)
+            {
+              body[c] = cen[c];
+              for (int d = 0; d < dim; ++d)
+                body[c] += W[c][d] * u[d];
+            }
+        }
+      for (int c = 0; c < dim; ++c)
+        {
+          Gu[c] = 0;
+          for (int d = 0; d < dim; ++d)
+            Gu[c] += G[c][d] * u[d];
+          R[c] = Gu[c] + gp[c] - nu * lap_u[c] - force[c] + body[c] + udot[c];
+        }
+      for (int a = 0; a < n_su; ++a)
+        {
+          double s = 0;
+          for (int d = 0; d < dim; ++d)
+            s += u[d] * dN[a * MAXD + d];
+          adv[a] = s;
+          L[a]   = s - nu * lap[a] + c0 * N[a];
+        }
+      if (assemble_matrix)
+        {
+          /* velocity rows */
+          for (int a = 0; a < n_su; ++a)
+            {
+              const double Na = N[a], adva = adv[a], *ga = dN + a * MAXD;
+              for (int b2 = 0; b2 < n_su; ++b2)
+                {
+                  const double Nb = N[b2], *gb = dN + b2 * MAXD;
+                  double       gg = 0;
+                  for (int d = 0; d < dim; ++d)
+                    gg += ga[d] * gb[d];
+                  const double diag = nu * gg + adv[b2] * Na + c0 * Na * Nb + tau * L[b2] * adva;
+                  const double NN = Na * Nb, tNa = tau * Nb * adva;
+                  for (int ci = 0; ci < dim; ++ci)
+                    for (int cj = 0; cj < dim; ++cj)
+                      M[(size_t)(ci * n_su + a) * n + cj * n_su + b2] +=
+                        ((ci == cj ? diag : 0.0) + (G[ci][cj] + W[ci][cj]) * (NN + tNa) +
+                         tau * R[ci] * ga[cj] * Nb) *
+                        JxW;
+                }
+              for (int b2 = 0; b2 < n_sp; ++b2)
+                for (int ci = 0; ci < dim; ++ci)
+                  M[(size_t)(ci * n_su + a) * n + dim * n_su + b2] +=
+                    (-ga[ci] * Np[b2] + tau * dNp[b2 * MAXD + ci] * adva) * JxW;
+            }
+          /* pressure rows */
+          for (int a = 0; a < n_sp; ++a)
+            {
+              const double *ga = dNp + a * MAXD;
+              for (int b2 = 0; b2 < n_su; ++b2)
+                for (int cj = 0; cj < dim; ++cj)
+                  {
+                    double t = 0;
+                    for (int c = 0; c < dim; ++c)
+                      t += (G[c][cj] + W[c][cj]) * ga[c];
+                    M[(size_t)(dim * n_su + a) * n + cj * n_su + b2] +=
+                      (Np[a] * dN[b2 * MAXD + cj] + tau * (N[b2] * t + ga[cj] * L[b2])) * JxW;
+                  }
+              for (int b2 = 0; b2 < n_sp; ++b2)
+                {
+                  double gg = 0;
+                  for (int d = 0; d < dim; ++d)
+                    gg += ga[d] * dNp[b2 * MAXD + d];
+                  M[(size_t)(dim * n_su + a) * n + dim * n_su + b2] += tau * gg * JxW;
+                }
+            }
+        }
+      for (int a = 0; a < n_su; ++a)
+        for (int ci = 0; ci < dim; ++ci)
+          {
+            double Gg = 0;
+            for (int d = 0; d < dim; ++d)
+              Gg += G[ci][d] * dN[a * MAXD + d];
+            b[ci * n_su + a] += (-nu * Gg + p * dN[a * MAXD + ci] +
+                                 (force[ci] - Gu[ci] - udot[ci] - body[ci]) * N[a] -
+                                 tau * R[ci] * adv[a]) *
+                                JxW;
+          }
+      for (int a = 0; a < n_sp; ++a)
+        {
+          double t = 0;
+          for (int d = 0; d < dim; ++d)
+            t += R[d] * dNp[a * MAXD + d];
+          b[dim * n_su + a] += (-div_u * Np[a] - tau * t) * JxW;
+        }
+    }
+}
+
 static inline int64_t
 csr_find(const int64_t *rowptr, const int32_t *col, int32_t row, int32_t c)
 {
@@ -431,6 +652,25 @@ scatter_cell(int n, const int32_t *dofs, const uint8_t *constrained,
     }
 }
 
+/* 0: the reference-faithful literal loop (default, what every parity test uses);
+ * 1: the structured form (bench.py's "Mode B" CPU figure only) */
+static int glso_cell_mode = 0;
+void
+glso_set_cell_mode(int structured)
+{
+  glso_cell_mode = structured ? 1 : 0;
+}
+static void
+cell_kernel(const glso_fe *fe, const glso_cells *cs, const glso_params *pr, int64_t cell,
+            const double *U, const double *U1, const double *U2, const double *U3,
+            int assemble_matrix, double *M, double *b, double *scratch)
+{
+  if (glso_cell_mode)
+    cell_structured(fe, cs, pr, cell, U, U1, U2, U3, assemble_matrix, M, b, scratch);
+  else
+    cell_literal(fe, cs, pr, cell, U, U1, U2, U3, assemble_matrix, M, b, scratch);
+}
+
 static size_t
 scratch_doubles(int n)
 {
@@ -457,7 +697,7 @@ glso_assemble(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
   memset(rhs, 0, sizeof(double) * ndof);           /* :239 */
   for (int64_t c = 0; c < cs->ncell; ++c)
     {
-      cell_literal(fe, cs, pr, c, U, U1, U2, U3, assemble_matrix, M, b, s);
+      cell_kernel(fe, cs, pr, c, U, U1, U2, U3, assemble_matrix, M, b, s);
       if (localM_out && assemble_matrix)
         memcpy(localM_out + (size_t)c * n * n, M, sizeof(double) * n * n);
       if (localb_out)
@@ -503,7 +743,7 @@ glso_assemble_mt(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
         for (int32_t t = color_ptr[col_i]; t < color_ptr[col_i + 1]; ++t)
           {
             const int64_t c = color_cells[t];
-            cell_literal(fe, cs, pr, c, U, U1, U2, U3, assemble_matrix, M, b, s);
+            cell_kernel(fe, cs, pr, c, U, U1, U2, U3, assemble_matrix, M, b, s);
             scatter_cell(n, cs->cell_dofs + c * n, constrained, rowptr, col,
                          assemble_matrix, M, b, val, rhs);
           }

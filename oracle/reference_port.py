@@ -491,9 +491,19 @@ def scheme_params(scheme, dts, viscosity, srf=False, omega=(0.0, 0.0, 0.0)):
 # hot path wrappers
 # ----------------------------------------------------------------------------------------------
 def assemble(mesh, U, params, assemble_matrix=True, force=None, U1=None, U2=None, U3=None,
-             return_local=False, threads=1):
-    """assembleGLS. Returns (val or None, rhs[, localM, localb])."""
+             return_local=False, threads=1, structured=False):
+    """assembleGLS. Returns (val or None, rhs[, localM, localb]).  structured=True: the same cell
+    matrices from the structured block form (gls_oracle.c: cell_structured, bench.py's best-CPU
+    figure), not the reference's literal loop."""
     L = lib()
+    L.glso_set_cell_mode(C.c_int(1 if structured else 0))
+    try:
+        return _assemble(L, mesh, U, params, assemble_matrix, force, U1, U2, U3, return_local, threads)
+    finally:
+        L.glso_set_cell_mode(C.c_int(0))
+
+
+def _assemble(L, mesh, U, params, assemble_matrix, force, U1, U2, U3, return_local, threads):
     fe_s, cs = mesh.fe.cstruct(), mesh.cells_struct(force)
     N, n = mesh.ndof, mesh.fe.n
     nnz = int(mesh.rowptr[-1])

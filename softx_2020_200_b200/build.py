@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libglsns.so")
-SOURCES = ["api.cu", "assembly.cu", "sparse.cu", "trsv.cu", "krylov.cu", "comm.cu", "host_mesh.cpp", "host_solver.cpp"]
+SOURCES = ["api.cu", "assembly.cu", "sparse.cu", "trsv.cu", "krylov.cu", "comm.cu", "host_mesh.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-fopenmp,-O3", "-ccbin", "/usr/bin/g++"] + \

@@ -1,10 +1,12 @@
-// Compiled front end of the host-side mirror (include/glsns_solver.hpp) for tests and benchmarks:
+// TEST HARNESS (tests/mirror/libglsns_mirror.so), not part of libglsns.so.
+// Compiled front end of the host-side mirror (include/glsns_solver.hpp) driven by the transcribed
+// reference drivers (reference_drivers.hpp), for the tests:
 //   * the reference's fake physics backend (tests/core/non_linear_test_system_01.h:50-129: the 2x2
 //     system x0^2 + x1 = 0, 2 x1 + 3 = 0) plugged into the mirrored Newton drivers — host only;
 //   * GLSNavierStokesSolver over the C ABI, built from a glsnsh_mesh and a .prm text.
 #include <sstream>
 
-#include "../../include/glsns_solver.hpp"
+#include "reference_drivers.hpp"
 
 extern "C" {
 typedef struct glsnsh_mesh glsnsh_mesh;
@@ -18,8 +20,9 @@ namespace
   {
   public:
     explicit TestClass(const glsns::Parameters::NonLinearSolver &params)
-      : PhysicsSolver(params)
+      : PhysicsSolver(nullptr)
     {
+      non_linear_solver = glsns::make_non_linear_solver<glsns::Vector>(this, params);
       evaluation_point.reinit(2), system_rhs.reinit(2), local_evaluation_point.reinit(2);
       present_solution.reinit(2), newton_update.reinit(2);
       present_solution[0] = 1, present_solution[1] = 0;
@@ -165,6 +168,8 @@ glsnsh_solver_create(const glsnsh_mesh *mesh, const char *prm_text, const double
       glsns_mesh_desc md;
       glsnsh_mesh_fill_desc(mesh, &fe, &md);
       h->solver = new glsns::GLSNavierStokesSolver(p, fe, md, forcing_at_q, cuda_device);
+      h->solver->non_linear_solver =
+        glsns::make_non_linear_solver<glsns::Vector>(h->solver, p.non_linear_solver);
       h->solver->pcout.set_stream(h->log);
     }
   catch (const std::exception &e)

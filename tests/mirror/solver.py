@@ -1,13 +1,25 @@
-"""Python proxy of the C++ host-side mirror (include/glsns_solver.hpp, csrc/host_solver.cpp):
-glsns::GLSNavierStokesSolver driven by the mirrored NewtonNonLinearSolver /
-SkipNewtonNonLinearSolver through host buffers, exactly as the reference's Newton drivers move
-their vectors (include/core/newton_non_linear_solver.h:76-139)."""
+"""TEST HARNESS. Python proxy of the product's host-side solver class (include/glsns_solver.hpp)
+driven by the transcribed reference drivers (tests/mirror/reference_drivers.hpp: Newton /
+SkipNewton, NavierStokesBase's time-stepping glue) through host buffers, exactly as the
+reference's Newton drivers move their vectors (include/core/newton_non_linear_solver.h:76-139)."""
 import ctypes as C
 
 import numpy as np
 
-from . import _lib
-from .hotpath import GlsnsError, NoConvergence
+from softx_2020_200_b200 import _lib
+from softx_2020_200_b200.hotpath import GlsnsError, NoConvergence
+
+_MIRROR = None
+
+
+def mirror_lib():
+    """tests/mirror/libglsns_mirror.so (built on demand; it links against libglsns.so)."""
+    global _MIRROR
+    if _MIRROR is None:
+        from . import build
+        _lib.lib()                      # the product library first (no CPU fallback: raises if missing)
+        _MIRROR = C.CDLL(build.build())
+    return _MIRROR
 
 METHODS = _lib.SCHEMES  # Parameters::SimulationControl::TimeSteppingMethod, same order
 
@@ -48,7 +60,7 @@ class GLSNavierStokesSolver:
     subsections of the hot path are read); forcing_at_q: [n_cells, n_q, dim] or None."""
 
     def __init__(self, mesh, prm="", forcing_at_q=None, device=0):
-        self._L = _lib.lib()
+        self._L = mirror_lib()
         _bind(self._L)
         self.mesh = mesh
         f = None if forcing_at_q is None else np.ascontiguousarray(forcing_at_q, dtype=np.float64)

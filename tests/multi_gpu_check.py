@@ -11,15 +11,13 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def main():
+def check(n, world, rank, local, dist, verbose=True):
+    """One Newton iteration of the 3D Q2-Q2 cavity at n cells per direction on `world` ranks (the
+    process group `dist` is up, the CUDA device is set) against the oracle with the same row
+    blocks.  Returns the parity record (identical on every rank)."""
     from oracle import reference_port as R
     from softx_2020_200_b200 import GLSHotPath
     from softx_2020_200_b200.mesh import BoxMesh
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     bcs = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (4, "noslip"), (5, "noslip"),
            (3, "function", (1.0, 0.0, 0.0))]
     g = BoxMesh(3, n, 2, 2, bcs=bcs)
@@ -67,7 +65,7 @@ def main():
     # ghost values of the updated evaluation point must equal their owners' values
     ev_glob = np.concatenate(ev_owned)
     assert np.array_equal(ev, ev_glob[l2g]), "halo exchange mismatch on rank %d" % rank
-    ok = True
+    ok, err_a, err_b, err_x, its_ref = True, 0.0, 0.0, 0.0, 0
     if rank == 0:
         R.lib().glso_set_num_threads(1)
         lid = lambda x: np.stack([np.ones(len(x)), 0 * x[:, 0], 0 * x[:, 0]], axis=1)
@@ -103,14 +101,31 @@ def main():
                  np.linalg.norm(b_ref), res1))
         ok = err_a <= 1e-12 and err_b <= 1e-12 and abs(info["iterations"] - its_ref) <= 2 and \
             err_x <= 1e-5 and abs(norm - np.linalg.norm(b_ref)) <= 1e-12 * norm
-    flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, 0)
+    rec = torch.zeros(6, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        rec = torch.tensor([1.0 if ok else 0.0, info["iterations"], its_ref, err_x, err_a, err_b],
+                           dtype=torch.float64, device="cuda")
+    dist.broadcast(rec, 0)
     hp.close()
+    g.close()
+    r = rec.cpu().numpy()
+    return {"ok": bool(r[0]), "cells_per_dir": n, "n_ranks": world, "iterations": int(r[1]),
+            "oracle_iterations": int(r[2]), "update_err": float(r[3]), "matrix_err": float(r[4]),
+            "rhs_err": float(r[5]), "oracle": "block-Jacobi ILU with the ranks' row blocks"}
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    rec = check(n, world, rank, local, dist)
     dist.destroy_process_group()
-    if not flag.item():
+    if not rec["ok"]:
         sys.exit(1)
     if rank == 0:
-        print("MULTI_GPU_CHECK_OK")
+        print("MULTI_GPU_CHECK_OK", rec)
 
 
 if __name__ == "__main__":

@@ -185,7 +185,7 @@ def test_mms2d_gls_prm_with_its_shipped_ilu_fill(oracle):
     fill = 4` (:84); its output table (mms2d_gls.output:24-26) through the mirrored C++ interface
     with that setting: 256 cells -> velocity L2 error 3.4363e-02."""
     from softx_2020_200_b200.mesh import BoxMesh
-    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.mirror.solver import GLSNavierStokesSolver
     from tests.test_host_mirror import _match_numbering
     mesh = BoxMesh(2, 16, 1, 1, with_q_points=True)
     force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)
@@ -306,7 +306,7 @@ def test_bicgstab_through_the_cpp_mirror(oracle):
     same discrete solution as with GMRES (restart_01's problem: velocity L2 error 0.0343628)."""
     import re
     from softx_2020_200_b200.mesh import BoxMesh
-    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.mirror.solver import GLSNavierStokesSolver
     from tests.test_host_mirror import _match_numbering
     mesh = BoxMesh(2, 16, 1, 1, with_q_points=True)
     force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)
@@ -363,7 +363,7 @@ def test_l2_projection_initial_condition_through_the_cpp_mirror(oracle):
     Taylor-Green field of applications_tests/.../taylor-green-vortex_gls_*.prm's initial condition
     (u = cos x sin y, v = -sin x cos y) on a periodic-free box, against the oracle."""
     from softx_2020_200_b200.mesh import BoxMesh
-    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.mirror.solver import GLSNavierStokesSolver
     from tests.test_host_mirror import _match_numbering
 
     def tg(x):
@@ -426,7 +426,7 @@ def test_example_01_cavity_prm_as_shipped(oracle, nu, n):
     counts within +-2, same discrete solution."""
     import re
     from softx_2020_200_b200.mesh import BoxMesh
-    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.mirror.solver import GLSNavierStokesSolver
     from tests.test_host_mirror import _match_numbering
     bcs = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (3, "function", (1.0, 0.0))]
     mesh = BoxMesh(2, n, 1, 1, bcs=bcs)
@@ -457,7 +457,7 @@ def test_set_initial_condition_viscous_and_nodal_through_the_cpp_mirror(oracle):
     restored afterwards) and `nodal` (set_nodal_values, navier_stokes_base.cc:926-944) on the 2D
     cavity, against the oracle's Newton solves."""
     from softx_2020_200_b200.mesh import BoxMesh
-    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.mirror.solver import GLSNavierStokesSolver
     from tests.test_host_mirror import _match_numbering
     n, nu, nu_ic = 16, 0.02, 1.0
     bcs = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (3, "function", (1.0, 0.0))]
@@ -541,8 +541,6 @@ def test_taylor_green_vortex_bdf1_golden_on_gpu(oracle):
     hp.close()
 
 
-@pytest.mark.skipif(not os.environ.get("GLSNS_UNVALIDATED_TESTS"),
-                    reason="written after the round's GPU budget was spent: run once, then enable")
 def test_taylor_green_vortex_sdirk3_through_the_cpp_mirror(oracle):
     """taylor-green-vortex_gls_sdirk3.prm end to end through the product's own host side: periodic
     C++ BoxMesh, GLSNavierStokesSolver with the file's solver subsections, set_initial_condition
@@ -550,7 +548,7 @@ def test_taylor_green_vortex_sdirk3_through_the_cpp_mirror(oracle):
     energy and velocity L2 error against taylor-green-vortex_gls_sdirk3.mpirun=2.output."""
     import json
     from softx_2020_200_b200.mesh import BoxMesh
-    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.mirror.solver import GLSNavierStokesSolver
     from tests.test_host_mirror import _match_numbering
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
                            "reference_golden.json")) as f:
@@ -621,7 +619,7 @@ def test_restart_01_through_the_cpp_mirror(oracle):
     vectors in and out; the log lines of solve_system_GMRES carry the golden iteration counts."""
     import re
     from softx_2020_200_b200.mesh import BoxMesh
-    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.mirror.solver import GLSNavierStokesSolver
     from tests.test_host_mirror import _match_numbering
     mesh = BoxMesh(2, 16, 1, 1, with_q_points=True)
     force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)
@@ -643,7 +641,7 @@ def test_cpp_mirror_error_behaviour():
     SolverControl::NoConvergence when max iters is hit."""
     from softx_2020_200_b200 import NoConvergence
     from softx_2020_200_b200.mesh import BoxMesh
-    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.mirror.solver import GLSNavierStokesSolver
     mesh = BoxMesh(2, 8, 1, 1, with_q_points=True)
     force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)
     s = GLSNavierStokesSolver(mesh, "subsection linear solver\n set method = amg\nend\n", force)
@@ -663,7 +661,7 @@ def test_skip_newton_and_transient_through_the_cpp_mirror(oracle):
     """skip_newton reuses Jacobian + ILU (renewed_matrix=false path, gls_navier_stokes.cc:1270);
     one bdf1 step of the MMS problem matches the oracle's Newton solve of the same step."""
     from softx_2020_200_b200.mesh import BoxMesh
-    from softx_2020_200_b200.solver import GLSNavierStokesSolver
+    from tests.mirror.solver import GLSNavierStokesSolver
     from tests.test_host_mirror import _match_numbering
     mesh = BoxMesh(2, 8, 2, 1, with_q_points=True)
     force = mms.forcing_2d(mesh.array("q_points").reshape(-1, 2)).reshape(mesh.n_cells, mesh.n_q, 2)

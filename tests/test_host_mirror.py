@@ -1,5 +1,6 @@
 """Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
-the C++ mirror of the reference's Newton drivers reproduces the reference's fake-backend tests, the
+the transcribed reference Newton drivers (tests/mirror, a test harness) reproduce the reference's
+fake-backend tests on the product's PhysicsSolver interface, the
 .prm reader honours the reference's option names and defaults, and the C++ box-mesh stand-in
 produces exactly the arrays of the oracle's deal.II restatement."""
 import ctypes as C
@@ -38,8 +39,8 @@ def test_no_cpu_fallback_without_a_device():
 def test_newton_drivers_on_the_reference_fake_backend(skip, skip_iterations):
     """tests/core/newton_non_linear_solver_01.output and skip_newton_non_linear_solver_01.output:
     'The final solution is : 1.22474 -1.50000' for x0^2+x1=0, 2x1+3=0 from (1,0)."""
-    from softx_2020_200_b200 import _lib
-    L = _lib.lib()
+    from tests.mirror.solver import mirror_lib
+    L = mirror_lib()
     x = (C.c_double * 2)()
     n_matrix = L.glsnsh_newton_toy(skip, skip_iterations, x)
     assert "%.5f %.5f" % (x[0], x[1]) == "1.22474 -1.50000"
@@ -48,8 +49,8 @@ def test_newton_drivers_on_the_reference_fake_backend(skip, skip_iterations):
 
 
 def _parse(text):
-    from softx_2020_200_b200 import _lib
-    L = _lib.lib()
+    from tests.mirror.solver import mirror_lib
+    L = mirror_lib()
     out = (C.c_double * 18)()
     err = C.create_string_buffer(256)
     rc = L.glsnsh_parse_prm(text.encode(), out, err, 256)
@@ -261,7 +262,8 @@ def test_level_of_fill_pattern_equals_the_oracle(oracle, dim, n, pu, pp, fill):
 
 def _time_stepping(method, n_steps, dt=0.1, scaling=0.4):
     from softx_2020_200_b200 import _lib
-    L = _lib.lib()
+    from tests.mirror.solver import mirror_lib
+    L = mirror_lib()
     L.glsnsh_time_stepping_trace.restype = C.c_int
     L.glsnsh_time_stepping_trace.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double,
                                              C.POINTER(C.c_double), C.c_int]

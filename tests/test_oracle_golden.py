@@ -277,3 +277,24 @@ def test_poiseuille_gls_output(oracle):
         eu, ep = oracle.l2_error(mesh, U, exact)
         assert "%.4e" % eu == g["error_velocity"][k]
         assert ep < 1e-6
+
+
+@pytest.mark.parametrize("dim,n,pu,pp,scheme,srf", [
+    (2, 3, 1, 1, "steady", False), (2, 3, 2, 1, "bdf2", False), (3, 2, 2, 2, "steady", False),
+    (3, 2, 2, 2, "sdirk3_2", True), (2, 3, 2, 2, "bdf1", True), (3, 2, 1, 1, "bdf3", False)])
+def test_structured_cell_kernel_equals_the_literal_loop(oracle, dim, n, pu, pp, scheme, srf):
+    """the structured block form of the local matrix (cell_structured, the
+    "Mode B" CPU baseline of bench.py and the form the CUDA kernel computes) against the literal
+    q x j x i loop of gls_navier_stokes.cc:387-748 on random states, entry by entry."""
+    from tests import mms
+    mesh = oracle.BoxMesh(dim, n, pu, pp)
+    rng = np.random.default_rng(5)
+    U, U1, U2, U3 = (rng.uniform(-1, 1, mesh.ndof) for _ in range(4))
+    force = mesh.evaluate_force(mms.forcing_2d if dim == 2 else mms.forcing_3d)
+    pr = oracle.scheme_params(scheme, None if scheme == "steady" else [0.1, 0.2, 0.3], 0.05, srf,
+                              (0.3, -0.4, 1.1))
+    _, _, m_lit, b_lit = oracle.assemble(mesh, U, pr, True, force, U1, U2, U3, return_local=True)
+    _, _, m_str, b_str = oracle.assemble(mesh, U, pr, True, force, U1, U2, U3, return_local=True,
+                                         structured=True)
+    assert np.max(np.abs(m_str - m_lit)) <= 1e-13 * np.max(np.abs(m_lit))
+    assert np.max(np.abs(b_str - b_lit)) <= 1e-13 * np.max(np.abs(b_lit))
