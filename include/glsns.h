@@ -124,8 +124,13 @@ typedef struct
                                     assembled redundantly; only owned rows are
                                     written, so no compress(add) exchange)      */
   const int32_t *cell_dofs;      /* [n_cells][n] local dof indices              */
-  /* geometry.  geometry_per_q = 0: affine cells, one inverse Jacobian and one
-     determinant per cell.  geometry_per_q = 1: per (cell,q) entries (MappingQ). */
+  /* geometry.  geometry_per_q = 0: affine cells (parallelograms / parallelepipeds), one
+     inverse Jacobian and one determinant per cell.  geometry_per_q = 1: per (cell,q)
+     entries (MappingQ, `qmapping all`, or Q1 mapping of a non-parallelogram cell); then
+     mapping_laplacian (below) is REQUIRED: without it the real-space Laplacians of the
+     shape functions that FEValues delivers with update_hessians
+     (gls_navier_stokes.cc:417-422) cannot be formed, and glsns_set_mesh returns
+     GLSNS_ERR_UNSUPPORTED rather than assemble wrong strong residuals. */
   int32_t        geometry_per_q;
   const double  *inv_jacobian;   /* [n_cells]([n_q])[dim][dim], [r][d]=dxi_r/dx_d */
   const double  *det_jacobian;   /* [n_cells]([n_q]); JxW = det * weight        */
@@ -153,6 +158,15 @@ typedef struct
   const int32_t *send_idx;       /* owned local indices to send                 */
   const int64_t *recv_ptr;       /* [n_neighbors+1]; ghosts of neighbour i are
                                     n_owned+recv_ptr[i] .. n_owned+recv_ptr[i+1] */
+  /* geometry_per_q = 1 only: [n_cells][n_q][dim], the mapping's second derivatives
+     contracted with the metric,
+        c_k = sum_{r,s} d2x_k/dxi_r dxi_s (J^-1 J^-T)_{rs}
+     (from fe_values.jacobian_grad(q) and inverse_jacobian(q), update_jacobian_grads).
+     The real-space Laplacian of a shape function is then
+        lap N = H_ref(N) : (J^-1 J^-T) - grad_x N . c
+     which is what trace(fe_values[velocities].hessian(k, q)) is on a curved cell.
+     NULL when geometry_per_q = 0. */
+  const double  *mapping_laplacian;
 } glsns_mesh_desc;
 
 /* `linear solver` subsection (source/core/parameters.cc:507-559). */

@@ -55,6 +55,13 @@ typedef struct
   const double  *cell_measure; /* [ncell]                                          */
   const double  *qpoints;      /* [ncell][nq][dim] or NULL (needed for SRF only)  */
   const double  *force;        /* [ncell][nq][dim] or NULL (NoForce)              */
+  /* MappingQ on curved cells (`qmapping all`, gls_navier_stokes.cc:244-252): cell_invJ and
+     cell_detJ are then per (cell, q), and map_lap [ncell][nq][dim] holds
+     c_k = sum_rs d2x_k/dxi_r dxi_s (J^-1 J^-T)_rs, the part of the real-space Hessian trace that
+     comes from the mapping:  lap N = H_ref(N) : (J^-1 J^-T) - grad_x N . c  (what FEValues
+     delivers with update_hessians, :417-422) */
+  int            geometry_per_q;
+  const double  *map_lap;
 } glso_cells;
 
 typedef struct
@@ -89,6 +96,7 @@ cell_literal(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
   const int32_t *dofs = cs->cell_dofs + cell * n;
   const double  *iJ   = cs->cell_invJ + cell * dim * dim;
   const double   nu   = pr->viscosity;
+  const double   zero3[MAXD] = {0, 0, 0};
 
   /* per-dof shape data at one q point (:282-288) */
   double *phi_u      = scratch;               /* [n][MAXD]       */
@@ -112,7 +120,14 @@ cell_literal(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
   for (int q = 0; q < nq; ++q)
     {
       /* :412-423 shape functions in real space (affine cell: grad = invJ^T grad_ref,
-         hessian = invJ^T H_ref invJ; what FEValues::reinit does on such a cell) */
+         hessian = invJ^T H_ref invJ; what FEValues::reinit does on such a cell; on a curved
+         cell the mapping's second derivatives add -grad . c to the Hessian trace) */
+      const double *mlap = zero3;
+      if (cs->geometry_per_q)
+        {
+          iJ   = cs->cell_invJ + ((size_t)cell * nq + q) * dim * dim;
+          mlap = cs->map_lap + ((size_t)cell * nq + q) * dim;
+        }
       memset(phi_u, 0, sizeof(double) * n * (MAXD + 9 + MAXD + 1 + 1 + MAXD));
       for (int c = 0; c < dim; ++c)
         for (int a = 0; a < n_su; ++a)
@@ -128,6 +143,8 @@ cell_literal(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
               for (int r = 0; r < dim; ++r)
                 for (int s = 0; s < dim; ++s)
                   lap += hr[r * dim + s] * iJ[r * dim + d] * iJ[s * dim + d];
+            for (int d = 0; d < dim; ++d)
+              lap -= g[d] * mlap[d];
             phi_u[k * MAXD + c] = fe->Nu[(size_t)q * n_su + a];
             for (int d = 0; d < dim; ++d)
               grad_phi_u[k * 9 + c * MAXD + d] = g[d];
@@ -181,7 +198,8 @@ cell_literal(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
       for (int c = 0; c < dim; ++c)
         unorm += u[c] * u[c];
       const double u_mag = fmax(sqrt(unorm), 1e-12 * 1.0 /*GLS_u_scale*/);
-      const double JxW   = cs->cell_detJ[cell] * fe->wq[q];
+      const double JxW =
+        cs->cell_detJ[cs->geometry_per_q ? (size_t)cell * nq + q : (size_t)cell] * fe->wq[q];
       const double tau =
         !pr->transient ?
           1. / sqrt(pow(2. * u_mag / h, 2) + 9 * pow(4 * nu / (h * h), 2)) :
@@ -434,8 +452,15 @@ cell_structured(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
           W[1][2] = -2 * om[0], W[2][0] = -2 * om[1], W[2][1] = 2 * om[0];
         }
     }
+  const double zero3[MAXD] = {0, 0, 0};
   for (int q = 0; q < nq; ++q)
     {
+      const double *mlap = zero3;
+      if (cs->geometry_per_q)
+        {
+          iJ   = cs->cell_invJ + ((size_t)cell * nq + q) * dim * dim;
+          mlap = cs->map_lap + ((size_t)cell * nq + q) * dim;
+        }
       for (int a = 0; a < n_su; ++a)
         {
           const double *gr = fe->dNu + ((size_t)q * n_su + a) * dim;
@@ -450,6 +475,7 @@ cell_structured(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
               for (int r = 0; r < dim; ++r)
                 for (int t = 0; t < dim; ++t)
                   l += hr[r * dim + t] * iJ[r * dim + d] * iJ[t * dim + d];
+              l -= g * mlap[d];
             }
           lap[a] = l;
           N[a]   = fe->Nu[(size_t)q * n_su + a];
@@ -493,7 +519,8 @@ cell_structured(const glso_fe *fe, const glso_cells *cs, const glso_params *pr,
       for (int c = 0; c < dim; ++c)
         unorm += u[c] * u[c], div_u += G[c][c];
       const double u_mag = fmax(sqrt(unorm), 1e-12);
-      const double JxW   = cs->cell_detJ[cell] * fe->wq[q];
+      const double JxW =
+        cs->cell_detJ[cs->geometry_per_q ? (size_t)cell * nq + q : (size_t)cell] * fe->wq[q];
       const double tau =
         !pr->transient ?
           1. / sqrt(pow(2. * u_mag / h, 2) + 9 * pow(4 * nu / (h * h), 2)) :

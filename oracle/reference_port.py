@@ -63,7 +63,8 @@ class _FE(C.Structure):
 class _Cells(C.Structure):
     _fields_ = [("ncell", C.c_int64), ("cell_dofs", c_i32_p), ("cell_invJ", c_double_p),
                 ("cell_detJ", c_double_p), ("cell_measure", c_double_p),
-                ("qpoints", c_double_p), ("force", c_double_p)]
+                ("qpoints", c_double_p), ("force", c_double_p),
+                ("geometry_per_q", C.c_int), ("map_lap", c_double_p)]
 
 
 class _Params(C.Structure):
@@ -217,7 +218,12 @@ class BoxMesh:
     """
 
     def __init__(self, dim, n, pu, pp, lo=-1.0, hi=1.0, bcs=None, renumber="cm", nq1=None,
-                 periodic=()):
+                 periodic=(), mapping=None):
+        """mapping: callable(param[:, dim]) -> x[:, dim].  The box is then the PARAMETER domain of a
+        curved mesh whose cells carry MappingQ(pu) geometry on all cells (`qmapping all = true`,
+        gls_navier_stokes.cc:244-252): the geometry nodes are the images of the velocity nodes
+        (where a manifold puts MappingQ's support points), Jacobians, determinants and the
+        mapping's second derivatives are per quadrature point."""
         assert pu % pp == 0
         self.dim, self.ncd, self.pu, self.pp = dim, n, pu, pp
         # per-direction cell counts and extents (scalars = the same in every direction:
@@ -285,6 +291,9 @@ class BoxMesh:
         comp[self.p_dof[has_p]] = dim
         dof_node[self.p_dof[has_p]] = np.arange(nnode)[has_p]
         coords = lov + self.node_idx * (hxv / pu)
+        self.mapping = mapping
+        if mapping is not None:
+            coords = np.asarray(mapping(coords), dtype=np.float64)
         # constraints
         constrained = np.zeros(self.ndof, dtype=np.uint8)
         cvalue = np.zeros(self.ndof)
@@ -334,6 +343,19 @@ class BoxMesh:
         self.cell_measure = np.full(self.ncell, vol)
         self.qpoints = np.ascontiguousarray(
             lov + (cidx[:, None, :] + fe.xq[None, :, :]) * hxv)             # [ncell, nq, dim]
+        self.geometry_per_q, self.map_lap = False, None
+        if mapping is not None:
+            assert dim == 2, "curved meshes: 2D only (cell->measure() of a 3D cell is not restated)"
+            self.cell_X = coords[un]                                        # [ncell, ns, dim] geometry nodes
+            g = self.mapped_geometry(fe)
+            self.cell_invJ, self.cell_detJ, self.qpoints, self.map_lap = g
+            self.geometry_per_q = True
+            # cell->measure(): the straight-sided quadrilateral through the four vertices
+            n1 = pu + 1
+            corner = [0, pu, n1 * n1 - 1, n1 * pu]                           # counter-clockwise
+            P = self.cell_X[:, corner, :]
+            x, y = P[:, :, 0], P[:, :, 1]
+            self.cell_measure = 0.5 * np.abs((x * np.roll(y, -1, axis=1) - np.roll(x, -1, axis=1) * y).sum(axis=1))
         # colours: no two cells of a colour share a dof.  Parity per direction; across a periodic
         # wrap with an odd cell count the last cell of the direction takes a third colour.
         per_dir = cidx % 2
@@ -344,6 +366,22 @@ class BoxMesh:
                 radix = 3
         self.cell_color = (per_dir * (radix ** np.arange(dim))).sum(axis=1).astype(np.int32)
         self.rowptr, self.col = self._sparsity()
+
+    def mapped_geometry(self, fe):
+        """MappingQ(pu) at the quadrature points of `fe` (tables of the same FE_Q(pu) basis):
+        inverse Jacobians [ncell, nq, dim, dim] (invJ[r][d] = d xi_r / d x_d), determinants,
+        real-space points, and c_k = sum_rs d2x_k/dxi_r dxi_s (J^-1 J^-T)_rs."""
+        X = self.cell_X
+        J = np.einsum("cak,qar->cqkr", X, fe.dNu)               # J[k][r] = d x_k / d xi_r
+        H = np.einsum("cak,qars->cqkrs", X, fe.d2Nu)
+        K = np.linalg.inv(J)                                    # K[r][d]
+        det = np.linalg.det(J)
+        assert np.all(det > 0), "negatively oriented cells"
+        KKt = np.einsum("cqrd,cqsd->cqrs", K, K)
+        c = np.einsum("cqkrs,cqrs->cqk", H, KKt)
+        xq = np.einsum("cak,qa->cqk", X, fe.Nu)
+        return (np.ascontiguousarray(K), np.ascontiguousarray(det), np.ascontiguousarray(xq),
+                np.ascontiguousarray(c))
 
     def _cuthill_mckee(self, cell_dofs):
         """DoFRenumbering::Cuthill_McKee stand-in (SURVEY Appendix A.1): plain Cuthill–McKee =
@@ -386,7 +424,8 @@ class BoxMesh:
         keep = [self.cell_dofs, self.cell_invJ, self.cell_detJ, self.cell_measure,
                 self.qpoints if with_qpoints else None,
                 None if force is None else np.ascontiguousarray(force, dtype=np.float64)]
-        s = _Cells(self.ncell, _p(keep[0], c_i32_p), *[_p(a, c_double_p) for a in keep[1:]])
+        s = _Cells(self.ncell, _p(keep[0], c_i32_p), *[_p(a, c_double_p) for a in keep[1:]],
+                   1 if self.geometry_per_q else 0, _p(self.map_lap, c_double_p))
         s._keep = keep
         return s
 
@@ -875,9 +914,13 @@ def l2_error(mesh, U, exact):
     exact(x[:, dim]) -> [:, dim+1]. Returns (err_u, err_p)."""
     dim = mesh.dim
     fe = FETables(dim, mesh.pu, mesh.pp, mesh.fe.nq1 + 1)
-    xq = mesh.lo + (mesh.cell_idx[:, None, :] + fe.xq[None, :, :]) * mesh.hx   # (scalars or [dim] arrays)
+    if getattr(mesh, "geometry_per_q", False):     # MappingQ(velocity degree, qmapping all), :262-263
+        _, det, xq, _ = mesh.mapped_geometry(fe)
+        JxW = det * fe.wq[None, :]
+    else:
+        xq = mesh.lo + (mesh.cell_idx[:, None, :] + fe.xq[None, :, :]) * mesh.hx   # (scalars or [dim] arrays)
+        JxW = mesh.cell_detJ[:, None] * fe.wq[None, :]
     ex = exact(xq.reshape(-1, dim)).reshape(mesh.ncell, fe.nq, dim + 1)
-    JxW = mesh.cell_detJ[:, None] * fe.wq[None, :]
     n_su = fe.n_su
     Uc = U[mesh.cell_dofs]
     uh = np.stack([Uc[:, c * n_su:(c + 1) * n_su] @ fe.Nu.T for c in range(dim)], axis=2)

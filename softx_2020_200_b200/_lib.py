@@ -40,7 +40,7 @@ class MeshDesc(C.Structure):
                 ("row_ptr", c_i64_p), ("col_idx", c_i32_p),
                 ("n_colors", C.c_int32), ("color_ptr", c_i32_p), ("color_cells", c_i32_p),
                 ("n_neighbors", C.c_int32), ("neighbor_rank", c_i32_p), ("send_ptr", c_i64_p),
-                ("send_idx", c_i32_p), ("recv_ptr", c_i64_p)]
+                ("send_idx", c_i32_p), ("recv_ptr", c_i64_p), ("mapping_laplacian", c_double_p)]
 
 
 class LinearSolverParams(C.Structure):

@@ -232,7 +232,7 @@ glsns_destroy(glsns_context *ctx)
   comm_destroy(ctx);
   DevBuf<double> *dbl[] = {&ctx->shape_u, &ctx->grad_u, &ctx->hess_u, &ctx->shape_p,
                            &ctx->grad_p, &ctx->weights, &ctx->inv_jac, &ctx->det_jac,
-                           &ctx->measure, &ctx->q_points, &ctx->force, &ctx->cvalues,
+                           &ctx->measure, &ctx->q_points, &ctx->force, &ctx->cvalues, &ctx->map_lap,
                            &ctx->val, &ctx->lu, &ctx->V, &ctx->w, &ctx->zg, &ctx->ytmp,
                            &ctx->tvec, &ctx->partials, &ctx->hbuf, &ctx->ycoef, &ctx->send_buf};
   for (auto *b : dbl)
@@ -332,6 +332,11 @@ glsns_set_mesh(glsns_context *ctx, const glsns_mesh_desc *m)
   const int64_t nnz = m->row_ptr[m->n_owned];
   if (nnz && !m->col_idx)
     return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "col_idx is null");
+  if (m->geometry_per_q && m->n_cells && !m->mapping_laplacian)
+    return fail(ctx, GLSNS_ERR_UNSUPPORTED,
+                "geometry_per_q = 1 needs mapping_laplacian: without the mapping's second derivatives "
+                "the shape-function Laplacians of gls_navier_stokes.cc:417-422 would be wrong on "
+                "non-affine cells");
   ctx->have_mesh = ctx->have_matrix = ctx->have_ilu = ctx->have_rhs = false;
   for (bool &b : ctx->vec_set)
     b = false;
@@ -350,6 +355,10 @@ glsns_set_mesh(glsns_context *ctx, const glsns_mesh_desc *m)
   GLSNS_TRY(dev_upload(ctx, ctx->inv_jac, m->inv_jacobian, geo * d * d));
   GLSNS_TRY(dev_upload(ctx, ctx->det_jac, m->det_jacobian, geo));
   GLSNS_TRY(dev_upload(ctx, ctx->measure, m->cell_measure, nc));
+  if (ctx->geometry_per_q && nc)
+    GLSNS_TRY(dev_upload(ctx, ctx->map_lap, m->mapping_laplacian, nc * q * d));
+  else
+    ctx->map_lap.release();
   if (m->q_points)
     GLSNS_TRY(dev_upload(ctx, ctx->q_points, m->q_points, nc * q * d));
   else

@@ -46,6 +46,7 @@ namespace glsns
       const int32_t *cell_dofs;
       int            geometry_per_q;
       const double  *inv_jac, *det_jac, *measure, *q_points, *force;
+      const double  *map_lap; // [n_cells][n_q][DIM] (geometry_per_q only): see glsns_mesh_desc
       // dofs
       int64_t        n_owned;
       const uint8_t *constrained;
@@ -150,6 +151,10 @@ namespace glsns
               for (int r = 0; r < DIM; ++r)
                 g += gr[r] * J[r][d];
               sGu[idx * DIM + d] = g;
+              // curved cell: the part of the real-space Hessian that comes from the mapping's
+              // own second derivatives, -grad_x N . c (c from the host, see glsns_mesh_desc)
+              if (A.geometry_per_q)
+                lap -= g * A.map_lap[((size_t)cell * nq + q) * DIM + d];
             }
 #pragma unroll
           for (int r = 0; r < DIM; ++r)
@@ -780,6 +785,7 @@ namespace glsns
     A.geometry_per_q = ctx->geometry_per_q;
     A.inv_jac = ctx->inv_jac.p, A.det_jac = ctx->det_jac.p, A.measure = ctx->measure.p;
     A.q_points    = ctx->q_points.p;
+    A.map_lap     = ctx->map_lap.p;
     A.force       = ctx->have_force ? ctx->force.p : nullptr;
     A.n_owned     = ctx->n_owned;
     A.constrained = ctx->constrained.p;

@@ -122,7 +122,7 @@ struct glsns_context
   int32_t                         trsv_grid = 0;
   std::vector<int32_t>            trsv_row_warp_l, trsv_row_warp_u; // schedule, for the trace
   glsns::DevBuf<int64_t> rowptr, diag_pos;
-  glsns::DevBuf<double>  inv_jac, det_jac, measure, q_points, force, cvalues;
+  glsns::DevBuf<double>  inv_jac, det_jac, measure, q_points, force, cvalues, map_lap;
   glsns::DevBuf<uint8_t> constrained;
   glsns::DevBuf<int2>    fgroups; // (first row, rows) of the row groups, by lower-sweep level
   glsns::DevBuf<int2>    sgroups; // every row in a group (diagonal-only rows too), by row: SpMV

@@ -192,6 +192,81 @@ namespace
       return i + (int64_t)gu[0] * (j + (int64_t)gu[1] * k);
     }
   };
+
+  // node order: natural or Cuthill-McKee on the node graph weighted by dofs per node
+  // (every dof of a node has the same neighbours, so this equals CM on the dof graph,
+  // DoFRenumbering::Cuthill_McKee at gls_navier_stokes.cc:70); node_order[position] = node
+  void
+  order_nodes(const Grid &G, const std::vector<int32_t> &ndof_node, const int renumber,
+              std::vector<int64_t> &node_order)
+  {
+    const int dim = G.dim;
+    node_order.resize(G.nnode);
+  if (!renumber)
+      std::iota(node_order.begin(), node_order.end(), (int64_t)0);
+    else
+      {
+        std::vector<int64_t> degree(G.nnode);
+#pragma omp parallel for schedule(static)
+        for (int64_t v = 0; v < G.nnode; ++v)
+          {
+            int idx[3], a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+            G.split(v, idx);
+            for (int d = 0; d < dim; ++d)
+              G.range(d, idx[d], a[d], b[d]);
+            int64_t deg = 0;
+            for (int k = a[2]; k <= b[2]; ++k)
+              for (int j = a[1]; j <= b[1]; ++j)
+                for (int i = a[0]; i <= b[0]; ++i)
+                  deg += ndof_node[G.join(i, j, k)];
+            degree[v] = deg;
+          }
+        std::vector<uint8_t> seen(G.nnode, 0);
+        int64_t              N = 0;
+        // seed: lowest-index node of minimal degree (a corner), as a stable argsort gives
+        std::vector<int64_t> by_deg(G.nnode);
+        std::iota(by_deg.begin(), by_deg.end(), (int64_t)0);
+        std::stable_sort(by_deg.begin(), by_deg.end(),
+                         [&](int64_t x, int64_t y) { return degree[x] < degree[y]; });
+        std::vector<int64_t> fresh;
+        for (int64_t z = 0; z < G.nnode && N < G.nnode; ++z)
+          {
+            if (seen[by_deg[z]])
+              continue;
+            node_order[N++]  = by_deg[z];
+            seen[by_deg[z]]  = 1;
+            int64_t level_lo = N - 1;
+            while (level_lo < N)
+              {
+                const int64_t level_hi = N;
+                for (int64_t t = level_lo; t < level_hi; ++t)
+                  {
+                    const int64_t v = node_order[t];
+                    int           idx[3], a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+                    G.split(v, idx);
+                    for (int d = 0; d < dim; ++d)
+                      G.range(d, idx[d], a[d], b[d]);
+                    fresh.clear();
+                    for (int k = a[2]; k <= b[2]; ++k)
+                      for (int j = a[1]; j <= b[1]; ++j)
+                        for (int i = a[0]; i <= b[0]; ++i)
+                          {
+                            const int64_t u = G.join(i, j, k);
+                            if (!seen[u])
+                              seen[u] = 1, fresh.push_back(u);
+                          }
+                    // neighbours of one parent by increasing degree, ties in index order
+                    std::stable_sort(fresh.begin(), fresh.end(), [&](int64_t x, int64_t y) {
+                      return degree[x] < degree[y];
+                    });
+                    for (int64_t u : fresh)
+                      node_order[N++] = u;
+                  }
+                level_lo = level_hi;
+              }
+          }
+      }
+  }
 } // namespace
 
 extern "C" {
@@ -253,7 +328,7 @@ glsnsh_mesh_create(int dim, const int *n_cells_dir, int pu, int pp, const double
   };
   // node order: natural or Cuthill-McKee on the node graph weighted by dofs per node
   // (every dof of a node has the same neighbours, so this equals CM on the dof graph)
-  std::vector<int64_t> node_order(G.nnode); // node_order[position] = node
+  std::vector<int64_t> node_order; // node_order[position] = node
   std::vector<int32_t> ndof_node(G.nnode);
   for (int64_t v = 0; v < G.nnode; ++v)
     {
@@ -261,70 +336,7 @@ glsnsh_mesh_create(int dim, const int *n_cells_dir, int pu, int pp, const double
       G.split(v, idx);
       ndof_node[v] = dim + (has_p(idx) ? 1 : 0);
     }
-  if (!renumber)
-    std::iota(node_order.begin(), node_order.end(), (int64_t)0);
-  else
-    {
-      std::vector<int64_t> degree(G.nnode);
-#pragma omp parallel for schedule(static)
-      for (int64_t v = 0; v < G.nnode; ++v)
-        {
-          int idx[3], a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
-          G.split(v, idx);
-          for (int d = 0; d < dim; ++d)
-            G.range(d, idx[d], a[d], b[d]);
-          int64_t deg = 0;
-          for (int k = a[2]; k <= b[2]; ++k)
-            for (int j = a[1]; j <= b[1]; ++j)
-              for (int i = a[0]; i <= b[0]; ++i)
-                deg += ndof_node[G.join(i, j, k)];
-          degree[v] = deg;
-        }
-      std::vector<uint8_t> seen(G.nnode, 0);
-      int64_t              N = 0;
-      // seed: lowest-index node of minimal degree (a corner), as a stable argsort gives
-      std::vector<int64_t> by_deg(G.nnode);
-      std::iota(by_deg.begin(), by_deg.end(), (int64_t)0);
-      std::stable_sort(by_deg.begin(), by_deg.end(),
-                       [&](int64_t x, int64_t y) { return degree[x] < degree[y]; });
-      std::vector<int64_t> fresh;
-      for (int64_t z = 0; z < G.nnode && N < G.nnode; ++z)
-        {
-          if (seen[by_deg[z]])
-            continue;
-          node_order[N++]  = by_deg[z];
-          seen[by_deg[z]]  = 1;
-          int64_t level_lo = N - 1;
-          while (level_lo < N)
-            {
-              const int64_t level_hi = N;
-              for (int64_t t = level_lo; t < level_hi; ++t)
-                {
-                  const int64_t v = node_order[t];
-                  int           idx[3], a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
-                  G.split(v, idx);
-                  for (int d = 0; d < dim; ++d)
-                    G.range(d, idx[d], a[d], b[d]);
-                  fresh.clear();
-                  for (int k = a[2]; k <= b[2]; ++k)
-                    for (int j = a[1]; j <= b[1]; ++j)
-                      for (int i = a[0]; i <= b[0]; ++i)
-                        {
-                          const int64_t u = G.join(i, j, k);
-                          if (!seen[u])
-                            seen[u] = 1, fresh.push_back(u);
-                        }
-                  // neighbours of one parent by increasing degree, ties in index order
-                  std::stable_sort(fresh.begin(), fresh.end(), [&](int64_t x, int64_t y) {
-                    return degree[x] < degree[y];
-                  });
-                  for (int64_t u : fresh)
-                    node_order[N++] = u;
-                }
-              level_lo = level_hi;
-            }
-        }
-    }
+  order_nodes(G, ndof_node, renumber, node_order);
   std::vector<int64_t> first_dof(G.nnode + 1, 0); // first new dof id of a node
   {
     int64_t next = 0;
@@ -770,6 +782,379 @@ glsnsh_mesh_partition(const glsnsh_mesh *serial, int n_ranks, int rank)
           for (int l = 0; l < S->n_loc; ++l)
             if (cd[l] >= r0 && cd[l] < r1)
               send_to[o].push_back(cd[l]);
+        }
+    }
+  std::vector<int> nb;
+  for (auto &kv : recv_from)
+    nb.push_back(kv.first);
+  for (auto &kv : send_to)
+    nb.push_back(kv.first);
+  std::sort(nb.begin(), nb.end());
+  nb.erase(std::unique(nb.begin(), nb.end()), nb.end());
+  M->send_ptr.assign(1, 0), M->recv_ptr.assign(1, 0);
+  for (int o : nb)
+    {
+      M->neighbor_rank.push_back(o);
+      std::vector<int64_t> &s = send_to[o];
+      std::sort(s.begin(), s.end());
+      s.erase(std::unique(s.begin(), s.end()), s.end());
+      for (int64_t g : s)
+        M->send_idx.push_back((int32_t)(g - r0));
+      M->send_ptr.push_back((int64_t)M->send_idx.size());
+      M->recv_ptr.push_back(M->recv_ptr.back() + (int64_t)recv_from[o].size());
+    }
+  return (glsnsh_mesh *)M;
+}
+
+// The rank-local mesh built directly, without ever holding the global dof-level arrays
+// (BASELINE.json configs[3]: 116^3 cells, 50.6 M dofs, 1.3e10 non-zeros -- the global CSR is
+// 52 GB of column indices): the same arrays, entry for entry, as glsnsh_mesh_create followed by
+// glsnsh_mesh_partition (tests/test_host_mirror.py holds the comparison), from node-level global
+// data only -- the Cuthill-McKee order of the node graph (12.6 M nodes at 116^3), the first dof of
+// every node, and row lengths per node (every dof of a node has the same row).
+glsnsh_mesh *
+glsnsh_mesh_create_local(int dim, const int *n_cells_dir, int pu, int pp, const double *lo,
+                         const double *hi, int nq1, const int *bc_type, const double *bc_value,
+                         const int *bc_order, int renumber, int with_q_points, int n_ranks, int rank)
+{
+  HostMesh *M = new HostMesh();
+  if ((dim != 2 && dim != 3) || pu < 1 || pp < 1 || pu % pp != 0 || n_ranks < 1 || rank < 0 ||
+      rank >= n_ranks)
+    {
+      M->error = "bad dim / degrees / rank";
+      return (glsnsh_mesh *)M;
+    }
+  M->dim = dim, M->pu = pu, M->pp = pp, M->nq1 = nq1 > 0 ? nq1 : pu + 1;
+  for (int d = 0; d < dim; ++d)
+    M->ncd[d] = n_cells_dir[d], M->lo[d] = lo[d], M->hi[d] = hi[d];
+  std::vector<double> x1, w1;
+  gauss01(M->nq1, x1, w1);
+  tensor_tables(dim, pu, x1, M->Nu, M->dNu, &M->d2Nu);
+  tensor_tables(dim, pp, x1, M->Np, M->dNp, nullptr);
+  M->n_su = 1, M->n_sp = 1, M->n_q = 1;
+  for (int d = 0; d < dim; ++d)
+    M->n_su *= pu + 1, M->n_sp *= pp + 1, M->n_q *= M->nq1;
+  M->n_loc = dim * M->n_su + M->n_sp;
+  M->wq.assign(M->n_q, 1.0), M->xq.assign((size_t)M->n_q * dim, 0.0);
+  for (int q = 0; q < M->n_q; ++q)
+    {
+      int qq = q;
+      for (int d = 0; d < dim; ++d)
+        {
+          const int i = qq % M->nq1;
+          qq /= M->nq1;
+          M->wq[q] *= w1[i];
+          M->xq[(size_t)q * dim + d] = x1[i];
+        }
+    }
+  Grid G;
+  G.dim = dim, G.pu = pu;
+  G.gu[0] = G.gu[1] = G.gu[2] = 1;
+  G.nnode = 1;
+  for (int d = 0; d < dim; ++d)
+    G.gu[d] = pu * M->ncd[d] + 1, G.nnode *= G.gu[d];
+  const int ratio = pu / pp;
+  auto      has_p = [&](const int idx[3]) {
+    for (int d = 0; d < dim; ++d)
+      if (idx[d] % ratio)
+        return false;
+    return true;
+  };
+  // the boundary the node's velocity dofs are constrained by (first listed wins), or -1
+  auto bc_face = [&](const int idx[3]) -> int {
+    for (int f = 0; f < 2 * dim; ++f)
+      {
+        const int face = bc_order ? bc_order[f] : f;
+        if (!bc_type || bc_type[face] == 0)
+          continue;
+        const int d = face / 2, side = face % 2;
+        if (idx[d] == (side ? G.gu[d] - 1 : 0))
+          return face;
+      }
+    return -1;
+  };
+  std::vector<int64_t> node_order;
+  std::vector<int32_t> ndof_node(G.nnode);
+#pragma omp parallel for schedule(static)
+  for (int64_t v = 0; v < G.nnode; ++v)
+    {
+      int idx[3];
+      G.split(v, idx);
+      ndof_node[v] = dim + (has_p(idx) ? 1 : 0);
+    }
+  order_nodes(G, ndof_node, renumber, node_order);
+  // position -> first dof (monotone), node -> first dof
+  std::vector<int64_t> pos_first(G.nnode + 1), first_dof(G.nnode);
+  {
+    int64_t next = 0;
+    for (int64_t t = 0; t < G.nnode; ++t)
+      {
+        pos_first[t]             = next;
+        first_dof[node_order[t]] = next;
+        next += ndof_node[node_order[t]];
+      }
+    pos_first[G.nnode] = next;
+    M->n_global        = next;
+  }
+  if (M->n_global >= (int64_t)INT32_MAX)
+    {
+      M->error = "more than 2^31 dofs";
+      return (glsnsh_mesh *)M;
+    }
+  // unconstrained dofs of every node, and of its neighbourhood (= the row length of its
+  // unconstrained dofs)
+  std::vector<int8_t> n_free(G.nnode);
+#pragma omp parallel for schedule(static)
+  for (int64_t v = 0; v < G.nnode; ++v)
+    {
+      int idx[3];
+      G.split(v, idx);
+      n_free[v] = (int8_t)(ndof_node[v] - (bc_face(idx) >= 0 ? dim : 0));
+    }
+  auto row_len_free = [&](int64_t v) -> int64_t {
+    int idx[3], a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+    G.split(v, idx);
+    for (int d = 0; d < dim; ++d)
+      G.range(d, idx[d], a[d], b[d]);
+    int64_t cnt = 0;
+    for (int k = a[2]; k <= b[2]; ++k)
+      for (int j = a[1]; j <= b[1]; ++j)
+        for (int i = a[0]; i <= b[0]; ++i)
+          cnt += n_free[G.join(i, j, k)];
+    return cnt;
+  };
+  // non-zeros before every position of the order
+  std::vector<int64_t> pos_nnz(G.nnode + 1);
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 0; t < G.nnode; ++t)
+    {
+      const int64_t v  = node_order[t];
+      const int     nf = n_free[v], nc = ndof_node[v] - nf;
+      pos_nnz[t + 1]   = nc + (nf ? nf * row_len_free(v) : 0);
+    }
+  pos_nnz[0] = 0;
+  for (int64_t t = 0; t < G.nnode; ++t)
+    pos_nnz[t + 1] += pos_nnz[t];
+  const int64_t nnz_global = pos_nnz[G.nnode];
+  // rowptr of a global dof (constrained dofs of a node come first: velocity components)
+  auto rowptr_of = [&](int64_t g) -> int64_t {
+    const int64_t t = std::upper_bound(pos_first.begin(), pos_first.end(), g) - pos_first.begin() - 1;
+    if (t >= G.nnode)
+      return nnz_global;
+    const int64_t v  = node_order[t];
+    const int     nf = n_free[v], nc = ndof_node[v] - nf, c = (int)(g - pos_first[t]);
+    return pos_nnz[t] + (c < nc ? c : nc + (int64_t)(c - nc) * row_len_free(v));
+  };
+  // block boundaries: equal share of the non-zeros, exactly as glsnsh_mesh_partition
+  std::vector<int64_t> begin(n_ranks + 1, 0);
+  for (int r = 1; r < n_ranks; ++r)
+    {
+      const int64_t target = nnz_global / n_ranks * r;
+      int64_t       a = 0, b = M->n_global; // smallest g with rowptr_of(g) >= target
+      while (a < b)
+        {
+          const int64_t mid = (a + b) / 2;
+          if (rowptr_of(mid) >= target)
+            b = mid;
+          else
+            a = mid + 1;
+        }
+      begin[r] = std::min<int64_t>(std::max(a, begin[r - 1]), M->n_global);
+    }
+  begin[n_ranks]   = M->n_global;
+  const int64_t r0 = begin[rank], r1 = begin[rank + 1];
+  M->owned_begin   = r0;
+  M->n_owned       = r1 - r0;
+  auto node_pos_of = [&](int64_t g) -> int64_t {
+    return std::upper_bound(pos_first.begin(), pos_first.end(), g) - pos_first.begin() - 1;
+  };
+  // ---- cells touching an owned dof, ghosts ----
+  const int64_t t0 = r1 > r0 ? node_pos_of(r0) : 0, t1 = r1 > r0 ? node_pos_of(r1 - 1) : -1;
+  int64_t       ncell_glob = 1;
+  for (int d = 0; d < dim; ++d)
+    ncell_glob *= M->ncd[d];
+  for (int64_t t = t0; t <= t1; ++t)
+    {
+      int idx[3], ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+      G.split(node_order[t], idx);
+      for (int d = 0; d < dim; ++d)
+        {
+          ca[d] = idx[d] % pu == 0 ? std::max(0, idx[d] / pu - 1) : idx[d] / pu;
+          cb[d] = std::min(M->ncd[d] - 1, idx[d] / pu);
+        }
+      for (int k = ca[2]; k <= cb[2]; ++k)
+        for (int j = ca[1]; j <= cb[1]; ++j)
+          for (int i = ca[0]; i <= cb[0]; ++i)
+            M->cell_ids.push_back(i + (int64_t)M->ncd[0] * (j + (int64_t)M->ncd[1] * k));
+    }
+  std::sort(M->cell_ids.begin(), M->cell_ids.end());
+  M->cell_ids.erase(std::unique(M->cell_ids.begin(), M->cell_ids.end()), M->cell_ids.end());
+  M->n_cells = (int64_t)M->cell_ids.size();
+  const int nu1 = pu + 1, np1 = pp + 1;
+  // global dofs of a cell, in the local dof layout of the ABI
+  auto cell_global_dofs = [&](int64_t c, int64_t *out) {
+    int ci[3] = {(int)(c % M->ncd[0]), (int)((c / M->ncd[0]) % M->ncd[1]),
+                 dim == 3 ? (int)(c / ((int64_t)M->ncd[0] * M->ncd[1])) : 0};
+    for (int a = 0; a < M->n_su; ++a)
+      {
+        int ai[3] = {a % nu1, (a / nu1) % nu1, dim == 3 ? a / (nu1 * nu1) : 0};
+        const int64_t v =
+          G.join(ci[0] * pu + ai[0], ci[1] * pu + ai[1], dim == 3 ? ci[2] * pu + ai[2] : 0);
+        for (int comp = 0; comp < dim; ++comp)
+          out[comp * M->n_su + a] = first_dof[v] + comp;
+      }
+    for (int a = 0; a < M->n_sp; ++a)
+      {
+        int ai[3] = {a % np1, (a / np1) % np1, dim == 3 ? a / (np1 * np1) : 0};
+        const int64_t v = G.join(ci[0] * pu + ai[0] * ratio, ci[1] * pu + ai[1] * ratio,
+                                 dim == 3 ? ci[2] * pu + ai[2] * ratio : 0);
+        out[dim * M->n_su + a] = first_dof[v] + dim;
+      }
+  };
+  std::vector<int64_t> cg((size_t)M->n_cells * M->n_loc);
+#pragma omp parallel for schedule(static)
+  for (int64_t lc = 0; lc < M->n_cells; ++lc)
+    cell_global_dofs(M->cell_ids[lc], cg.data() + (size_t)lc * M->n_loc);
+  std::vector<int64_t> ghosts;
+  for (int64_t g : cg)
+    if (g < r0 || g >= r1)
+      ghosts.push_back(g);
+  std::sort(ghosts.begin(), ghosts.end());
+  ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+  M->n_dofs     = M->n_owned + (int64_t)ghosts.size();
+  auto to_local = [&](int64_t g) -> int32_t {
+    if (g >= r0 && g < r1)
+      return (int32_t)(g - r0);
+    return (int32_t)(M->n_owned +
+                     (std::lower_bound(ghosts.begin(), ghosts.end(), g) - ghosts.begin()));
+  };
+  M->local_to_global.resize(M->n_dofs);
+  for (int64_t i = 0; i < M->n_owned; ++i)
+    M->local_to_global[i] = r0 + i;
+  for (size_t i = 0; i < ghosts.size(); ++i)
+    M->local_to_global[M->n_owned + i] = ghosts[i];
+  const double hx[3] = {(M->hi[0] - M->lo[0]) / M->ncd[0], (M->hi[1] - M->lo[1]) / M->ncd[1],
+                        dim == 3 ? (M->hi[2] - M->lo[2]) / M->ncd[2] : 1.0};
+  M->constrained.resize(M->n_dofs), M->cvalues.resize(M->n_dofs), M->dof_comp.resize(M->n_dofs);
+  M->dof_coords.resize((size_t)M->n_dofs * dim);
+  std::vector<int64_t> node_of_local(M->n_dofs);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < M->n_dofs; ++i)
+    {
+      const int64_t g = M->local_to_global[i], t = node_pos_of(g), v = node_order[t];
+      const int     c = (int)(g - pos_first[t]);
+      int           idx[3];
+      G.split(v, idx);
+      node_of_local[i]  = v;
+      const int face    = c < dim ? bc_face(idx) : -1;
+      M->constrained[i] = face >= 0;
+      M->cvalues[i]     = face >= 0 && bc_type[face] == 2 ? bc_value[face * 3 + c] : 0.0;
+      M->dof_comp[i]    = c;
+      for (int d = 0; d < dim; ++d)
+        M->dof_coords[(size_t)i * dim + d] = M->lo[d] + idx[d] * hx[d] / pu;
+    }
+  // ---- cells: local dofs, geometry, colours ----
+  M->cell_dofs.resize((size_t)M->n_cells * M->n_loc);
+  M->inv_jac.assign((size_t)M->n_cells * dim * dim, 0.0);
+  M->det_jac.resize(M->n_cells), M->measure.resize(M->n_cells);
+  if (with_q_points)
+    M->q_points.resize((size_t)M->n_cells * M->n_q * dim);
+  std::vector<int32_t> color(M->n_cells);
+  double               vol = 1;
+  for (int d = 0; d < dim; ++d)
+    vol *= hx[d];
+#pragma omp parallel for schedule(static)
+  for (int64_t lc = 0; lc < M->n_cells; ++lc)
+    {
+      const int64_t c = M->cell_ids[lc];
+      int ci[3] = {(int)(c % M->ncd[0]), (int)((c / M->ncd[0]) % M->ncd[1]),
+                   dim == 3 ? (int)(c / ((int64_t)M->ncd[0] * M->ncd[1])) : 0};
+      for (int k = 0; k < M->n_loc; ++k)
+        M->cell_dofs[(size_t)lc * M->n_loc + k] = to_local(cg[(size_t)lc * M->n_loc + k]);
+      for (int d = 0; d < dim; ++d)
+        M->inv_jac[(size_t)lc * dim * dim + d * dim + d] = 1.0 / hx[d];
+      M->det_jac[lc] = M->measure[lc] = vol;
+      if (with_q_points)
+        for (int q = 0; q < M->n_q; ++q)
+          for (int d = 0; d < dim; ++d)
+            M->q_points[((size_t)lc * M->n_q + q) * dim + d] =
+              M->lo[d] + (ci[d] + M->xq[(size_t)q * dim + d]) * hx[d];
+      color[lc] = (ci[0] & 1) + 2 * (ci[1] & 1) + (dim == 3 ? 4 * (ci[2] & 1) : 0);
+    }
+  const int ncolor = 1 << dim;
+  M->color_ptr.assign(ncolor + 1, 0);
+  for (int64_t c = 0; c < M->n_cells; ++c)
+    M->color_ptr[color[c] + 1]++;
+  for (int k = 0; k < ncolor; ++k)
+    M->color_ptr[k + 1] += M->color_ptr[k];
+  M->color_cells.resize(M->n_cells);
+  {
+    std::vector<int32_t> pos(M->color_ptr.begin(), M->color_ptr.end() - 1);
+    for (int64_t c = 0; c < M->n_cells; ++c)
+      M->color_cells[pos[color[c]]++] = (int32_t)c;
+  }
+  // ---- CSR of the owned rows ----
+  M->rowptr.assign(M->n_owned + 1, 0);
+  auto row_entries = [&](int64_t i, int32_t *out) -> int64_t {
+    if (M->constrained[i])
+      {
+        if (out)
+          out[0] = (int32_t)i;
+        return 1;
+      }
+    const int64_t v = node_of_local[i];
+    if (!out)
+      return row_len_free(v);
+    int idx[3], a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+    G.split(v, idx);
+    for (int d = 0; d < dim; ++d)
+      G.range(d, idx[d], a[d], b[d]);
+    int64_t cnt = 0;
+    for (int k = a[2]; k <= b[2]; ++k)
+      for (int j = a[1]; j <= b[1]; ++j)
+        for (int ii = a[0]; ii <= b[0]; ++ii)
+          {
+            const int64_t u  = G.join(ii, j, k);
+            const int     nf = n_free[u], nc = ndof_node[u] - nf;
+            for (int c = nc; c < ndof_node[u]; ++c)
+              out[cnt++] = to_local(first_dof[u] + c);
+          }
+    std::sort(out, out + cnt);
+    return cnt;
+  };
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < M->n_owned; ++i)
+    M->rowptr[i + 1] = row_entries(i, nullptr);
+  for (int64_t i = 0; i < M->n_owned; ++i)
+    M->rowptr[i + 1] += M->rowptr[i];
+  M->col.resize((size_t)M->rowptr[M->n_owned]);
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int64_t i = 0; i < M->n_owned; ++i)
+    row_entries(i, M->col.data() + M->rowptr[i]);
+  // ---- halo lists (as glsnsh_mesh_partition, from the local cells) ----
+  std::map<int, std::vector<int64_t>> recv_from, send_to;
+  auto                                 owner = [&](int64_t g) {
+    return (int)(std::upper_bound(begin.begin(), begin.end(), g) - begin.begin()) - 1;
+  };
+  for (int64_t g : ghosts)
+    recv_from[owner(g)].push_back(g);
+  for (int64_t lc = 0; lc < M->n_cells; ++lc)
+    {
+      const int64_t *cd = cg.data() + (size_t)lc * M->n_loc;
+      for (int k = 0; k < M->n_loc; ++k)
+        {
+          if (cd[k] >= r0 && cd[k] < r1)
+            continue;
+          const int            o = owner(cd[k]);
+          std::vector<int64_t> &s = send_to[o];
+          for (int l = 0; l < M->n_loc; ++l)
+            if (cd[l] >= r0 && cd[l] < r1)
+              s.push_back(cd[l]);
+          if (s.size() > (size_t)(1 << 22))
+            { // keep the lists small while they are built
+              std::sort(s.begin(), s.end());
+              s.erase(std::unique(s.begin(), s.end()), s.end());
+            }
         }
     }
   std::vector<int> nb;

@@ -355,11 +355,32 @@ namespace glsns
                      unsigned long long *trace, const int64_t trace_n, const int K_gate /* helpers per team */)
     {
       extern __shared__ __align__(128) unsigned char smem_all[];
-      const int K = K_gate;
+      // K_gate: helpers per team | warp layout << 8 | teams per CTA << 16.  A warp's scheduler is
+      // its index modulo 4, and a solver warp that shares a scheduler with the other solver and
+      // two polling helpers (layout 0: team t = warps t (K+1) ..., both solvers on scheduler 0 when
+      // K = 7) gets a fraction of the issue slots -- its 350 instructions per block took 1400
+      // cycles.  Layout 1: the solvers are warps 0 .. teams-1 (one scheduler each), the helpers
+      // follow, dealt round-robin to the teams.  Layout 2: as 1, and warps 4 .. 4+teams-1 stay
+      // idle, so a solver's scheduler carries one warp less.
+      const int K = K_gate & 255, layout = (K_gate >> 8) & 255, n_teams_cta = K_gate >> 16;
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-      const int team_in_cta = warp / (K + 1), role = warp - team_in_cta * (K + 1);
-      const int n_teams_cta = (blockDim.x >> 5) / (K + 1);
-      if (team_in_cta >= n_teams_cta)
+      int       team_in_cta, role;
+      if (layout == 0)
+        {
+          team_in_cta = warp / (K + 1), role = warp - team_in_cta * (K + 1);
+        }
+      else if (warp < n_teams_cta)
+        {
+          team_in_cta = warp, role = 0;
+        }
+      else
+        {
+          if (layout == 2 && warp >= 4 && warp < 4 + n_teams_cta)
+            return;
+          const int h = warp - n_teams_cta - (layout == 2 && warp >= 4 ? n_teams_cta : 0);
+          team_in_cta = h % n_teams_cta, role = 1 + h / n_teams_cta;
+        }
+      if (team_in_cta >= n_teams_cta || role > K)
         return;
       const int64_t team      = (int64_t)team_in_cta * gridDim.x + blockIdx.x; // consecutive lists on different SMs
       const size_t  team_smem = (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_NSLOT * TS_SSLOT + TS_TEAM_AREA;
@@ -776,6 +797,12 @@ namespace glsns
       // with 128-entry items 10.8 ms per application at 64^3 cells, 2 x (1+5) 8.75 ms,
       // 2 x (1+6) with 96-entry items 8.51 ms, 2 x (1+7) with 64-entry items 8.33 ms.
       int teams = 2, helpers = 7;
+      int layout = 1; // which warps are the solvers (see trsv_team_kernel)
+      int
+      warps() const
+      {
+        return teams * (helpers + 1) + (layout == 2 ? teams : 0);
+      }
     };
 
     size_t
@@ -793,8 +820,12 @@ namespace glsns
           t.teams = atoi(getenv("GLSNS_TRSV_TEAMS"));
         if (getenv("GLSNS_TRSV_HELPERS"))
           t.helpers = atoi(getenv("GLSNS_TRSV_HELPERS"));
+        if (getenv("GLSNS_TRSV_LAYOUT"))
+          t.layout = std::max(0, std::min(2, atoi(getenv("GLSNS_TRSV_LAYOUT"))));
         t.helpers = std::max(1, std::min(11, t.helpers));
         t.teams   = std::max(1, std::min(16 / (t.helpers + 1), t.teams));
+        if (t.warps() > 16 || (t.layout == 2 && t.teams > 4))
+          t.layout = 1;
         while (t.teams > 1 && t.teams * team_smem_bytes(t.helpers) > (size_t)TS_SMEM_MAX)
           --t.teams;
         return t;
@@ -813,11 +844,11 @@ namespace glsns
       GLSNS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
       int  *counters = ctx->counters.p;
-      int   K        = cfg.helpers;
+      int   K        = cfg.helpers | (cfg.layout << 8) | (cfg.teams << 16);
       void *args[]   = {(void *)&dir,      (void *)&stream, (void *)&rhs,          (void *)&x,
                         (void *)&counters, (void *)&trace,  (void *)&ctx->n_owned, (void *)&K};
       GLSNS_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kern, dim3(ctx->trsv_grid),
-                                                  dim3(cfg.teams * (cfg.helpers + 1) * 32), args,
+                                                  dim3(cfg.warps() * 32), args,
                                                   smem, ctx->stream));
       ctx->kernel_launches++;
       return GLSNS_OK;

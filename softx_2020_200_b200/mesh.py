@@ -29,6 +29,8 @@ def _bind(L):
     L.glsnsh_mesh_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
                                      _lib.c_double_p, _lib.c_double_p, C.c_int, C.POINTER(C.c_int),
                                      _lib.c_double_p, C.POINTER(C.c_int), C.c_int, C.c_int]
+    L.glsnsh_mesh_create_local.restype = C.c_void_p
+    L.glsnsh_mesh_create_local.argtypes = L.glsnsh_mesh_create.argtypes + [C.c_int, C.c_int]
     L.glsnsh_mesh_make_periodic.restype = C.c_int
     L.glsnsh_mesh_make_periodic.argtypes = [C.c_void_p, C.c_int]
     L.glsnsh_mesh_partition.restype = C.c_void_p
@@ -58,7 +60,9 @@ class BoxMesh:
     """
 
     def __init__(self, dim, n, pu, pp, lo=-1.0, hi=1.0, bcs=None, renumber=True, nq1=0,
-                 with_q_points=False, periodic=(), _handle=None):
+                 with_q_points=False, periodic=(), _handle=None, local=None):
+        """local=(n_ranks, rank): build only that rank's part (owned rows + ghost layer) without
+        the global dof-level arrays -- the same arrays as BoxMesh(...).partition(n_ranks, rank)."""
         self._L = _lib.lib()
         _bind(self._L)
         if _handle is not None:
@@ -85,9 +89,13 @@ class BoxMesh:
                         for c, v in enumerate(bc[2]):
                             vals[f * 3 + c] = v
                 order = listed + [f for f in range(6) if f not in listed]
-            self._h = self._L.glsnsh_mesh_create(dim, nd, pu, pp, lo3, hi3, nq1, types, vals,
-                                                 (C.c_int * 6)(*order), 1 if renumber else 0,
-                                                 1 if with_q_points else 0)
+            args = (dim, nd, pu, pp, lo3, hi3, nq1, types, vals, (C.c_int * 6)(*order),
+                    1 if renumber else 0, 1 if with_q_points else 0)
+            if local is not None:
+                assert not len(periodic), "periodic meshes are serial"
+                self._h = self._L.glsnsh_mesh_create_local(*args, int(local[0]), int(local[1]))
+            else:
+                self._h = self._L.glsnsh_mesh_create(*args)
             if len(periodic):
                 self._L.glsnsh_mesh_make_periodic(self._h, sum(1 << d for d in periodic))
         err = self._L.glsnsh_mesh_error(self._h).decode()

@@ -66,3 +66,34 @@ def exact_mms2d(x):
     X, Y = x[:, 0], x[:, 1]
     return np.stack([s(pi * X) ** 2 * c(pi * Y) * s(pi * Y), -c(pi * X) * s(pi * X) * s(pi * Y) ** 2,
                      s(pi * X) + s(pi * Y)], axis=1)
+
+
+# ---- Taylor-Couette (applications_tests/gls_navier_stokes_2d/taylorcouette_gls.prm) ----
+def shell_mapping(p):
+    """Parameter box (r, theta) -> the annulus: GridGenerator::hyper_shell with its
+    SphericalManifold, uniformly refined (new vertices and MappingQ support points at the polar
+    midpoints)."""
+    return np.stack([p[:, 0] * np.cos(p[:, 1]), p[:, 0] * np.sin(p[:, 1])], axis=1)
+
+
+def couette_inner_wall(x):
+    """bc 0 of taylorcouette_gls.prm:72-83: u = -y, v = x (inner cylinder at unit angular speed)."""
+    return np.stack([-x[:, 1], x[:, 0]], axis=1)
+
+
+def couette_exact(x):
+    """taylorcouette_gls.prm:36-43 (eta = ri = 0.25)."""
+    eta, ri = 0.25, 0.25
+    A, B = -(eta * eta) / (1 - eta * eta), ri * ri / (1 - eta * eta)
+    r, th = np.hypot(x[:, 0], x[:, 1]), np.arctan2(x[:, 1], x[:, 0])
+    ut = A * r + B / r
+    return np.stack([-np.sin(th) * ut, np.cos(th) * ut,
+                     A * A * r * r / 2 + 2 * A * B * np.log(r) - 0.5 * B * B / (r * r)], axis=1)
+
+
+def couette_mesh(oracle, refinement):
+    """hyper_shell(0.25, 1, 4 cells) refined `refinement` times: 4 * 2^r cells around, 2^r across."""
+    k = 2 ** refinement
+    return oracle.BoxMesh(2, (k, 4 * k), 2, 2, lo=(0.25, 0.0), hi=(1.0, 2 * np.pi),
+                          bcs={1: ("noslip",), 0: ("function", couette_inner_wall)}, periodic=(1,),
+                          mapping=shell_mapping)

@@ -202,6 +202,23 @@ def test_mms2d_gls_prm_with_its_shipped_ilu_fill(oracle):
     s.close()
 
 
+def test_geometry_per_q_without_mapping_laplacian_is_refused(oracle):
+    """glsns.h: per-point geometry needs the mapping's second derivatives; without them the
+    Laplacian terms would be silently wrong, so glsns_set_mesh refuses (GLSNS_ERR_UNSUPPORTED)."""
+    from softx_2020_200_b200 import GLSHotPath, GlsnsError
+    mesh = mms.couette_mesh(oracle, 2)
+    fe = mesh.fe
+    hp = GLSHotPath(0)
+    hp.set_fe(mesh.dim, mesh.pu, fe.Nu, fe.dNu, fe.d2Nu, fe.Np, fe.dNp, fe.wq)
+    ptr, order, _ = mesh.color_lists()
+    with pytest.raises(GlsnsError) as e:
+        hp.set_mesh(mesh.ndof, mesh.cell_dofs, mesh.cell_invJ, mesh.cell_detJ, mesh.cell_measure,
+                    mesh.constrained, mesh.rowptr, mesh.col, ptr, order, q_points=mesh.qpoints,
+                    constraint_values=mesh.constraint_value, geometry_per_q=True)
+    assert e.value.status == 6
+    hp.close()
+
+
 def _newton_gpu(hp, mesh, U0, scheme="steady", dts=None, tol=1e-6, max_it=10, lin=None, log=None):
     """NewtonNonLinearSolver::solve (newton_non_linear_solver.h:76-139) over the C ABI with the
     device-resident line search."""
@@ -244,6 +261,35 @@ def test_restart_01_golden_on_gpu(oracle):
         assert abs(r - g) <= 2e-6 * g
     err_u, _ = oracle.l2_error(mesh, U, mms.exact_2d)
     assert float("%.6g" % err_u) == 0.0343628
+    hp.close()
+
+
+def test_taylor_couette_curved_q2_cells_on_gpu(oracle):
+    """examples/02-taylor-couette's geometry (MappingQ(2) on every cell of a hyper_shell,
+    taylorcouette_gls.prm with `qmapping all = true`): Jacobian and residual entries of the CUDA
+    assembly on curved cells against the oracle (steady, BDF2 and rotating-frame terms), then the
+    Newton solution through the CUDA path reproduces taylorcouette_gls.output:45 -- velocity L2
+    error 7.7383e-04 at 64 cells, the reference's pin of the Q2 Laplacian terms on curved cells."""
+    mesh = mms.couette_mesh(oracle, 2)
+    assert mesh.geometry_per_q
+    hp = hotpath_from_oracle_mesh(mesh, 1.0, None)
+    _check_assembly(oracle, mesh, hp, random_state(mesh, scale=0.3), "steady", None, (None,) * 3,
+                    None, 1.0)
+    _check_assembly(oracle, mesh, hp, random_state(mesh, 5, 0.3), "bdf2", [0.05, 0.05, 0.05],
+                    (random_state(mesh, 6, 0.3), random_state(mesh, 7, 0.3), None), None, 1.0)
+    hp.close()
+    hp = hotpath_from_oracle_mesh(mesh, 0.2, None, True, (0, 0, 1.7))
+    _check_assembly(oracle, mesh, hp, random_state(mesh, 8, 0.3), "steady", None, (None,) * 3, None,
+                    0.2, True, (0, 0, 1.7))
+    hp.close()
+    hp = hotpath_from_oracle_mesh(mesh, 1.0, None)
+    U0 = mesh.apply_nonzero_constraints(np.zeros(mesh.ndof))
+    U, it, res = _newton_gpu(hp, mesh, U0, tol=1e-10,
+                             lin=dict(relative_residual=1e-8, minimum_residual=1e-13,
+                                      max_iterations=4000, ilu_atol=1e-10))
+    assert res <= 1e-10
+    err_u, _ = oracle.l2_error(mesh, U, mms.couette_exact)
+    assert "%.4e" % err_u == "7.7383e-04", err_u
     hp.close()
 
 

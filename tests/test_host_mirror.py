@@ -304,3 +304,26 @@ def test_time_stepping_glue_of_navier_stokes_base():
     assert [c[0] for c in calls] == ["bdf1", "bdf1", "bdf3", "bdf3"]
     assert [c[3][0] for c in calls] == [0.04, 0.04, 0.02, 0.1]
     assert calls[2][4] == (2, 1, 0) and calls[3][4] == (3, 2, 1)
+
+
+@pytest.mark.parametrize("dim,n,pu,pp,ranks", [(3, (4, 3, 5), 2, 2, 3), (3, 4, 1, 1, 2), (2, (7, 5), 2, 1, 4),
+                                               (3, 5, 2, 2, 8), (2, 6, 2, 2, 1)])
+def test_rank_local_mesh_equals_the_partition_of_the_global_one(dim, n, pu, pp, ranks):
+    """glsnsh_mesh_create_local (what bench.py uses for N > 1 and for the 50 M dof mesh of
+    BASELINE.json configs[3], where no rank can hold the global CSR) against glsnsh_mesh_create +
+    glsnsh_mesh_partition, array by array."""
+    from softx_2020_200_b200.mesh import BoxMesh, _DTYPES
+    bcs = [(0, "noslip"), (1, "noslip"), (2, "noslip"), (3, "function", (1.0, 0.5, 0.25))]
+    if dim == 3:
+        bcs += [(4, "noslip"), (5, "noslip")]
+    glob = BoxMesh(dim, n, pu, pp, bcs=bcs, with_q_points=True)
+    for rank in range(ranks):
+        a = glob.partition(ranks, rank)
+        b = BoxMesh(dim, n, pu, pp, bcs=bcs, with_q_points=True, local=(ranks, rank))
+        for attr in ("n_dofs", "n_owned", "n_cells", "nnz", "n_colors", "n_neighbors", "n_global",
+                     "owned_begin"):
+            assert getattr(a, attr) == getattr(b, attr), (attr, rank)
+        for name in _DTYPES:
+            if name in ("periodic_slave", "periodic_master"):
+                continue
+            assert np.array_equal(a.array(name), b.array(name)), (name, rank)

@@ -298,3 +298,62 @@ def test_structured_cell_kernel_equals_the_literal_loop(oracle, dim, n, pu, pp, 
                                          structured=True)
     assert np.max(np.abs(m_str - m_lit)) <= 1e-13 * np.max(np.abs(m_lit))
     assert np.max(np.abs(b_str - b_lit)) <= 1e-13 * np.max(np.abs(b_lit))
+
+
+def test_taylor_couette_golden_curved_q2_cells(oracle):
+    """applications_tests/gls_navier_stokes_2d/taylorcouette_gls.output:45-47 -- the reference's only
+    pin of the Q2 Laplacian terms on curved (MappingQ) cells: velocity L2 errors 7.7383e-04,
+    1.1452e-04, 1.5173e-05 at 64 / 256 / 1024 cells, and the straight-sided volumes it prints.
+    (Newton-converged to 1e-10, so independent of the reference's AMG solver.)"""
+    from tests import mms
+    g = REF["taylorcouette_gls"]
+    pr = oracle.scheme_params("steady", None, 1.0)
+    for level, (cells, err) in enumerate(zip(g["cells"], g["error_velocity"])):
+        mesh = mms.couette_mesh(oracle, level + 2)
+        assert mesh.ncell == cells
+        # deal.II's shell has no duplicated nodes across theta = 0; here they stay as identified rows
+        assert mesh.ndof - mesh.periodic_slave.size == g["dofs"][level]
+        if level:
+            assert "%.6g" % mesh.cell_measure.sum() == g["volume_q1"][level - 1]
+        U0 = mesh.apply_nonzero_constraints(np.zeros(mesh.ndof))
+        U, it, res = oracle.newton_solve(mesh, U0, pr, None, tol=1e-10, max_it=10,
+                                         lin=dict(rel=1e-8, abs_=1e-13, max_iters=4000, ilu_atol=1e-10))
+        assert res <= 1e-10
+        err_u, _ = oracle.l2_error(mesh, U, mms.couette_exact)
+        assert "%.4e" % err_u == err, (cells, err_u, err)
+
+
+def test_mapping_laplacian_formula_against_finite_differences(oracle):
+    """lap N = H_ref(N) : (J^-1 J^-T) - grad_x N . c with c_k = sum_rs d2x_k/dxi_r dxi_s (J^-1 J^-T)_rs
+    (include/glsns.h: mapping_laplacian) against a finite-difference Laplacian in real space of
+    x -> N(xi(x)) on a curved Q2 cell of the shell mesh."""
+    from tests import mms
+    mesh = mms.couette_mesh(oracle, 2)
+    fe, c, q = mesh.fe, 5, 4
+    X = mesh.cell_X[c]
+    K, lapc = mesh.cell_invJ[c, q], mesh.map_lap[c, q]
+    grad = fe.dNu[q] @ K                                                  # [ns, dim] real-space gradients
+    lap = np.einsum("ars,rs->a", fe.d2Nu[q], K @ K.T) - grad @ lapc
+
+    def shape_at(x):                                                     # N(xi(x)) by Newton on the mapping
+        xi = fe.xq[q].copy()
+        for _ in range(30):
+            N, dN, _ = oracle._tensor_tables(2, 2, [0.5])               # placeholder shapes (overwritten below)
+            V0, D0, _ = oracle.lagrange1d(2, [xi[0]])
+            V1, D1, _ = oracle.lagrange1d(2, [xi[1]])
+            N = np.array([V0[a % 3, 0] * V1[a // 3, 0] for a in range(9)])
+            dN = np.array([[D0[a % 3, 0] * V1[a // 3, 0], V0[a % 3, 0] * D1[a // 3, 0]] for a in range(9)])
+            r = N @ X - x
+            if np.linalg.norm(r) < 1e-15:
+                break
+            xi -= np.linalg.solve((X.T @ dN), r)
+        return N
+    x0, h = mesh.qpoints[c, q], 2e-4
+    fd = np.zeros(9)
+    for d in range(2):
+        e = np.zeros(2)
+        e[d] = h
+        fd += (shape_at(x0 + e) - 2 * shape_at(x0) + shape_at(x0 - e)) / (h * h)
+    assert np.max(np.abs(fd - lap)) <= 2e-5 * np.max(np.abs(lap))
+    # and the correction is not small on this cell: without it the test above would fail
+    assert np.max(np.abs(grad @ lapc)) >= 1e-2 * np.max(np.abs(lap))

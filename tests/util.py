@@ -12,7 +12,9 @@ def hotpath_from_oracle_mesh(mesh, viscosity=1.0, force=None, srf=False, omega=(
     ptr, order, _ = mesh.color_lists()
     hp.set_mesh(mesh.ndof, mesh.cell_dofs, mesh.cell_invJ, mesh.cell_detJ, mesh.cell_measure,
                 mesh.constrained, mesh.rowptr, mesh.col, ptr, order, q_points=mesh.qpoints,
-                constraint_values=mesh.constraint_value)
+                constraint_values=mesh.constraint_value,
+                geometry_per_q=getattr(mesh, "geometry_per_q", False),
+                mapping_laplacian=getattr(mesh, "map_lap", None))
     hp.set_physics(viscosity, srf, omega)
     hp.set_forcing(force)
     return hp
