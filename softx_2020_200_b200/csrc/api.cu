@@ -248,6 +248,7 @@ glsns_destroy(glsns_context *ctx)
   ctx->dinv.release();
   ctx->a2p.release();
   ctx->diag_rows.release();
+  ctx->grp_first.release();
   ctx->fgroups.release();
   ctx->sgroups.release();
   ctx->rowptr.release();

@@ -118,6 +118,7 @@ struct glsns_context
   glsns::DevBuf<int64_t> a2p;
   int32_t geometry_per_q = 0, n_colors = 0;
   glsns::DevBuf<int32_t> cell_dofs, col, color_cells, order_l, diag_rows;
+  glsns::DevBuf<int32_t> grp_first; // per row: first row of its group (-1: diagonal-only row)
   glsns::TrsvSweep                trsv_l, trsv_u;
   int32_t                         trsv_grid = 0;
   std::vector<int32_t>            trsv_row_warp_l, trsv_row_warp_u; // schedule, for the trace

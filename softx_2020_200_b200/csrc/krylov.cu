@@ -49,14 +49,16 @@ namespace glsns
       return r; // valid in thread 0
     }
 
-    // partials[(v0+v)*nblocks + block] = sum over this block's elements of V[v0+v][t]*w[t]
+    // partials[(v0+v)*nblocks + block] = sum over this block's elements of V[v0+v][t]*w[t];
+    // SELF: also partials[self_index*nblocks + block] = sum of w[t]^2 (w is in registers anyway)
+    template <bool SELF>
     __global__ void __launch_bounds__(VB)
     multi_dot_kernel(const int64_t n, const double *__restrict__ V, const int64_t ld,
                      const int v0, const int nv, const double *__restrict__ w,
-                     double *__restrict__ partials)
+                     double *__restrict__ partials, const int self_index)
     {
       __shared__ double sh[VB / 32];
-      double            acc[DOT_BATCH];
+      double            acc[DOT_BATCH], self = 0;
 #pragma unroll
       for (int v = 0; v < DOT_BATCH; ++v)
         acc[v] = 0;
@@ -68,6 +70,8 @@ namespace glsns
           for (int v = 0; v < DOT_BATCH; ++v)
             if (v < nv)
               acc[v] += V[(int64_t)(v0 + v) * ld + t] * wt;
+          if (SELF)
+            self += wt * wt;
         }
 #pragma unroll
       for (int v = 0; v < DOT_BATCH; ++v)
@@ -77,6 +81,12 @@ namespace glsns
             if (threadIdx.x == 0)
               partials[(int64_t)(v0 + v) * gridDim.x + blockIdx.x] = r;
           }
+      if (SELF)
+        {
+          const double r = block_sum(self, sh);
+          if (threadIdx.x == 0)
+            partials[(int64_t)self_index * gridDim.x + blockIdx.x] = r;
+        }
     }
 
     // out[v] = sum_b partials[v*nblocks + b]   (one block per v, fixed order)
@@ -150,12 +160,26 @@ namespace glsns
         }
     }
 
-    // out = w / sqrt(*sumsq)   (sumsq on the device) or out = w * scale when sumsq == nullptr
+    // ||w - V h||^2 for w' = w before the projections h were subtracted, V orthonormal:
+    // ||w'||^2 - sum h_i^2.  (Used after the SECOND Gram-Schmidt pass only, where h is the
+    // rounding-level correction of a vector that is already orthogonal to V: no cancellation.)
+    // The host evaluates the same expression in the same order.
+    __host__ __device__ inline double
+    norm2_after_projection(const double sumsq, const double *h, const int nh)
+    {
+      double s = sumsq;
+      for (int i = 0; i < nh; ++i)
+        s = fma(-h[i], h[i], s);
+      return s;
+    }
+
+    // out = w / sqrt(*sumsq - sum h^2)   (on the device) or out = w * scale when sumsq == nullptr
     __global__ void __launch_bounds__(VB)
     scale_kernel(const int64_t n, const double *__restrict__ w, const double *__restrict__ sumsq,
-                 const double scale, double *__restrict__ out)
+                 const double scale, double *__restrict__ out, const double *__restrict__ h = nullptr,
+                 const int nh = 0)
     {
-      const double  f      = sumsq ? 1.0 / sqrt(*sumsq) : scale;
+      const double  f      = sumsq ? 1.0 / sqrt(norm2_after_projection(*sumsq, h, nh)) : scale;
       const int64_t stride = (int64_t)gridDim.x * VB;
       for (int64_t t = (int64_t)blockIdx.x * VB + threadIdx.x; t < n; t += stride)
         out[t] = w[t] * f;
@@ -211,20 +235,24 @@ namespace glsns
         1, std::min<int64_t>((n + VB - 1) / VB, (int64_t)ctx->n_sm * 8));
     }
 
-    // hbuf[out_off + v] = V[v] . w for v < nv (all-reduced over ranks)
+    // hbuf[out_off + v] = V[v] . w for v < nv (all-reduced over ranks); with_self: one more
+    // entry, hbuf[out_off + nv] = w . w, in the same kernels and the same all-reduce
     glsns_status
     batched_dots(glsns_context *ctx, const double *V, int64_t ld, int nv, const double *w,
-                 int out_off)
+                 int out_off, bool with_self = false)
     {
       const int64_t n    = ctx->n_owned;
       const int     grid = vec_grid(ctx, n);
       for (int v0 = 0; v0 < nv; v0 += DOT_BATCH)
         {
-          multi_dot_kernel<<<grid, VB, 0, ctx->stream>>>(n, V, ld, v0,
-                                                         std::min(DOT_BATCH, nv - v0), w,
-                                                         ctx->partials.p);
+          const int nb = std::min(DOT_BATCH, nv - v0);
+          if (with_self && v0 + DOT_BATCH >= nv) // (the last batch also squares w)
+            multi_dot_kernel<true><<<grid, VB, 0, ctx->stream>>>(n, V, ld, v0, nb, w, ctx->partials.p, nv);
+          else
+            multi_dot_kernel<false><<<grid, VB, 0, ctx->stream>>>(n, V, ld, v0, nb, w, ctx->partials.p, -1);
           ctx->kernel_launches++;
         }
+      nv += with_self;
       reduce_partials_kernel<<<nv, VB, 0, ctx->stream>>>(grid, ctx->partials.p,
                                                          ctx->hbuf.p + out_off);
       ctx->kernel_launches++;
@@ -299,7 +327,10 @@ namespace glsns
   }
 
   // One CGS2 orthogonalisation of ctx->w against V[0..nv) and normalisation into
-  // V[nv].  Leaves h1 in hbuf[0..nv), h2 in hbuf[64..64+nv), ||w||^2 in hbuf[128].
+  // V[nv].  Leaves h1 in hbuf[0..nv), h2 in hbuf[64..64+nv) and, in hbuf[64+nv], ||w'||^2 of
+  // the vector w' after the first pass: the norm of the final vector is
+  // sqrt(||w'||^2 - sum h2^2) (norm2_after_projection), so the second pass needs no reduction
+  // of its own -- two all-reduces per iteration instead of three.
   static glsns_status
   orthogonalise(glsns_context *ctx, int nv)
   {
@@ -308,15 +339,11 @@ namespace glsns
     double       *V = ctx->V.p, *w = ctx->w.p;
     GLSNS_TRY(batched_dots(ctx, V, n, nv, w, 0));
     multi_axpy_kernel<false><<<grid, VB, 0, ctx->stream>>>(n, V, n, nv, ctx->hbuf.p, w, nullptr);
-    GLSNS_TRY(batched_dots(ctx, V, n, nv, w, 64));
-    multi_axpy_kernel<true><<<grid, VB, 0, ctx->stream>>>(n, V, n, nv, ctx->hbuf.p + 64, w,
-                                                          ctx->partials.p);
-    reduce_partials_kernel<<<1, VB, 0, ctx->stream>>>(grid, ctx->partials.p, ctx->hbuf.p + 128);
+    GLSNS_TRY(batched_dots(ctx, V, n, nv, w, 64, true));
+    multi_axpy_kernel<false><<<grid, VB, 0, ctx->stream>>>(n, V, n, nv, ctx->hbuf.p + 64, w, nullptr);
+    scale_kernel<<<grid, VB, 0, ctx->stream>>>(n, w, ctx->hbuf.p + 64 + nv, 0.0, V + (int64_t)nv * n,
+                                               ctx->hbuf.p + 64, nv);
     ctx->kernel_launches += 3;
-    GLSNS_TRY(allreduce_sum(ctx, ctx->hbuf.p + 128, 1));
-    scale_kernel<<<grid, VB, 0, ctx->stream>>>(n, w, ctx->hbuf.p + 128, 0.0,
-                                               V + (int64_t)nv * n);
-    ctx->kernel_launches++;
     GLSNS_CUDA(ctx, cudaGetLastError());
     return GLSNS_OK;
   }
@@ -383,14 +410,14 @@ namespace glsns
             timer_begin(ctx, T_ORTHOG);
             GLSNS_TRY(orthogonalise(ctx, j + 1));
             timer_end(ctx, T_ORTHOG);
-            GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->hbuf.p, 129 * sizeof(double),
+            GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->hbuf.p, (64 + j + 2) * sizeof(double),
                                             cudaMemcpyDeviceToHost, st));
             GLSNS_CUDA(ctx, cudaStreamSynchronize(st));
             timers_drain(ctx);
             const double *h1 = ctx->h_pinned, *h2 = ctx->h_pinned + 64;
             for (int i = 0; i <= j; ++i)
               H[(size_t)i * m + j] = h1[i] + h2[i];
-            H[(size_t)(j + 1) * m + j] = sqrt(ctx->h_pinned[128]);
+            H[(size_t)(j + 1) * m + j] = sqrt(norm2_after_projection(h2[j + 1], h2, j + 1));
             for (int i = 0; i < j; ++i)
               {
                 const double a = H[(size_t)i * m + j], c = H[(size_t)(i + 1) * m + j];

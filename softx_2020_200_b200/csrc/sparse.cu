@@ -95,6 +95,9 @@ namespace glsns
           gr_n = groups[g];
           rs_n = rowptr[gr_n.x], re_n = rowptr[gr_n.x + 1];
         }
+      int32_t pc0 = 0, pc1 = 0;
+      double  pv0[4] = {0, 0, 0, 0}, pv1[4] = {0, 0, 0, 0};
+      bool    have_pre = false;
       for (; g < n_groups; g += stride)
         {
           const int2    gr = gr_n;
@@ -113,6 +116,17 @@ namespace glsns
           int k = lane;
           if (m == 4)
             { // the common case, fully unrolled
+              if (have_pre)
+                { // the group's first entries were requested before the previous group's reduction
+                  const double x0 = __ldg(x + pc0), x1 = __ldg(x + pc1);
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    {
+                      s[a][0] += pv0[a] * x0;
+                      s[a][1] += pv1[a] * x1;
+                    }
+                  k += 2 * TPG;
+                }
               for (; k + TPG < len; k += 2 * TPG)
                 {
                   const int32_t c0 = __ldcs(col + rs + k), c1 = __ldcs(col + rs + k + TPG);
@@ -140,15 +154,50 @@ namespace glsns
                 if (a < m)
                   s[a][0] += __ldcs(val + rs + (int64_t)a * len + k) * xv;
             }
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
+          // the next group's first entries go out now, so that the memory system has work while
+          // this group's totals are reduced (a 64-bit shuffle costs 25 cycles)
+          have_pre = false;
+          if (g + stride < n_groups && gr_n.y == 4 && lane + TPG < (int)(re_n - rs_n))
             {
-              double t = s[a][0] + s[a][1];
+              const int len_n = (int)(re_n - rs_n);
+              pc0 = __ldcs(col + rs_n + lane), pc1 = __ldcs(col + rs_n + lane + TPG);
 #pragma unroll
-              for (int o = TPG / 2; o > 0; o >>= 1)
-                t += __shfl_down_sync(0xffffffffu, t, o, TPG);
-              if (lane == 0 && a < m)
-                y[r0 + a] = t;
+              for (int a = 0; a < 4; ++a)
+                {
+                  pv0[a] = __ldcs(val + rs_n + (int64_t)a * len_n + lane);
+                  pv1[a] = __ldcs(val + rs_n + (int64_t)a * len_n + lane + TPG);
+                }
+              have_pre = true;
+            }
+          if (TPG == 32 && m == 4)
+            { // four totals over 32 lanes in 6 shuffles: halve the number of rows a lane carries
+              // while the partners are 16 and 8 lanes apart, then sum over the rest; lanes
+              // 8 a .. 8 a + 7 end up with the total of row a
+              const double t0 = s[0][0] + s[0][1], t1 = s[1][0] + s[1][1], t2 = s[2][0] + s[2][1],
+                           t3 = s[3][0] + s[3][1];
+              const bool   h16 = lane & 16, h8 = lane & 8;
+              double       k0 = h16 ? t2 : t0, k1 = h16 ? t3 : t1;
+              k0 += __shfl_xor_sync(0xffffffffu, h16 ? t0 : t2, 16);
+              k1 += __shfl_xor_sync(0xffffffffu, h16 ? t1 : t3, 16);
+              double tot = (h8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+              tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+              tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+              tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+              if ((lane & 7) == 0)
+                y[r0 + (lane >> 3)] = tot;
+            }
+          else
+            {
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                {
+                  double t = s[a][0] + s[a][1];
+#pragma unroll
+                  for (int o = TPG / 2; o > 0; o >>= 1)
+                    t += __shfl_down_sync(0xffffffffu, t, o, TPG);
+                  if (lane == 0 && a < m)
+                    y[r0 + a] = t;
+                }
             }
         }
     }
@@ -505,6 +554,268 @@ namespace glsns
               apply_row(std::integral_constant<int, 2>(), kk + 2);
               fetch(std::integral_constant<int, 2>(), kk + 6);
               apply_row(std::integral_constant<int, 3>(), kk + 3);
+            }
+          // ---- rows of the group eliminate each other ----
+          for (int b = 0; b + 1 < m; ++b)
+            {
+              const int pb = nl + b;
+              if (lane > b && lane < m)
+                {
+                  const double l      = sv[lane * maxlen + pb] / sv[b * maxlen + pb];
+                  sv[lane * maxlen + pb] = l;
+                  l4[lane]            = l;
+                }
+              __syncwarp();
+              for (int p = pb + 1 + lane; p < len; p += 32)
+                if (sc[p] < n)
+                  {
+                    const double ub = sv[b * maxlen + p];
+#pragma unroll
+                    for (int a = 1; a < 4; ++a)
+                      if (a > b && a < m)
+                        sv[a * maxlen + p] -= l4[a] * ub;
+                  }
+              __syncwarp();
+            }
+          for (int k = lane; k < len; k += 32)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (a < m)
+                lu[rs + (int64_t)a * len + k] = sv[a * maxlen + k];
+          if (lane < m && sv[lane * maxlen + nl + lane] == 0.0)
+            atomicExch(&counters[1], 1);
+          __syncwarp();
+          __threadfence(); // the rows, then (one fence for all of them) their flags
+          if (lane < m)
+            *(volatile int *)(row_done + r0 + lane) = epoch;
+          __syncwarp();
+        }
+    }
+
+    // The same factorisation with the PIVOT rows taken group-wise as well.  The rows that
+    // eliminate a group come in runs of up to 4 consecutive rows of one group (the dofs of a
+    // neighbouring mesh node): one column pattern, so one read of the indices and ONE hash
+    // look-up per column serve the whole run, and the run is one step of the warp's
+    // dependent loop instead of four.  ilu_factor_groups_kernel issued ~410 GB of pivot-row
+    // reads in 1.5 KB pieces, one piece per (group, pivot row) with a hash probe per entry;
+    // here a piece is a run (<= 4 rows x 1 KB of values + 0.5 KB of indices) and the probes
+    // drop fourfold.  The arithmetic per entry is unchanged -- the pivots of a run are
+    // applied in ascending order, one fused multiply-add each, exactly the scalar IKJ
+    // sequence -- so the factors are bitwise those of the row-wise kernels
+    // (tests/test_gpu_parity.py compares them).
+    constexpr int FR_PRE = 4; // 32-entry chunks of a run requested early
+
+    __global__ void __launch_bounds__(320, 1)
+    ilu_factor_runs_kernel(const int32_t n_groups, const int2 *__restrict__ groups,
+                           const int64_t n, const int64_t *__restrict__ rowptr,
+                           const int32_t *__restrict__ col, const int64_t *__restrict__ diag_pos,
+                           const int32_t *__restrict__ grp_first, double *lu, int *row_done,
+                           const int epoch, int *counters, const int maxlen, const int hbits)
+    {
+      extern __shared__ __align__(16) unsigned char fg_smem[];
+      const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int      hsize = 1 << hbits, hmask = hsize - 1;
+      const size_t   per_warp = (size_t)maxlen * 36 + 192 + (size_t)hsize * 6;
+      unsigned char *W  = fg_smem + warp * per_warp;
+      double        *sv = reinterpret_cast<double *>(W);                       // [4][maxlen]
+      double        *l4 = reinterpret_cast<double *>(W + (size_t)maxlen * 32); // [4 rows][4 pivots]
+      int32_t       *sc = reinterpret_cast<int32_t *>(W + (size_t)maxlen * 32 + 192); // [maxlen]
+      int32_t       *hkey = sc + maxlen;                                       // [hsize], -1 = empty
+      int16_t       *hpos = reinterpret_cast<int16_t *>(hkey + hsize);         // [hsize]
+      auto hash = [&](int32_t j) { return (int)(((unsigned)j * 2654435761u) >> (32 - hbits)); };
+      for (;;)
+        {
+          int t = 0;
+          if (lane == 0)
+            t = atomicAdd(&counters[0], 1);
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if (t >= n_groups)
+            break;
+          const int2    g  = groups[t];
+          const int     r0 = g.x, m = g.y;
+          const int64_t rs = rowptr[r0];
+          const int     len = (int)(rowptr[r0 + 1] - rs), nl = (int)(diag_pos[r0] - rs);
+          for (int k = lane; k < hsize; k += 32)
+            hkey[k] = -1;
+          __syncwarp();
+          for (int k = lane; k < len; k += 32)
+            {
+              const int32_t j = col[rs + k];
+              sc[k]           = j;
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                if (a < m)
+                  sv[a * maxlen + k] = lu[rs + (int64_t)a * len + k];
+              int s = hash(j);
+              while (atomicCAS(hkey + s, -1, j) != -1)
+                s = (s + 1) & hmask;
+              hpos[s] = (int16_t)k;
+            }
+          __syncwarp();
+          // readiness of the pivot rows, as in ilu_factor_groups_kernel
+          int  first_unready = 0;
+          auto scan_ready    = [&]() {
+            while (first_unready < nl)
+              {
+                const int  kk   = first_unready + lane;
+                const bool nope = kk >= nl ? false : *(volatile int *)(row_done + sc[kk]) != epoch;
+                const unsigned bal = __ballot_sync(0xffffffffu, nope);
+                if (bal)
+                  {
+                    first_unready += __ffs(bal) - 1;
+                    break;
+                  }
+                first_unready = min(nl, first_unready + 32);
+              }
+            __threadfence();
+          };
+          scan_ready();
+          // two runs in flight: the next one is requested while the current one is applied
+          int     rc[2] = {0, 0}, rkk[2] = {0, 0}, rbase[2] = {0, 0}, rlen[2] = {0, 0};
+          int64_t rrs[2][4];
+          double  rdiag[2][4], rin[2][6];
+          int32_t cjS[2][FR_PRE];
+          double  uvS[2][4][FR_PRE];
+          auto fetch = [&](auto SET, const int kk) -> int { // returns the pivot index after the run
+            constexpr int st = decltype(SET)::value;
+            rc[st]           = 0;
+            if (kk >= nl)
+              return nl;
+            const int32_t k  = sc[kk];
+            const int32_t gf = grp_first[k];
+            int           c  = 1;
+            while (c < 4 && kk + c < nl && sc[kk + c] == k + c && grp_first[k + c] == gf)
+              ++c;
+            if (kk + c > first_unready)
+              { // some row of the run was not final when last looked: wait for it
+                if (lane == 0)
+                  for (int b = 0; b < c; ++b)
+                    {
+                      long long spins = 0;
+                      while (*(volatile int *)(row_done + k + b) != epoch)
+                        if (++spins > SPIN_LIMIT)
+                          {
+                            atomicExch(&counters[1], 2);
+                            break;
+                          }
+                    }
+                __syncwarp();
+                first_unready = kk + c;
+                scan_ready();
+              }
+            rc[st] = c, rkk[st] = kk;
+            const int64_t rs0 = rowptr[k], d0 = diag_pos[k] - rs0;
+            rlen[st]  = (int)(rowptr[k + 1] - rs0);
+            rbase[st] = (int)d0 + c;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              if (b < c)
+                {
+                  rrs[st][b]   = rs0 + (int64_t)b * rlen[st];
+                  rdiag[st][b] = __ldcg(lu + rrs[st][b] + d0 + b);
+                }
+            { // couplings inside the run: u(b, b') for b < b', packed 01 02 03 12 13 23
+              int q = 0;
+#pragma unroll
+              for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int b2 = b + 1; b2 < 4; ++b2, ++q)
+                  rin[st][q] = b2 < c ? __ldcg(lu + rrs[st][b] + d0 + b2) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < FR_PRE; ++u)
+              {
+                const int o = rbase[st] + lane + 32 * u;
+                cjS[st][u]  = o < rlen[st] ? __ldg(col + rs0 + o) : 0x7fffffff;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                  uvS[st][b][u] = (b < c && o < rlen[st]) ? __ldcg(lu + rrs[st][b] + o) : 0.0;
+              }
+            return kk + c;
+          };
+          auto apply_run = [&](auto SET) {
+            constexpr int st = decltype(SET)::value;
+            const int     c  = rc[st];
+            if (c == 0)
+              return;
+            // multipliers of the group's rows, pivot by pivot (scalar IKJ order)
+            if (lane < m)
+              {
+                double *row = sv + lane * maxlen + rkk[st];
+                int     q   = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                  {
+                    if (b < c)
+                      {
+                        const double l = row[b] / rdiag[st][b];
+                        row[b]         = l;
+                        l4[lane * 4 + b] = l;
+#pragma unroll
+                        for (int b2 = b + 1; b2 < 4; ++b2)
+                          if (b2 < c)
+                            row[b2] = fma(-l, rin[st][q + b2 - b - 1], row[b2]);
+                      }
+                    q += 3 - b;
+                  }
+              }
+            __syncwarp();
+            double lm[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+                lm[a][b] = (a < m && b < c) ? l4[a * 4 + b] : 0.0;
+            auto apply = [&](const int32_t j, const double u0, const double u1, const double u2,
+                             const double u3) {
+              if (j >= n)
+                return; // ghost column (or past the end): outside the diagonal block
+              int s = hash(j);
+              for (;;)
+                {
+                  const int32_t key = hkey[s];
+                  if (key == j)
+                    {
+                      const int p = hpos[s];
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        if (a < m)
+                          {
+                            double v = sv[a * maxlen + p];
+                            v        = fma(-lm[a][0], u0, v);
+                            if (c > 1)
+                              v = fma(-lm[a][1], u1, v);
+                            if (c > 2)
+                              v = fma(-lm[a][2], u2, v);
+                            if (c > 3)
+                              v = fma(-lm[a][3], u3, v);
+                            sv[a * maxlen + p] = v;
+                          }
+                      return;
+                    }
+                  if (key == -1)
+                    return; // not in the pattern: ILU(0) drops the fill
+                  s = (s + 1) & hmask;
+                }
+            };
+#pragma unroll
+            for (int u = 0; u < FR_PRE; ++u)
+              apply(cjS[st][u], uvS[st][0][u], uvS[st][1][u], uvS[st][2][u], uvS[st][3][u]);
+            for (int o = rbase[st] + lane + 32 * FR_PRE; o < rlen[st]; o += 32)
+              apply(__ldg(col + rrs[st][0] + o), __ldcg(lu + rrs[st][0] + o),
+                    c > 1 ? __ldcg(lu + rrs[st][1] + o) : 0.0, c > 2 ? __ldcg(lu + rrs[st][2] + o) : 0.0,
+                    c > 3 ? __ldcg(lu + rrs[st][3] + o) : 0.0);
+            __syncwarp();
+          };
+          int next = fetch(std::integral_constant<int, 0>(), 0);
+          while (rc[0])
+            {
+              next = fetch(std::integral_constant<int, 1>(), next);
+              apply_run(std::integral_constant<int, 0>());
+              if (!rc[1])
+                break;
+              next = fetch(std::integral_constant<int, 0>(), next);
+              apply_run(std::integral_constant<int, 1>());
             }
           // ---- rows of the group eliminate each other ----
           for (int b = 0; b + 1 < m; ++b)
@@ -922,7 +1233,26 @@ namespace glsns
         const size_t per_warp = (size_t)maxlen * 36 + 64 + ((size_t)6 << hbits);
         const int    warps    = (int)std::min<size_t>(16, (size_t)(227 * 1024) / per_warp);
         static const bool by_rows = getenv("GLSNS_ILU_BY_ROWS") != nullptr;
-        if (warps >= 2 && ctx->n_groups > 0 && !by_rows)
+        static const bool by_pivot_rows = getenv("GLSNS_ILU_BY_PIVOT_ROWS") != nullptr;
+        const size_t per_warp_r = per_warp + 128;
+        const int    warps_r    = (int)std::min<size_t>(10, (size_t)(227 * 1024) / per_warp_r);
+        if (warps_r >= 2 && ctx->n_groups > 0 && !by_rows && !by_pivot_rows && ctx->grp_first.p)
+          {
+            // rows of a group share one warp, and so do the pivot rows of a run
+            if (ctx->n_diag_rows)
+              ilu_mark_rows_kernel<<<(ctx->n_diag_rows + 255) / 256, 256, 0, ctx->stream>>>(
+                ctx->n_diag_rows, ctx->diag_rows.p, ctx->row_done.p, ctx->epoch);
+            const size_t smem = warps_r * per_warp_r;
+            GLSNS_CUDA(ctx, cudaFuncSetAttribute(ilu_factor_runs_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem));
+            const int grid = (int)std::min<int64_t>((ctx->n_groups + warps_r - 1) / warps_r, ctx->n_sm);
+            ilu_factor_runs_kernel<<<grid, warps_r * 32, smem, ctx->stream>>>(
+              ctx->n_groups, ctx->fgroups.p, n, ctx->rowptr.p, ctx->col.p, ctx->diag_pos.p,
+              ctx->grp_first.p, ctx->lu.p, ctx->row_done.p, ctx->epoch, ctx->counters.p, maxlen, hbits);
+            ctx->kernel_launches += 3;
+          }
+        else if (warps >= 2 && ctx->n_groups > 0 && !by_rows)
           {
             // rows of a group share one warp (the general case)
             if (ctx->n_diag_rows)

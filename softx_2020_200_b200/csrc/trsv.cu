@@ -912,6 +912,13 @@ namespace glsns
       GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     GLSNS_TRY(dev_upload(ctx, ctx->diag_rows, diag_rows.data(), diag_rows.size()));
+    { // per row: the first row of its group (the factorisation takes its pivot rows group-wise)
+      std::vector<int32_t> gf((size_t)std::max<int64_t>(n, 1), -1);
+      for (int64_t i = 0; i < n; ++i)
+        gf[i] = grp_of[i] >= 0 ? grp_ptr[grp_of[i]] : -1;
+      GLSNS_TRY(dev_upload(ctx, ctx->grp_first, gf.data(), gf.size()));
+      GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
 
     const TrsvConfig cfg = trsv_config();
     ctx->trsv_grid       = ctx->n_sm;
@@ -1313,14 +1320,17 @@ namespace glsns
     GLSNS_TRY(schedule(false, ctx->trsv_l, ctx->levels_l, nullptr));
     GLSNS_TRY(schedule(true, ctx->trsv_u, ctx->levels_u, nullptr));
 
-    // ---- profile-guided list order ----
+    // ---- profile-guided list order (opt-in: GLSNS_TRSV_TUNE=<rounds>) ----
     // The level order assumes that every level takes the same time everywhere; it does not
     // (chains advance several levels in the time a hop between teams takes), and a team then
-    // keeps a chain that is ready waiting behind one that is late (tools/trsv_trace.py: a few
-    // dozen such stalls of 10-20 us were 30 % of a sweep).  So: run the schedule once on zero
-    // factors with the trace on, re-order the lists by when each block's inputs were there,
-    // keep the new schedule if it is faster, repeat.  Once per sparsity pattern.
-    const int rounds = getenv("GLSNS_TRSV_TUNE") ? atoi(getenv("GLSNS_TRSV_TUNE")) : 3;
+    // keeps a chain that is ready waiting behind one that is late.  So: run the schedule once on
+    // zero factors with the trace on, re-order the lists by when each block's inputs were there,
+    // keep the new schedule if it is faster, repeat.  Measured: -4.6 % at 32^3 cells with the
+    // round-1 kernel, but at 64^3 the first round is slower (7.85 -> 8.43 ms) and is discarded
+    // after seconds of set-up time, and a tuned order depends on measured times, so the last
+    // bits of an ILU application differed between two contexts.  Off by default: the schedule
+    // is then a function of the sparsity pattern alone and results are reproducible run to run.
+    const int rounds = getenv("GLSNS_TRSV_TUNE") ? atoi(getenv("GLSNS_TRSV_TUNE")) : 0;
     if (rounds > 0 && ng > 0)
       {
         DevBuf<double>             r, z;
