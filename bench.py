@@ -221,9 +221,10 @@ class GpuCase:
         from softx_2020_200_b200.mesh import BoxMesh
         self.n, self.world, self.dist, self.torch = n, world, dist, torch
         t0 = time.perf_counter()
-        gmesh = BoxMesh(3, n, 2, 2, bcs=CAVITY)
-        self.n_global, self.nnz_global = gmesh.n_dofs, (int(gmesh.nnz) if world == 1 else None)
-        self.mesh = mesh = gmesh if world == 1 else gmesh.partition(world, rank)
+        # N > 1: every rank builds its own part only (owned rows + ghost layer,
+        # glsnsh_mesh_create_local): no rank ever holds the global CSR
+        self.mesh = mesh = BoxMesh(3, n, 2, 2, bcs=CAVITY, local=(world, rank) if world > 1 else None)
+        self.n_global, self.nnz_global = mesh.n_global, (int(mesh.nnz) if world == 1 else None)
         self.hp = hp = GLSHotPath(local_rank)
         if world > 1:
             uid = torch.zeros(128, dtype=torch.uint8)
@@ -235,8 +236,6 @@ class GpuCase:
         mesh.attach(hp)
         hp.set_physics(NU)
         self.setup_s = time.perf_counter() - t0
-        if world > 1:
-            gmesh.close()
         self.constrained = mesh.array("constrained").astype(bool)
         self.cvalues = mesh.array("constraint_values").copy()
         U0 = mesh.initial_state()

@@ -73,7 +73,10 @@ namespace glsns
     // found by trsv_analyse) are multiplied together: the column indices and the x
     // entries are read once per group instead of once per row, i.e. 9 instead of 12
     // bytes per nonzero for 4-row groups.  TPG threads per group, consecutive lanes on
-    // consecutive nonzeros.
+    // consecutive nonzeros.  Measured and rejected in round 2 (64^3 cells, 4.70 ms as is):
+    // requesting the next group's first 64 entries before the reduction (80 registers, three
+    // CTAs per SM instead of five: 5.89 ms); the four totals reduced together in 6 shuffles
+    // with the register count held at 48 by __launch_bounds__(256, 5) (7.54 ms).
     template <int TPG>
     __global__ void __launch_bounds__(256)
     spmv_groups_kernel(const int32_t n_groups, const int2 *__restrict__ groups,
@@ -95,9 +98,6 @@ namespace glsns
           gr_n = groups[g];
           rs_n = rowptr[gr_n.x], re_n = rowptr[gr_n.x + 1];
         }
-      int32_t pc0 = 0, pc1 = 0;
-      double  pv0[4] = {0, 0, 0, 0}, pv1[4] = {0, 0, 0, 0};
-      bool    have_pre = false;
       for (; g < n_groups; g += stride)
         {
           const int2    gr = gr_n;
@@ -116,17 +116,6 @@ namespace glsns
           int k = lane;
           if (m == 4)
             { // the common case, fully unrolled
-              if (have_pre)
-                { // the group's first entries were requested before the previous group's reduction
-                  const double x0 = __ldg(x + pc0), x1 = __ldg(x + pc1);
-#pragma unroll
-                  for (int a = 0; a < 4; ++a)
-                    {
-                      s[a][0] += pv0[a] * x0;
-                      s[a][1] += pv1[a] * x1;
-                    }
-                  k += 2 * TPG;
-                }
               for (; k + TPG < len; k += 2 * TPG)
                 {
                   const int32_t c0 = __ldcs(col + rs + k), c1 = __ldcs(col + rs + k + TPG);
@@ -154,50 +143,15 @@ namespace glsns
                 if (a < m)
                   s[a][0] += __ldcs(val + rs + (int64_t)a * len + k) * xv;
             }
-          // the next group's first entries go out now, so that the memory system has work while
-          // this group's totals are reduced (a 64-bit shuffle costs 25 cycles)
-          have_pre = false;
-          if (g + stride < n_groups && gr_n.y == 4 && lane + TPG < (int)(re_n - rs_n))
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
             {
-              const int len_n = (int)(re_n - rs_n);
-              pc0 = __ldcs(col + rs_n + lane), pc1 = __ldcs(col + rs_n + lane + TPG);
+              double t = s[a][0] + s[a][1];
 #pragma unroll
-              for (int a = 0; a < 4; ++a)
-                {
-                  pv0[a] = __ldcs(val + rs_n + (int64_t)a * len_n + lane);
-                  pv1[a] = __ldcs(val + rs_n + (int64_t)a * len_n + lane + TPG);
-                }
-              have_pre = true;
-            }
-          if (TPG == 32 && m == 4)
-            { // four totals over 32 lanes in 6 shuffles: halve the number of rows a lane carries
-              // while the partners are 16 and 8 lanes apart, then sum over the rest; lanes
-              // 8 a .. 8 a + 7 end up with the total of row a
-              const double t0 = s[0][0] + s[0][1], t1 = s[1][0] + s[1][1], t2 = s[2][0] + s[2][1],
-                           t3 = s[3][0] + s[3][1];
-              const bool   h16 = lane & 16, h8 = lane & 8;
-              double       k0 = h16 ? t2 : t0, k1 = h16 ? t3 : t1;
-              k0 += __shfl_xor_sync(0xffffffffu, h16 ? t0 : t2, 16);
-              k1 += __shfl_xor_sync(0xffffffffu, h16 ? t1 : t3, 16);
-              double tot = (h8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
-              tot += __shfl_xor_sync(0xffffffffu, tot, 4);
-              tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-              tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-              if ((lane & 7) == 0)
-                y[r0 + (lane >> 3)] = tot;
-            }
-          else
-            {
-#pragma unroll
-              for (int a = 0; a < 4; ++a)
-                {
-                  double t = s[a][0] + s[a][1];
-#pragma unroll
-                  for (int o = TPG / 2; o > 0; o >>= 1)
-                    t += __shfl_down_sync(0xffffffffu, t, o, TPG);
-                  if (lane == 0 && a < m)
-                    y[r0 + a] = t;
-                }
+              for (int o = TPG / 2; o > 0; o >>= 1)
+                t += __shfl_down_sync(0xffffffffu, t, o, TPG);
+              if (lane == 0 && a < m)
+                y[r0 + a] = t;
             }
         }
     }
