@@ -328,7 +328,7 @@ def run_ours(args):
     parity = None
     if world > 1 and not args.no_parity_check:
         from tests.multi_gpu_check import check as multi_gpu_check
-        parity = multi_gpu_check(args.parity_cells, world, rank, local_rank, dist)
+        parity = multi_gpu_check(args.parity_cells, world, rank, local_rank, dist, verbose=False)
         if not parity["ok"]:
             raise SystemExit("multi-GPU parity check failed: %r" % (parity,))
 
@@ -413,6 +413,7 @@ def run_ours(args):
                                "the state after the first Newton update from rest; GMRES(30)+ILU(0), "
                                "rel 1e-4 / abs 1e-9, ILU atol 1e-12",
                    "cells_per_dir": n, "n_dofs": case.n_global, "nnz": case.nnz_global,
+                   "n_dofs_per_gpu_rank0": int(mesh.n_owned), "nnz_per_gpu_rank0": int(mesh.nnz),
                    "gmres_iterations": its, "line_search_trials": trials,
                    "true_residual": info["true_residual"], "tolerance": info["tolerance"],
                    "ilu_blocks": world,

@@ -136,8 +136,8 @@ typedef struct
   const double  *det_jacobian;   /* [n_cells]([n_q]); JxW = det * weight        */
   const double  *cell_measure;   /* [n_cells] cell->measure()                   */
   const double  *q_points;       /* [n_cells][n_q][dim] or NULL (needed for SRF) */
-  /* zero_constraints: 1 = homogeneous-Dirichlet-constrained dof. Hanging-node
-     lines are not supported yet (GLSNS_ERR_UNSUPPORTED path is the host's). */
+  /* zero_constraints: 1 = homogeneous-Dirichlet-constrained dof; 2 = hanging-node line
+     (then constraint_ptr/idx/weight below hold its entries).                           */
   const uint8_t *constrained;    /* [n_dofs]                                    */
   /* nonzero_constraints inhomogeneities (values the constrained dofs take in
      apply_constraints, physics_solver.h:98-102); NULL = all zero.             */
@@ -167,6 +167,21 @@ typedef struct
      which is what trace(fe_values[velocities].hessian(k, q)) is on a curved cell.
      NULL when geometry_per_q = 0. */
   const double  *mapping_laplacian;
+  /* Hanging-node lines (DoFTools::make_hanging_node_constraints in setup_dofs; Kelly-refined
+     meshes, navier_stokes_base.cc:610-729), in the CLOSED form of zero_constraints: dof i with
+     constrained[i] == 2 is x_i = sum_k constraint_weight[k] x_{constraint_idx[k]},
+     k in [constraint_ptr[i], constraint_ptr[i+1]); the masters are unconstrained dofs (Dirichlet
+     masters have dropped out; a line may be empty).  constraint_inhomogeneity[i] is what the
+     Dirichlet masters contribute in nonzero_constraints (apply_constraints,
+     physics_solver.h:98-102), NULL = 0.  The scatter resolves the lines as
+     AffineConstraints::distribute_local_to_global does (gls_navier_stokes.cc:755-771); the solver
+     distributes them after the solve (:1287).  The cell colouring must then separate cells that
+     share a MASTER, not only a dof.  All NULL when there are no hanging nodes.  One rank only
+     (GLSNS_ERR_UNSUPPORTED with n_ranks > 1); glsns_assemble_l2_projection does not take them.  */
+  const int64_t *constraint_ptr;          /* [n_dofs+1] or NULL                 */
+  const int32_t *constraint_idx;
+  const double  *constraint_weight;
+  const double  *constraint_inhomogeneity; /* [n_dofs] or NULL                  */
 } glsns_mesh_desc;
 
 /* `linear solver` subsection (source/core/parameters.cc:507-559). */

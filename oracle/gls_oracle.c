@@ -657,11 +657,58 @@ csr_find(const int64_t *rowptr, const int32_t *col, int32_t row, int32_t c)
  * built with keep_constrained_dofs = false, :204-208): a constrained row keeps
  * only its diagonal, which receives |local(i,i)|; its RHS entry stays 0;
  * couplings to constrained columns are dropped.  */
+/* Hanging-node lines of the constraints (Kelly-refined meshes, navier_stokes_base.cc:610-729;
+ * DoFTools::make_hanging_node_constraints in setup_dofs): dof i with constrained[i] == 2 is
+ * x_i = sum_k w_k x_{m_k} over the entries hptr[i] .. hptr[i+1] (masters unconstrained: the closed
+ * form of zero_constraints, Dirichlet masters dropped).  Set by glso_set_hanging, NULL = none. */
+static const int64_t *g_hptr = NULL;
+static const int32_t *g_hidx = NULL;
+static const double  *g_hw   = NULL;
+void
+glso_set_hanging(const int64_t *ptr, const int32_t *idx, const double *w)
+{
+  g_hptr = ptr, g_hidx = idx, g_hw = w;
+}
+
 static void
 scatter_cell(int n, const int32_t *dofs, const uint8_t *constrained,
              const int64_t *rowptr, const int32_t *col, int assemble_matrix,
              const double *M, const double *b, double *val, double *rhs)
 {
+  if (g_hptr)
+    { /* distribute_local_to_global with hanging-node lines: every local dof stands for its
+         masters (itself with weight 1 when unconstrained, nothing when Dirichlet); a constrained
+         row -- Dirichlet or hanging -- keeps |local(i,i)| on its own diagonal */
+      for (int i = 0; i < n; ++i)
+        {
+          const int32_t gi = dofs[i];
+          if (constrained[gi] && assemble_matrix)
+            val[csr_find(rowptr, col, gi, gi)] += fabs(M[(size_t)i * n + i]);
+          const int64_t ib = constrained[gi] == 2 ? g_hptr[gi] : 0,
+                        ie = constrained[gi] == 2 ? g_hptr[gi + 1] : (constrained[gi] ? 0 : 1);
+          for (int64_t ki = ib; ki < ie; ++ki)
+            {
+              const int32_t ri = constrained[gi] == 2 ? g_hidx[ki] : gi;
+              const double  wi = constrained[gi] == 2 ? g_hw[ki] : 1.0;
+              rhs[ri] += wi * b[i];
+              if (!assemble_matrix)
+                continue;
+              for (int j = 0; j < n; ++j)
+                {
+                  const int32_t gj = dofs[j];
+                  const int64_t jb = constrained[gj] == 2 ? g_hptr[gj] : 0,
+                                je = constrained[gj] == 2 ? g_hptr[gj + 1] : (constrained[gj] ? 0 : 1);
+                  for (int64_t kj = jb; kj < je; ++kj)
+                    {
+                      const int32_t cj = constrained[gj] == 2 ? g_hidx[kj] : gj;
+                      const double  wj = constrained[gj] == 2 ? g_hw[kj] : 1.0;
+                      val[csr_find(rowptr, col, ri, cj)] += wi * wj * M[(size_t)i * n + j];
+                    }
+                }
+            }
+        }
+      return;
+    }
   for (int i = 0; i < n; ++i)
     {
       const int32_t gi = dofs[i];

@@ -464,6 +464,230 @@ class BoxMesh:
         return U
 
 
+class RefinedBoxMesh(BoxMesh):
+    """A box mesh of n^dim cells of which the cells selected by `refine(cell_centre[:, dim]) -> bool`
+    are refined once (one level of Kelly / uniform-in-a-region refinement,
+    navier_stokes_base.cc:610-729): a non-conforming mesh with HANGING NODES on the faces and edges
+    between refined and unrefined cells, constrained as DoFTools::make_hanging_node_constraints does
+    (setup_dofs, gls_navier_stokes.cc:57-228): the value at a fine node on a coarse cell's boundary is
+    the coarse cell's trace there, x_i = sum_a N_a(xi_i) x_a.  In the closed zero_constraints the
+    Dirichlet masters drop out; nonzero_constraints keep them as an inhomogeneity.  Everything else
+    (dof numbering by Cuthill-McKee, sparsity with keep_constrained_dofs = false, boundary values,
+    colours) follows BoxMesh.  parity: unpinned -- no reference test with hanging nodes can be
+    reproduced here (cylinder_gls needs gmsh + Kelly); the class is checked by a patch test (a
+    solution in the FE space is reproduced to rounding on the non-conforming mesh)."""
+
+    def __init__(self, dim, n, pu, pp, refine, lo=-1.0, hi=1.0, bcs=None, renumber="cm", nq1=None):
+        assert pu % pp == 0
+        self.dim, self.ncd, self.pu, self.pp = dim, n, pu, pp
+        self.lo, self.hi = float(lo), float(hi)
+        self.fe = fe = FETables(dim, pu, pp, nq1)
+        self.geometry_per_q, self.map_lap, self.mapping = False, None, None
+        H = (hi - lo) / n
+        L = 2 * pu                                   # lattice units per coarse cell (fine spacing = 1)
+        base = np.indices((n,) * dim).reshape(dim, -1)[::-1].T            # x fastest
+        centre = lo + (base + 0.5) * H
+        ref = np.asarray(refine(centre), dtype=bool)
+        orig, size = [], []                                                # per active cell (lattice units)
+        child = np.indices((2,) * dim).reshape(dim, -1)[::-1].T
+        for c in range(base.shape[0]):
+            if ref[c]:
+                for ch in child:
+                    orig.append(base[c] * L + ch * pu)
+                    size.append(pu)
+            else:
+                orig.append(base[c] * L)
+                size.append(L)
+        orig, size = np.array(orig, dtype=np.int64), np.array(size, dtype=np.int64)
+        self.ncell = ncell = orig.shape[0]
+        self.cell_is_fine = size == pu
+
+        def lattice(p):                                                    # local node offsets in units of size/p
+            n1 = p + 1
+            a = np.arange(n1 ** dim)
+            return np.stack([(a // n1 ** d) % n1 for d in range(dim)], axis=1)
+        au, ap = lattice(pu), lattice(pp)
+        un_xyz = orig[:, None, :] + au[None, :, :] * (size[:, None, None] // pu)     # [ncell, n_su, dim]
+        pn_xyz = orig[:, None, :] + ap[None, :, :] * (size[:, None, None] // pp)
+        G = n * L + 1
+        key = lambda xyz: (xyz * (G ** np.arange(dim))).sum(axis=-1)
+        ukeys, pkeys = key(un_xyz), key(pn_xyz)
+        node_keys = np.unique(ukeys)
+        nnode = node_keys.size
+        node_of = lambda k: np.searchsorted(node_keys, k)
+        has_p = np.zeros(nnode, dtype=bool)
+        has_p[node_of(np.unique(pkeys))] = True
+        node_xyz = np.stack([(node_keys // G ** d) % G for d in range(dim)], axis=1)
+        ndof_node = dim + has_p.astype(np.int64)
+        first = np.concatenate([[0], np.cumsum(ndof_node)])
+        self.ndof = int(first[-1])
+        vel_dof = first[:-1, None] + np.arange(dim)[None, :]
+        p_dof = np.where(has_p, first[:-1] + dim, -1)
+        un, pn = node_of(ukeys), node_of(pkeys)
+        cell_dofs = np.concatenate([vel_dof[un, c] for c in range(dim)] + [p_dof[pn]], axis=1)
+        assert cell_dofs.min() >= 0
+        comp = np.zeros(self.ndof, dtype=np.int32)
+        dof_node = np.zeros(self.ndof, dtype=np.int64)
+        for c in range(dim):
+            comp[vel_dof[:, c]] = c
+            dof_node[vel_dof[:, c]] = np.arange(nnode)
+        comp[p_dof[has_p]] = dim
+        dof_node[p_dof[has_p]] = np.arange(nnode)[has_p]
+        coords = lo + node_xyz * (H / L)
+        # ---- hanging-node lines: fine nodes on the boundary of a coarse cell that are not its own ----
+        lines = {}                                                         # dof -> {master dof: weight}
+        keyset = {int(k): i for i, k in enumerate(node_keys)}
+
+        def trace_lines(p, own_dof, has):                                  # element of degree p
+            step = L // p
+            half = np.indices((2 * p + 1,) * dim).reshape(dim, -1)[::-1].T            # half-lattice of the coarse cell
+            half = half[np.any((half == 0) | (half == 2 * p), axis=1) & np.any(half % 2 == 1, axis=1)]
+            xi = half / (2.0 * p)
+            V = [lagrange1d(p, xi[:, d])[0] for d in range(dim)]           # [p+1, npts] per direction
+            lat = lattice(p)
+            W = np.ones((half.shape[0], lat.shape[0]))
+            for d in range(dim):
+                W *= V[d][lat[:, d], :].T
+            for c in np.nonzero(~self.cell_is_fine)[0]:
+                pts = orig[c] + half * (step // 2)
+                masters_nodes = node_of(key(orig[c] + lat * step))
+                for t in range(pts.shape[0]):
+                    nd = keyset.get(int(key(pts[t])))
+                    if nd is None or not has(nd):
+                        continue
+                    w = W[t]
+                    nz = np.nonzero(np.abs(w) > 1e-14)[0]
+                    for dofs_of in own_dof:                                # one line per component
+                        lines.setdefault(int(dofs_of(nd)), {int(dofs_of(masters_nodes[a])): float(w[a]) for a in nz})
+        trace_lines(pu, [(lambda nd, c=c: vel_dof[nd, c]) for c in range(dim)], lambda nd: True)
+        trace_lines(pp, [lambda nd: p_dof[nd]], lambda nd: has_p[nd])
+        # ---- boundary values (not on dofs that already carry a hanging-node line) ----
+        constrained = np.zeros(self.ndof, dtype=np.uint8)
+        cvalue = np.zeros(self.ndof)
+        for d_ in lines:
+            constrained[d_] = 2
+        if bcs is None:
+            bcs = {None: ("noslip",)}
+        dirichlet_value = {}
+        for face, bc in bcs.items():
+            if face is None:
+                on = np.any((node_xyz == 0) | (node_xyz == G - 1), axis=1)
+            else:
+                d, side = face // 2, face % 2
+                on = node_xyz[:, d] == (G - 1 if side else 0)
+            nodes = np.nonzero(on)[0]
+            vals = np.zeros((nodes.size, dim)) if bc[0] == "noslip" else np.asarray(
+                bc[1](coords[nodes]), dtype=np.float64)
+            for c in range(dim):
+                d_ = vel_dof[nodes, c]
+                for k, dd in enumerate(d_):
+                    if dd not in dirichlet_value:                          # first listed boundary wins
+                        dirichlet_value[int(dd)] = float(vals[k, c])
+                new = constrained[d_] == 0
+                constrained[d_[new]] = 1
+                cvalue[d_[new]] = vals[new, c]
+        # close(): Dirichlet masters leave the zero_constraints lines and become an inhomogeneity of
+        # the nonzero_constraints lines
+        hang_rows, hang_inhom = {}, {}
+        for d_, ms in lines.items():
+            hang_rows[d_] = {m: w for m, w in ms.items() if constrained[m] == 0}
+            hang_inhom[d_] = sum(w * dirichlet_value.get(m, 0.0) for m, w in ms.items() if constrained[m] == 1)
+            assert all(constrained[m] != 2 for m in ms), "chained hanging nodes (more than one level)"
+        # ---- renumbering on the graph of the expanded cells ----
+        def expand(cd):
+            out = []
+            for g in cd:
+                out.extend(hang_rows[g].keys() if constrained[g] == 2 else [g])
+            return sorted(set(out) | set(cd))
+        exp_cells = [expand(cell_dofs[c].tolist()) for c in range(ncell)]
+        if isinstance(renumber, str) and renumber == "cm":
+            import scipy.sparse as sp
+            from scipy.sparse.csgraph import reverse_cuthill_mckee
+            rows = np.concatenate([np.repeat(e, len(e)) for e in exp_cells])
+            cols = np.concatenate([np.tile(e, len(e)) for e in exp_cells])
+            Gm = sp.csr_matrix((np.ones(rows.size, dtype=np.int8), (rows, cols)), shape=(self.ndof, self.ndof))
+            Gm.sum_duplicates()
+            perm = reverse_cuthill_mckee(Gm, symmetric_mode=True)[::-1]
+            new_of_old = np.empty(self.ndof, dtype=np.int64)
+            new_of_old[perm] = np.arange(self.ndof)
+        elif isinstance(renumber, str):
+            new_of_old = np.arange(self.ndof)
+        else:
+            new_of_old = np.asarray(renumber)
+        self.new_of_old = new_of_old
+        inv = np.empty_like(new_of_old)
+        inv[new_of_old] = np.arange(self.ndof)
+        self.cell_dofs = np.ascontiguousarray(new_of_old[cell_dofs].astype(np.int32))
+        self.dof_comp = comp[inv]
+        self.dof_coords = coords[dof_node[inv]]
+        self.constrained = np.ascontiguousarray(constrained[inv])
+        self.constraint_value = cvalue[inv]
+        self.periodic_slave = np.zeros(0, dtype=np.int64)
+        self.periodic_master = np.zeros(0, dtype=np.int64)
+        # hanging-node lines in the new numbering, CSR over all dofs
+        ptr, idx, wts = [0], [], []
+        self.hang_inhomogeneity = np.zeros(self.ndof)
+        for g in range(self.ndof):
+            old = int(inv[g])
+            if constrained[old] == 2:
+                for m, w in sorted((int(new_of_old[m]), w) for m, w in hang_rows[old].items()):
+                    idx.append(m)
+                    wts.append(w)
+                self.hang_inhomogeneity[g] = hang_inhom[old]
+            ptr.append(len(idx))
+        self.hang_ptr = np.array(ptr, dtype=np.int64)
+        self.hang_idx = np.array(idx, dtype=np.int32)
+        self.hang_w = np.array(wts, dtype=np.float64)
+        # ---- geometry (affine, two cell sizes) ----
+        hc = size * (H / L)
+        self.cell_invJ = np.ascontiguousarray(np.eye(dim)[None] / hc[:, None, None])
+        self.cell_detJ = hc ** dim
+        self.cell_measure = hc ** dim
+        self.qpoints = np.ascontiguousarray(lo + orig[:, None, :] * (H / L) + fe.xq[None, :, :] * hc[:, None, None])
+        self.cell_idx = None
+        # ---- colours on the expanded cells (greedy), sparsity on them ----
+        new_exp = [np.array(sorted(int(new_of_old[g]) for g in e), dtype=np.int64) for e in exp_cells]
+        used = [set() for _ in range(self.ndof)]
+        color = np.zeros(ncell, dtype=np.int32)
+        for c in range(ncell):
+            k = 0
+            while any(k in used[g] for g in new_exp[c]):
+                k += 1
+            color[c] = k
+            for g in new_exp[c]:
+                used[g].add(k)
+        self.cell_color = color
+        import scipy.sparse as sp
+        rows, cols = [], []
+        for e in new_exp:
+            f = e[self.constrained[e] == 0]
+            rows.append(np.repeat(f, f.size))
+            cols.append(np.tile(f, f.size))
+        rows = np.concatenate(rows + [np.arange(self.ndof)])
+        cols = np.concatenate(cols + [np.arange(self.ndof)])
+        A = sp.csr_matrix((np.ones(rows.size, dtype=np.int8), (rows, cols)), shape=(self.ndof, self.ndof))
+        A.sum_duplicates()
+        A.sort_indices()
+        self.rowptr, self.col = A.indptr.astype(np.int64), A.indices.astype(np.int32)
+
+    def distribute_hanging(self, U, inhomogeneous=True):
+        """AffineConstraints::distribute for the hanging-node lines: x_i = sum w x_master (+ the part
+        that Dirichlet masters contribute in nonzero_constraints)."""
+        U = U.copy()
+        h = np.nonzero(self.constrained == 2)[0]
+        for g in h:
+            s = self.hang_ptr[g], self.hang_ptr[g + 1]
+            U[g] = float(self.hang_w[s[0]:s[1]] @ U[self.hang_idx[s[0]:s[1]]]) + \
+                (self.hang_inhomogeneity[g] if inhomogeneous else 0.0)
+        return U
+
+    def apply_nonzero_constraints(self, U):
+        U = U.copy()
+        m = self.constrained == 1
+        U[m] = self.constraint_value[m]
+        return self.distribute_hanging(U, True)
+
+
 # ----------------------------------------------------------------------------------------------
 # time integration scalars
 # ----------------------------------------------------------------------------------------------
@@ -536,10 +760,13 @@ def assemble(mesh, U, params, assemble_matrix=True, force=None, U1=None, U2=None
     figure), not the reference's literal loop."""
     L = lib()
     L.glso_set_cell_mode(C.c_int(1 if structured else 0))
+    if getattr(mesh, "hang_ptr", None) is not None:
+        L.glso_set_hanging(_p(mesh.hang_ptr, c_i64_p), _p(mesh.hang_idx, c_i32_p), _p(mesh.hang_w, c_double_p))
     try:
         return _assemble(L, mesh, U, params, assemble_matrix, force, U1, U2, U3, return_local, threads)
     finally:
         L.glso_set_cell_mode(C.c_int(0))
+        L.glso_set_hanging(None, None, None)
 
 
 def _assemble(L, mesh, U, params, assemble_matrix, force, U1, U2, U3, return_local, threads):
@@ -744,6 +971,8 @@ def solve_linear_system(mesh, val, rhs, rel=1e-3, abs_=1e-8, max_iters=1000, ilu
     if not ok:
         raise NoConvergence("%s did not converge in %d iterations" % (method, it))
     x[constrained != 0] = 0.0           # zero_constraints.distribute (:1287)
+    if getattr(mesh, "hang_ptr", None) is not None:
+        x = mesh.distribute_hanging(x, inhomogeneous=False)
     return x, it, res
 
 

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libglsns.so")
+LIB_PATH = os.environ.get("GLSNS_LIB", os.path.join(HERE, "libglsns.so"))   # (GLSNS_LIB: a differently tuned build, for experiments)
 
 c_double_p = C.POINTER(C.c_double)
 c_i32_p = C.POINTER(C.c_int32)
@@ -40,7 +40,9 @@ class MeshDesc(C.Structure):
                 ("row_ptr", c_i64_p), ("col_idx", c_i32_p),
                 ("n_colors", C.c_int32), ("color_ptr", c_i32_p), ("color_cells", c_i32_p),
                 ("n_neighbors", C.c_int32), ("neighbor_rank", c_i32_p), ("send_ptr", c_i64_p),
-                ("send_idx", c_i32_p), ("recv_ptr", c_i64_p), ("mapping_laplacian", c_double_p)]
+                ("send_idx", c_i32_p), ("recv_ptr", c_i64_p), ("mapping_laplacian", c_double_p),
+                ("constraint_ptr", c_i64_p), ("constraint_idx", c_i32_p),
+                ("constraint_weight", c_double_p), ("constraint_inhomogeneity", c_double_p)]
 
 
 class LinearSolverParams(C.Structure):

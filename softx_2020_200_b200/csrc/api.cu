@@ -249,6 +249,8 @@ glsns_destroy(glsns_context *ctx)
   ctx->a2p.release();
   ctx->diag_rows.release();
   ctx->grp_first.release();
+  ctx->hang_ptr.release(), ctx->hang_idx.release(), ctx->hang_w.release(), ctx->hang_list.release();
+  ctx->hang_inhom.release();
   ctx->fgroups.release();
   ctx->sgroups.release();
   ctx->rowptr.release();
@@ -365,12 +367,52 @@ glsns_set_mesh(glsns_context *ctx, const glsns_mesh_desc *m)
   else
     ctx->q_points.release();
   GLSNS_TRY(dev_upload(ctx, ctx->constrained, m->constrained, (size_t)m->n_dofs));
+  { // hanging-node lines
+    std::vector<int32_t> hang;
+    for (int64_t i = 0; i < m->n_dofs; ++i)
+      if (m->constrained[i] == 2)
+        hang.push_back((int32_t)i);
+    ctx->n_hanging = (int64_t)hang.size();
+    ctx->hang_ptr.release(), ctx->hang_idx.release(), ctx->hang_w.release(), ctx->hang_list.release();
+    ctx->hang_inhom.release();
+    if (ctx->n_hanging)
+      {
+        if (!m->constraint_ptr || (m->constraint_ptr[m->n_dofs] && (!m->constraint_idx || !m->constraint_weight)))
+          return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "constrained[i] == 2 without constraint_ptr / idx / weight");
+        if (ctx->n_ranks > 1)
+          return fail(ctx, GLSNS_ERR_UNSUPPORTED, "hanging-node constraints on more than one rank");
+        const int64_t ne = m->constraint_ptr[m->n_dofs];
+        for (int64_t k = 0; k < ne; ++k)
+          if (m->constraint_idx[k] < 0 || m->constraint_idx[k] >= m->n_dofs ||
+              m->constrained[m->constraint_idx[k]] != 0)
+            return fail(ctx, GLSNS_ERR_BAD_ARGUMENT,
+                        "a hanging-node line refers to a constrained dof: pass the closed constraints");
+        GLSNS_TRY(dev_upload(ctx, ctx->hang_ptr, m->constraint_ptr, (size_t)m->n_dofs + 1));
+        GLSNS_TRY(dev_alloc(ctx, ctx->hang_idx, (size_t)ne + 1));
+        GLSNS_TRY(dev_alloc(ctx, ctx->hang_w, (size_t)ne + 1));
+        if (ne)
+          {
+            GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->hang_idx.p, m->constraint_idx, sizeof(int32_t) * ne,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+            GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->hang_w.p, m->constraint_weight, sizeof(double) * ne,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+          }
+        GLSNS_TRY(dev_upload(ctx, ctx->hang_list, hang.data(), hang.size()));
+        if (m->constraint_inhomogeneity)
+          GLSNS_TRY(dev_upload(ctx, ctx->hang_inhom, m->constraint_inhomogeneity, (size_t)m->n_dofs));
+        GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `hang` goes out of scope
+      }
+  }
   if (m->constraint_values)
     GLSNS_TRY(dev_upload(ctx, ctx->cvalues, m->constraint_values, (size_t)m->n_dofs));
   else
     ctx->cvalues.release();
   GLSNS_TRY(dev_upload(ctx, ctx->rowptr, m->row_ptr, (size_t)m->n_owned + 1));
-  GLSNS_TRY(dev_upload(ctx, ctx->col, m->col_idx, (size_t)nnz));
+  // (a few elements of padding: bulk copies of the last row's entries round up to 16 bytes)
+  GLSNS_TRY(dev_alloc(ctx, ctx->col, (size_t)nnz + 8));
+  if (nnz)
+    GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->col.p, m->col_idx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice,
+                                    ctx->stream));
   GLSNS_TRY(dev_upload(ctx, ctx->color_cells, m->color_cells, nc));
   ctx->force.release();
   ctx->have_force = false;
@@ -395,7 +437,7 @@ glsns_set_mesh(glsns_context *ctx, const glsns_mesh_desc *m)
   else if (m->n_dofs != m->n_owned && ctx->n_ranks == 1)
     return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "ghost dofs without neighbours");
   // matrix storage, vectors
-  GLSNS_TRY(dev_alloc(ctx, ctx->val, (size_t)std::max<int64_t>(nnz, 1)));
+  GLSNS_TRY(dev_alloc(ctx, ctx->val, (size_t)nnz + 8));
   ctx->lu.release();
   for (int v = 0; v < 7; ++v)
     {
@@ -535,6 +577,8 @@ glsns_assemble_l2_projection(glsns_context *ctx, const double *initial_at_q)
     return fail(ctx, GLSNS_ERR_STATE, "no mesh");
   if (!initial_at_q && ctx->n_cells)
     return fail(ctx, GLSNS_ERR_BAD_ARGUMENT, "null pointer");
+  if (ctx->n_hanging)
+    return fail(ctx, GLSNS_ERR_UNSUPPORTED, "assemble_L2_projection with hanging-node constraints");
   glsns::DevBuf<double> init;
   GLSNS_TRY(dev_upload(ctx, init, initial_at_q,
                        (size_t)ctx->n_cells * ctx->n_q * (ctx->dim + 1)));

@@ -52,6 +52,10 @@ namespace glsns
       const uint8_t *constrained;
       const int64_t *rowptr, *diag_pos;
       const int32_t *col;
+      // hanging-node lines (null: none): dof i with constrained[i] == 2 stands for its masters
+      const int64_t *hang_ptr;
+      const int32_t *hang_idx;
+      const double  *hang_w;
       // state
       const double *U, *U1, *U2, *U3;
       // parameters
@@ -102,11 +106,17 @@ namespace glsns
       int32_t *sCon = sDof + n;                  // [n]
 
       // ---- phase 0: element dofs and nodal values ----
+      __shared__ int sHang; // does the cell have a dof with a hanging-node line?
+      if (tid == 0)
+        sHang = 0;
+      __syncthreads();
       for (int k = tid; k < n; k += nt)
         {
           const int32_t g = A.cell_dofs[cell * n + k];
           sDof[k]         = g;
           sCon[k]         = A.constrained[g];
+          if (sCon[k] == 2)
+            sHang = 1;
           sU[k]           = A.U[g];
           double ud       = 0;
           if (A.transient)
@@ -363,7 +373,7 @@ namespace glsns
       for (int i = tid; i < n; i += nt)
         {
           const int32_t gi = sDof[i];
-          if (sCon[i] || gi >= A.n_owned)
+          if (sCon[i] == 1 || (sCon[i] == 2 && !A.hang_ptr) || gi >= A.n_owned)
             continue;
           double s = 0;
           if (i < DIM * n_su)
@@ -395,7 +405,13 @@ namespace glsns
                   s += Q[Q_JXW] * (-Q[Q_DIVU] * sNp[q * n_sp + a] - Q[Q_TAU] * Rg);
                 }
             }
-          A.rhs[gi] += s;
+          if (!sHang)
+            A.rhs[gi] += s; // (cells of one colour share no dof)
+          else if (sCon[i] == 0)
+            atomicAdd(A.rhs + gi, s); // (a master of a hanging dof of this very cell may be gi)
+          else
+            for (int64_t k = A.hang_ptr[gi]; k < A.hang_ptr[gi + 1]; ++k)
+              atomicAdd(A.rhs + A.hang_idx[k], A.hang_w[k] * s);
         }
 
       // ---- phase 6: Jacobian blocks (:519-625) and scatter (:755-771) ----
@@ -506,76 +522,74 @@ namespace glsns
                     }
                 }
 
-              // scatter: constrained row keeps |local(i,i)| on its diagonal, couplings
-              // to constrained columns are dropped
+              // scatter (AffineConstraints::distribute_local_to_global, :755-771): a constrained
+              // row keeps |local(i,i)| on its diagonal, couplings to Dirichlet columns are
+              // dropped; a dof with a hanging-node line stands for its masters, row and column
+              auto put = [&](const int i, const int j, const double v) {
+                const int32_t gi = sDof[i];
+                if (gi >= A.n_owned)
+                  return;
+                if (!sHang)
+                  { // no hanging node in the cell: plain read-modify-write (coloured cells)
+                    if (sCon[i])
+                      {
+                        if (i == j)
+                          A.val[A.diag_pos[gi]] += fabs(v);
+                        return;
+                      }
+                    if (!sCon[j])
+                      A.val[find_col(A.col, sRow[2 * i], sRow[2 * i + 1], sDof[j])] += v;
+                    return;
+                  }
+                // a cell with hanging nodes: two of its entries may land on one matrix entry
+                // (a master is often a dof of the same cell), hence atomics
+                if (sCon[i] && i == j)
+                  atomicAdd(A.val + A.diag_pos[gi], fabs(v));
+                if (sCon[i] == 1 || sCon[j] == 1)
+                  return;
+                const int32_t gj = sDof[j];
+                const int64_t ib = sCon[i] == 2 ? A.hang_ptr[gi] : 0, ie = sCon[i] == 2 ? A.hang_ptr[gi + 1] : 1;
+                const int64_t jb = sCon[j] == 2 ? A.hang_ptr[gj] : 0, je = sCon[j] == 2 ? A.hang_ptr[gj + 1] : 1;
+                for (int64_t ki = ib; ki < ie; ++ki)
+                  {
+                    const int32_t ri = sCon[i] == 2 ? A.hang_idx[ki] : gi;
+                    const double  wi = sCon[i] == 2 ? A.hang_w[ki] : 1.0;
+                    const int64_t rs = A.rowptr[ri], re = A.rowptr[ri + 1];
+                    for (int64_t kj = jb; kj < je; ++kj)
+                      {
+                        const int32_t cj = sCon[j] == 2 ? A.hang_idx[kj] : gj;
+                        const double  wj = sCon[j] == 2 ? A.hang_w[kj] : 1.0;
+                        atomicAdd(A.val + find_col(A.col, rs, re, cj), wi * wj * v);
+                      }
+                  }
+              };
               if (au)
                 {
 #pragma unroll
                   for (int ci = 0; ci < DIM; ++ci)
                     {
-                      const int     i  = ci * n_su + a;
-                      const int32_t gi = sDof[i];
-                      if (gi >= A.n_owned)
-                        continue;
-                      if (sCon[i])
-                        {
-                          if (bu && a == b)
-                            A.val[A.diag_pos[gi]] += fabs(uu[ci][ci]);
-                          continue;
-                        }
-                      const int64_t rs = sRow[2 * i], re = sRow[2 * i + 1];
+                      const int i = ci * n_su + a;
                       if (bu)
                         {
 #pragma unroll
                           for (int cj = 0; cj < DIM; ++cj)
-                            {
-                              const int j = cj * n_su + b;
-                              if (sCon[j])
-                                continue;
-                              A.val[find_col(A.col, rs, re, sDof[j])] += uu[ci][cj];
-                            }
+                            put(i, cj * n_su + b, uu[ci][cj]);
                         }
                       if (bp)
-                        {
-                          const int j = DIM * n_su + b;
-                          if (!sCon[j])
-                            A.val[find_col(A.col, rs, re, sDof[j])] += up[ci];
-                        }
+                        put(i, DIM * n_su + b, up[ci]);
                     }
                 }
               if (ap)
                 {
-                  const int     i  = DIM * n_su + a;
-                  const int32_t gi = sDof[i];
-                  if (gi < A.n_owned)
+                  const int i = DIM * n_su + a;
+                  if (bu)
                     {
-                      if (sCon[i])
-                        {
-                          if (bp && a == b)
-                            A.val[A.diag_pos[gi]] += fabs(pp);
-                        }
-                      else
-                        {
-                          const int64_t rs = sRow[2 * i], re = sRow[2 * i + 1];
-                          if (bu)
-                            {
 #pragma unroll
-                              for (int cj = 0; cj < DIM; ++cj)
-                                {
-                                  const int j = cj * n_su + b;
-                                  if (sCon[j])
-                                    continue;
-                                  A.val[find_col(A.col, rs, re, sDof[j])] += pu[cj];
-                                }
-                            }
-                          if (bp)
-                            {
-                              const int j = DIM * n_su + b;
-                              if (!sCon[j])
-                                A.val[find_col(A.col, rs, re, sDof[j])] += pp;
-                            }
-                        }
+                      for (int cj = 0; cj < DIM; ++cj)
+                        put(i, cj * n_su + b, pu[cj]);
                     }
+                  if (bp)
+                    put(i, DIM * n_su + b, pp);
                 }
             }
         }
@@ -790,6 +804,8 @@ namespace glsns
     A.n_owned     = ctx->n_owned;
     A.constrained = ctx->constrained.p;
     A.rowptr = ctx->rowptr.p, A.diag_pos = ctx->diag_pos.p, A.col = ctx->col.p;
+    A.hang_ptr = ctx->n_hanging ? ctx->hang_ptr.p : nullptr;
+    A.hang_idx = ctx->hang_idx.p, A.hang_w = ctx->hang_w.p;
     A.U  = ctx->vec[GLSNS_VEC_EVALUATION_POINT].p;
     A.U1 = ctx->vec_set[GLSNS_VEC_SOLUTION_M1] ? ctx->vec[GLSNS_VEC_SOLUTION_M1].p : nullptr;
     A.U2 = ctx->vec_set[GLSNS_VEC_SOLUTION_M2] ? ctx->vec[GLSNS_VEC_SOLUTION_M2].p : nullptr;

@@ -125,6 +125,12 @@ struct glsns_context
   glsns::DevBuf<int64_t> rowptr, diag_pos;
   glsns::DevBuf<double>  inv_jac, det_jac, measure, q_points, force, cvalues, map_lap;
   glsns::DevBuf<uint8_t> constrained;
+  // hanging-node lines (glsns_mesh_desc::constraint_*): CSR over the dofs, the list of the
+  // hanging dofs, their inhomogeneities (may be empty)
+  int64_t                n_hanging = 0;
+  glsns::DevBuf<int64_t> hang_ptr;
+  glsns::DevBuf<int32_t> hang_idx, hang_list;
+  glsns::DevBuf<double>  hang_w, hang_inhom;
   glsns::DevBuf<int2>    fgroups; // (first row, rows) of the row groups, by lower-sweep level
   glsns::DevBuf<int2>    sgroups; // every row in a group (diagonal-only rows too), by row: SpMV
   int64_t                n_sgroups = 0;

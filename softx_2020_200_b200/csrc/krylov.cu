@@ -228,6 +228,24 @@ namespace glsns
         eval[t] = constrained[t] ? (cvalues ? cvalues[t] : 0.0) : present[t] + alpha * update[t];
     }
 
+    // AffineConstraints::distribute for the hanging-node lines: x_i = sum_k w_k x_{m_k} (+ g_i);
+    // the masters are unconstrained dofs, so one pass after the Dirichlet values is enough
+    __global__ void __launch_bounds__(VB)
+    distribute_hanging_kernel(const int64_t n_hanging, const int32_t *__restrict__ list,
+                              const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                              const double *__restrict__ w, const double *__restrict__ inhom,
+                              double *__restrict__ x)
+    {
+      const int64_t t = (int64_t)blockIdx.x * VB + threadIdx.x;
+      if (t >= n_hanging)
+        return;
+      const int32_t i = list[t];
+      double        s = inhom ? inhom[i] : 0.0;
+      for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k)
+        s += w[k] * x[idx[k]];
+      x[i] = s;
+    }
+
     int
     vec_grid(const glsns_context *ctx, int64_t n)
     {
@@ -294,6 +312,21 @@ namespace glsns
     return GLSNS_OK;
   }
 
+  // hanging dofs of x <- their lines (inhomogeneous: with the share of the Dirichlet masters)
+  static glsns_status
+  launch_distribute_hanging(glsns_context *ctx, double *x, bool inhomogeneous)
+  {
+    if (!ctx->n_hanging)
+      return GLSNS_OK;
+    distribute_hanging_kernel<<<(unsigned)((ctx->n_hanging + VB - 1) / VB), VB, 0, ctx->stream>>>(
+      ctx->n_hanging, ctx->hang_list.p, ctx->hang_ptr.p, ctx->hang_idx.p, ctx->hang_w.p,
+      inhomogeneous ? ctx->hang_inhom.p : nullptr, x);
+    ctx->kernel_launches++;
+    GLSNS_CUDA(ctx, cudaGetLastError());
+    return GLSNS_OK;
+  }
+
+  // zero_constraints.distribute(x)
   glsns_status
   launch_zero_constrained(glsns_context *ctx, double *x)
   {
@@ -301,7 +334,7 @@ namespace glsns
     zero_constrained_kernel<<<vec_grid(ctx, n), VB, 0, ctx->stream>>>(n, ctx->constrained.p, x);
     ctx->kernel_launches++;
     GLSNS_CUDA(ctx, cudaGetLastError());
-    return GLSNS_OK;
+    return launch_distribute_hanging(ctx, x, false);
   }
 
   glsns_status
@@ -311,7 +344,7 @@ namespace glsns
                                                                 ctx->cvalues.p, x);
     ctx->kernel_launches++;
     GLSNS_CUDA(ctx, cudaGetLastError());
-    return GLSNS_OK;
+    return launch_distribute_hanging(ctx, x, true);
   }
 
   glsns_status
@@ -323,6 +356,7 @@ namespace glsns
       ctx->constrained.p, ctx->cvalues.p, ctx->vec[GLSNS_VEC_EVALUATION_POINT].p);
     ctx->kernel_launches++;
     GLSNS_CUDA(ctx, cudaGetLastError());
+    GLSNS_TRY(launch_distribute_hanging(ctx, ctx->vec[GLSNS_VEC_EVALUATION_POINT].p, true));
     return halo_exchange(ctx, ctx->vec[GLSNS_VEC_EVALUATION_POINT].p);
   }
 

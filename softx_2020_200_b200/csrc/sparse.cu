@@ -76,7 +76,8 @@ namespace glsns
     // consecutive nonzeros.  Measured and rejected in round 2 (64^3 cells, 4.70 ms as is):
     // requesting the next group's first 64 entries before the reduction (80 registers, three
     // CTAs per SM instead of five: 5.89 ms); the four totals reduced together in 6 shuffles
-    // with the register count held at 48 by __launch_bounds__(256, 5) (7.54 ms).
+    // with the register count held at 48 by __launch_bounds__(256, 5) (7.54 ms).  What did
+    // help is further down: spmv_stream_kernel, used for the large matrices.
     template <int TPG>
     __global__ void __launch_bounds__(256)
     spmv_groups_kernel(const int32_t n_groups, const int2 *__restrict__ groups,
@@ -153,6 +154,290 @@ namespace glsns
               if (lane == 0 && a < m)
                 y[r0 + a] = t;
             }
+        }
+    }
+
+    // ---- the same product with the matrix STREAMED through shared memory ----
+    // spmv_groups_kernel keeps its loads in registers: two entries per lane and row in flight,
+    // 40 warps per SM, and nothing in flight while a group's totals are reduced -- 81 % of the
+    // measured HBM peak on the algorithmic bytes at 64^3 cells, 66 % on the bytes it really
+    // moves.  Here one lane per warp moves whole pieces of a group (<= 256 entries per row: the
+    // indices once and the entries of its <= 4 rows, five bulk copies completing on one
+    // mbarrier) into a ring of two slots per warp, 12 warps per SM: up to 24 pieces of 9 KB in
+    // flight per SM whatever the other lanes are doing.  The x entries of a piece are gathered as
+    // soon as its indices have arrived, one piece ahead of the products; group descriptors are
+    // read 32 at a time, one per lane.  The stream is marked evict-first in L2, which is left
+    // to x.  Bulk copies need 16-byte alignment and rows start anywhere, so a copy starts at the
+    // aligned address below its first entry and the reader skips the slack (the value and index
+    // arrays are allocated with a few elements of padding for the last row).
+    // Measured at 64^3 cells (2.06e9 non-zeros), ms per product: 8 warps x 3 slots 4.42,
+    // 8 x 4 slots of 192 entries 5.97, 16 x 3 slots of 128 entries 4.50, **12 x 2 slots 4.17**
+    // (spmv_groups_kernel 4.72): 0.91 of the HBM peak on the algorithmic bytes.  At 32^3 cells
+    // it is 3 % slower than spmv_groups_kernel (0.56 vs 0.54 ms), so launch_spmv takes it for
+    // matrices of 5e8 non-zeros and more (GLSNS_SPMV_STREAM=0/1 forces either).
+#ifndef GLSNS_SS_WARPS
+#define GLSNS_SS_WARPS 12
+#endif
+#ifndef GLSNS_SS_SLOTS
+#define GLSNS_SS_SLOTS 2
+#endif
+#ifndef GLSNS_SS_CH
+#define GLSNS_SS_CH 256
+#endif
+    constexpr int SS_WARPS = GLSNS_SS_WARPS, SS_SLOTS = GLSNS_SS_SLOTS, SS_CH = GLSNS_SS_CH;
+    constexpr int SS_COLB  = 4 * SS_CH + 16;       // bytes of a slot's index part
+    constexpr int SS_ROWB  = 8 * SS_CH + 16;       // bytes of one row of a slot's value part
+    constexpr int SS_SLOTB = SS_COLB + 4 * SS_ROWB; // 9296
+
+    __device__ __forceinline__ void
+    ss_mbar_init(void *bar, int count)
+    {
+      const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    }
+    __device__ __forceinline__ void
+    ss_mbar_expect_tx(void *bar, unsigned bytes)
+    {
+      const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ bool
+    ss_mbar_try_wait(void *bar, unsigned parity)
+    {
+      const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+      unsigned       ok;
+      asm volatile("{\n\t.reg .pred p;\n\t"
+                   "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                   "selp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok)
+                   : "r"(a), "r"(parity)
+                   : "memory");
+      return ok != 0;
+    }
+    __device__ __forceinline__ void
+    ss_bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, void *bar, unsigned long long policy)
+    {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+      const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+                   "[%0], [%1], %2, [%3], %4;" ::"r"(d),
+                   "l"(gsrc), "r"(bytes), "r"(b), "l"(policy)
+                   : "memory");
+    }
+
+    struct SsPiece // what the consumer needs to know about the piece in a slot (32 bytes)
+    {
+      int64_t rs;
+      int32_t r0, m, len, off, cnt, last;
+    };
+
+    __global__ void __launch_bounds__(SS_WARPS * 32, 1)
+    spmv_stream_kernel(const int32_t n_groups, const int2 *__restrict__ groups,
+                       const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                       const double *__restrict__ val, const double *__restrict__ x,
+                       double *__restrict__ y)
+    {
+      extern __shared__ __align__(128) unsigned char ss_smem[];
+      const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      unsigned char *ring = ss_smem + (size_t)warp * SS_SLOTS * SS_SLOTB;
+      unsigned char *tail = ss_smem + (size_t)SS_WARPS * SS_SLOTS * SS_SLOTB;
+      unsigned long long *bars = reinterpret_cast<unsigned long long *>(tail) + warp * SS_SLOTS;
+      SsPiece *info = reinterpret_cast<SsPiece *>(tail + 8 * SS_WARPS * SS_SLOTS) + warp * SS_SLOTS;
+      const int64_t W = (int64_t)gridDim.x * SS_WARPS, wid = (int64_t)blockIdx.x * SS_WARPS + warp;
+      unsigned long long policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      // the warp's groups are wid, wid + W, ...; their descriptors are read 32 at a time, one
+      // per lane (two dependent loads per batch instead of per group)
+      int64_t batch0 = wid;       // group of lane 0 in the batch
+      int     bi     = 32;        // next entry of the batch to hand out (32: batch used up)
+      int     d_r0 = 0, d_m = 0, d_len = 0;
+      int64_t d_rs = 0;
+      int64_t n_mine = wid < n_groups ? (n_groups - 1 - wid) / W + 1 : 0; // groups of this warp
+      int64_t gi     = 0;         // groups handed out so far
+      auto next_group = [&](int &r0, int &m, int64_t &rs, int &len) {
+        if (bi == 32)
+          {
+            const int64_t g = batch0 + (int64_t)lane * W;
+            if (g < n_groups)
+              {
+                const int2 gr = groups[g];
+                d_r0 = gr.x, d_m = gr.y;
+                d_rs  = rowptr[gr.x];
+                d_len = (int)(rowptr[gr.x + 1] - d_rs);
+              }
+            batch0 += 32 * W;
+            bi = 0;
+          }
+        r0  = __shfl_sync(0xffffffffu, d_r0, bi);
+        m   = __shfl_sync(0xffffffffu, d_m, bi);
+        rs  = __shfl_sync(0xffffffffu, d_rs, bi);
+        len = __shfl_sync(0xffffffffu, d_len, bi);
+        ++bi, ++gi;
+      };
+      // producer position: the current group and the chunk of it to issue next
+      int     p_r0 = 0, p_m = 0, p_len = 0, p_ch = 0, p_nch = 0;
+      int64_t p_rs = 0;
+      bool    p_valid = false;
+      auto producer_step = [&](const int s) -> bool { // issue the next piece into slot s
+        if (!p_valid || p_ch == p_nch)
+          {
+            if (gi >= n_mine)
+              return false;
+            next_group(p_r0, p_m, p_rs, p_len);
+            p_nch = max(1, (p_len + SS_CH - 1) / SS_CH), p_ch = 0, p_valid = true;
+          }
+        if (lane == 0)
+          {
+            unsigned char *S   = ring + (size_t)s * SS_SLOTB;
+            const int      off = p_ch * SS_CH, cnt = min(SS_CH, p_len - off);
+            const int64_t  c0 = p_rs + off, c0a = c0 & ~(int64_t)3;
+            const unsigned cb = (unsigned)(((c0 - c0a + cnt) * 4 + 15) & ~15);
+            unsigned       total = cb, vb[4];
+            int64_t        v0a[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              {
+                const int64_t v0 = p_rs + (int64_t)a * p_len + off;
+                v0a[a]           = v0 & ~(int64_t)1;
+                vb[a]            = a < p_m ? (unsigned)(((v0 - v0a[a] + cnt) * 8 + 15) & ~15) : 0u;
+                total += vb[a];
+              }
+            SsPiece pc;
+            pc.rs = p_rs, pc.r0 = p_r0, pc.m = p_m, pc.len = p_len, pc.off = off, pc.cnt = cnt;
+            pc.last = p_ch + 1 == p_nch;
+            info[s] = pc;
+            ss_mbar_expect_tx(bars + s, total);
+            ss_bulk_load(S, col + c0a, cb, bars + s, policy);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (a < p_m)
+                ss_bulk_load(S + SS_COLB + a * SS_ROWB, val + v0a[a], vb[a], bars + s, policy);
+          }
+        ++p_ch;
+        return true;
+      };
+      if (lane == 0)
+        {
+          for (int s = 0; s < SS_SLOTS; ++s)
+            ss_mbar_init(bars + s, 1);
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+      __syncwarp();
+      int64_t n_issued = 0, n_done = 0;
+      for (int s = 0; s < SS_SLOTS; ++s)
+        if (producer_step(s))
+          ++n_issued;
+      __syncwarp();
+      int      slot  = 0;
+      unsigned phase = 0;
+      double   acc[4] = {0, 0, 0, 0};
+      // the x entries of a piece are requested one piece ahead (as soon as its indices have
+      // arrived), so that their trip through L2 overlaps the products of the piece before it
+      double xb[2][SS_CH / 32]; // two register sets, selected at compile time by the unrolled loop
+      bool   have_x = false;
+      auto gather = [&](const int s, double (&out)[SS_CH / 32]) {
+        const SsPiece        pc = info[s];
+        const unsigned char *S  = ring + (size_t)s * SS_SLOTB;
+        const int32_t *sc = reinterpret_cast<const int32_t *>(S) + (int)((pc.rs + pc.off) & 3);
+#pragma unroll
+        for (int u = 0; u < SS_CH / 32; ++u)
+          {
+            const int k = lane + 32 * u;
+            out[u]      = k < pc.cnt ? __ldg(x + sc[k]) : 0.0;
+          }
+      };
+      auto piece = [&](auto CUR) {
+        constexpr int cur = decltype(CUR)::value, nxt = 1 - cur;
+        while (!ss_mbar_try_wait(bars + slot, phase))
+          ;
+        const SsPiece        pc = info[slot];
+        const unsigned char *S  = ring + (size_t)slot * SS_SLOTB;
+        const double        *sv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          sv[a] = reinterpret_cast<const double *>(S + SS_COLB + a * SS_ROWB) +
+                  (int)((pc.rs + (int64_t)a * pc.len + pc.off) & 1);
+        if (!have_x)
+          gather(slot, xb[cur]);
+        const int      ns = slot + 1 == SS_SLOTS ? 0 : slot + 1;
+        const unsigned np = phase ^ (unsigned)(ns == 0);
+        have_x            = n_done + 1 < n_issued && ss_mbar_try_wait(bars + ns, np);
+        if (have_x)
+          gather(ns, xb[nxt]);
+        if (pc.m == 4)
+          {
+#pragma unroll
+            for (int u = 0; u < SS_CH / 32; ++u)
+              {
+                const int k = lane + 32 * u;
+                if (k < pc.cnt)
+                  {
+                    acc[0] += sv[0][k] * xb[cur][u];
+                    acc[1] += sv[1][k] * xb[cur][u];
+                    acc[2] += sv[2][k] * xb[cur][u];
+                    acc[3] += sv[3][k] * xb[cur][u];
+                  }
+              }
+          }
+        else
+          {
+#pragma unroll
+            for (int u = 0; u < SS_CH / 32; ++u)
+              {
+                const int k = lane + 32 * u;
+                if (k < pc.cnt)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    if (a < pc.m)
+                      acc[a] += sv[a][k] * xb[cur][u];
+              }
+          }
+        __syncwarp(); // every lane is done with the slot (and its record) before it is refilled
+        if (producer_step(slot))
+          ++n_issued;
+        if (pc.last)
+          { // the group is complete: its totals
+            if (pc.m == 4)
+              { // four totals over 32 lanes in 6 shuffles (lanes 8 a .. 8 a + 7 end with row a's)
+                const bool h16 = lane & 16, h8 = lane & 8;
+                double     k0 = h16 ? acc[2] : acc[0], k1 = h16 ? acc[3] : acc[1];
+                k0 += __shfl_xor_sync(0xffffffffu, h16 ? acc[0] : acc[2], 16);
+                k1 += __shfl_xor_sync(0xffffffffu, h16 ? acc[1] : acc[3], 16);
+                double tot = (h8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+                tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+                tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                if ((lane & 7) == 0)
+                  y[pc.r0 + (lane >> 3)] = tot;
+              }
+            else
+              {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                  {
+                    double t = acc[a];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                      t += __shfl_down_sync(0xffffffffu, t, o);
+                    if (lane == 0 && a < pc.m)
+                      y[pc.r0 + a] = t;
+                  }
+              }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              acc[a] = 0;
+          }
+        ++n_done;
+        slot  = ns;
+        phase = np;
+        __syncwarp();
+      };
+      while (n_done < n_issued)
+        {
+          piece(std::integral_constant<int, 0>());
+          if (n_done < n_issued)
+            piece(std::integral_constant<int, 1>());
         }
     }
 
@@ -828,7 +1113,18 @@ namespace glsns
     const int block = 256;
     const int tpr   = ctx->avg_row_len >= 96 ? 32 : ctx->avg_row_len >= 40 ? 16 : 8;
     static const bool by_rows = getenv("GLSNS_SPMV_BY_ROWS") != nullptr;
-    if (ctx->n_sgroups > 0 && !by_rows)
+    static const int stream_env = getenv("GLSNS_SPMV_STREAM") ? atoi(getenv("GLSNS_SPMV_STREAM")) : -1;
+    const bool       streamed   = stream_env >= 0 ? stream_env != 0 : ctx->nnz >= 500000000ll;
+    if (ctx->n_sgroups > 0 && !by_rows && streamed)
+      {
+        const size_t smem = (size_t)SS_WARPS * SS_SLOTS * SS_SLOTB + (size_t)SS_WARPS * SS_SLOTS * (8 + sizeof(SsPiece));
+        GLSNS_CUDA(ctx, cudaFuncSetAttribute(spmv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem));
+        const int grid = (int)std::min<int64_t>((ctx->n_sgroups + SS_WARPS - 1) / SS_WARPS, ctx->n_sm);
+        spmv_stream_kernel<<<grid, SS_WARPS * 32, smem, ctx->stream>>>(
+          (int32_t)ctx->n_sgroups, ctx->sgroups.p, ctx->rowptr.p, ctx->col.p, ctx->val.p, x, y);
+      }
+    else if (ctx->n_sgroups > 0 && !by_rows)
       {
         const int64_t ng   = ctx->n_sgroups;
         const int64_t want = (ng * tpr + block - 1) / block;
@@ -1046,7 +1342,7 @@ namespace glsns
     // values: installed pattern -> host pattern -> new pattern
     DevBuf<double> base_val, new_val;
     GLSNS_TRY(dev_alloc(ctx, base_val, (size_t)std::max<int64_t>(nnz_b, 1)));
-    GLSNS_TRY(dev_alloc(ctx, new_val, (size_t)std::max<int64_t>(nnz_p, 1)));
+    GLSNS_TRY(dev_alloc(ctx, new_val, (size_t)nnz_p + 8));
     const unsigned gb = (unsigned)((nnz_b + 255) / 256);
     if (nnz_b)
       {
@@ -1090,7 +1386,10 @@ namespace glsns
     ctx->lu.release();
     ctx->nnz = nnz_p;
     GLSNS_TRY(dev_upload(ctx, ctx->rowptr, nrow, (size_t)n + 1));
-    GLSNS_TRY(dev_upload(ctx, ctx->col, ncol, (size_t)nnz_p));
+    GLSNS_TRY(dev_alloc(ctx, ctx->col, (size_t)nnz_p + 8)); // (padding: see glsns_set_mesh)
+    if (nnz_p)
+      GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->col.p, ncol, sizeof(int32_t) * nnz_p, cudaMemcpyHostToDevice,
+                                      ctx->stream));
     GLSNS_TRY(ilu_analyse(ctx, nrow, ncol));
     GLSNS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->epoch    = 0;

@@ -89,7 +89,8 @@ class GLSHotPath:
     def set_mesh(self, n_dofs, cell_dofs, inv_jacobian, det_jacobian, cell_measure, constrained,
                  row_ptr, col_idx, color_ptr, color_cells, q_points=None, constraint_values=None,
                  geometry_per_q=False, n_owned=None, neighbor_rank=None, send_ptr=None,
-                 send_idx=None, recv_ptr=None, mapping_laplacian=None):
+                 send_idx=None, recv_ptr=None, mapping_laplacian=None, constraint_ptr=None,
+                 constraint_idx=None, constraint_weight=None, constraint_inhomogeneity=None):
         n_owned = n_dofs if n_owned is None else n_owned
         cd = _c(cell_dofs, np.int32)
         keep = dict(
@@ -99,7 +100,9 @@ class GLSHotPath:
             rp=_c(row_ptr, np.int64), ci=_c(col_idx, np.int32), cp=_c(color_ptr, np.int32),
             cc=_c(color_cells, np.int32), nr=_c(neighbor_rank, np.int32),
             sp=_c(send_ptr, np.int64), si=_c(send_idx, np.int32), rv=_c(recv_ptr, np.int64),
-            ml=_c(mapping_laplacian, np.float64))
+            ml=_c(mapping_laplacian, np.float64), hp=_c(constraint_ptr, np.int64),
+            hi=_c(constraint_idx, np.int32), hw=_c(constraint_weight, np.float64),
+            hg=_c(constraint_inhomogeneity, np.float64))
         n_cells = cd.shape[0] if cd.ndim == 2 else cd.size // self.n_loc
         assert keep["rp"].size == n_owned + 1 and keep["con"].size == n_dofs
         m = MeshDesc(n_dofs, n_owned, n_cells, _ptr(cd, c_i32_p), 1 if geometry_per_q else 0,
@@ -111,7 +114,9 @@ class GLSHotPath:
                      _ptr(keep["cc"], c_i32_p),
                      0 if neighbor_rank is None else len(keep["nr"]), _ptr(keep["nr"], c_i32_p),
                      _ptr(keep["sp"], c_i64_p), _ptr(keep["si"], c_i32_p),
-                     _ptr(keep["rv"], c_i64_p), _ptr(keep["ml"], c_double_p))
+                     _ptr(keep["rv"], c_i64_p), _ptr(keep["ml"], c_double_p),
+                     _ptr(keep["hp"], c_i64_p), _ptr(keep["hi"], c_i32_p), _ptr(keep["hw"], c_double_p),
+                     _ptr(keep["hg"], c_double_p))
         self._check(self._L.glsns_set_mesh(self._ctx, C.byref(m)))
         self.n_dofs, self.n_owned, self.n_cells = n_dofs, n_owned, n_cells
         self.nnz = int(keep["rp"][-1])

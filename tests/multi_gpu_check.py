@@ -95,7 +95,7 @@ def check(n, world, rank, local, dist, verbose=True):
             o = np.argsort(col_g[rp[i]:rp[i + 1]])
             ref = a_ref[om.rowptr[i]:om.rowptr[i + 1]]
             err_a = max(err_a, np.max(np.abs(a_loc[rp[i]:rp[i + 1]][o] - ref)) / max(np.max(np.abs(ref)), 1e-300))
-        print("multi_gpu_check world=%d n=%d: matrix err %.2e rhs err %.2e | GMRES %d (oracle, %d "
+        (print if verbose else (lambda *a: None))("multi_gpu_check world=%d n=%d: matrix err %.2e rhs err %.2e | GMRES %d (oracle, %d "
               "blocks: %d) update err %.2e | ||rhs|| %.6e (oracle %.6e) -> %.3e"
               % (world, n, err_a, err_b, info["iterations"], world, its_ref, err_x, norm,
                  np.linalg.norm(b_ref), res1))

@@ -264,6 +264,52 @@ def test_restart_01_golden_on_gpu(oracle):
     hp.close()
 
 
+HANGING = [  # dim, n, pu, pp, refined region
+    (2, 4, 1, 1, lambda c: (c[:, 0] > 0) & (c[:, 1] < 0.5)),
+    (2, 4, 2, 2, lambda c: (c[:, 0] > 0) & (c[:, 1] < 0.5)),
+    (2, 5, 2, 1, lambda c: np.abs(c[:, 0]) + np.abs(c[:, 1]) < 0.7),
+    (3, 3, 1, 1, lambda c: (c[:, 0] > 0) & (c[:, 1] < 0.3) & (c[:, 2] > -0.4)),
+    (3, 2, 2, 2, lambda c: (c[:, 0] > 0) & (c[:, 1] < 0.3) & (c[:, 2] > -0.4))]
+
+
+@pytest.mark.parametrize("dim,n,pu,pp,refine", HANGING)
+def test_hanging_node_constraints_against_oracle(oracle, dim, n, pu, pp, refine):
+    """A box with a once-refined region (what Kelly refinement produces, examples/03-cylinder and
+    04-ribbon_mixer; navier_stokes_base.cc:610-729): the hanging-node lines resolved in the scatter
+    as AffineConstraints::distribute_local_to_global does (gls_navier_stokes.cc:755-771) -- matrix
+    and right-hand side entry by entry against the oracle, steady and BDF2 -- and distributed after
+    the solve and in the line search: a Newton solve of a flow that lies in the finite element
+    space (Couette for Q1, Poiseuille for Q2) is reproduced to rounding on the non-conforming mesh."""
+    nu = 0.7
+    if pu == 1:
+        shear = (lambda x: x[:, 1]) if dim == 2 else (lambda x: x[:, 1] + 0.5 * x[:, 2])
+    else:
+        shear = lambda x: 1 - x[:, 1] ** 2
+    bc = lambda x: np.stack([shear(x)] + [0 * x[:, 0]] * (dim - 1), axis=1)
+    mesh = oracle.RefinedBoxMesh(dim, n, pu, pp, refine, bcs={None: ("function", bc)})
+    assert (mesh.constrained == 2).sum() > 0
+    hp = hotpath_from_oracle_mesh(mesh, nu, None)
+    _check_assembly(oracle, mesh, hp, random_state(mesh, scale=0.4), "steady", None, (None,) * 3, None, nu)
+    _check_assembly(oracle, mesh, hp, random_state(mesh, 5, 0.4), "bdf2", [0.05, 0.05, 0.05],
+                    (random_state(mesh, 6, 0.4), random_state(mesh, 7, 0.4), None), None, nu)
+    U0 = mesh.apply_nonzero_constraints(np.zeros(mesh.ndof))
+    lin = dict(rel=1e-10, abs_=1e-14, max_iters=3000, ilu_atol=1e-10)
+    log_ref, log = [], []
+    U_ref, it_ref, _ = oracle.newton_solve(mesh, U0, oracle.scheme_params("steady", None, nu), None,
+                                           tol=1e-11, max_it=15, lin=lin, log=log_ref)
+    U, it, res = _newton_gpu(hp, mesh, U0, tol=1e-11, max_it=15, log=log,
+                             lin=dict(relative_residual=1e-10, minimum_residual=1e-14,
+                                      max_iterations=3000, ilu_atol=1e-10))
+    assert res <= 1e-11 and it == it_ref
+    for (k, _), (k_ref, _) in zip(log, log_ref):
+        assert abs(k - k_ref) <= 2
+    vel = mesh.dof_comp < dim
+    exact = np.where(mesh.dof_comp == 0, shear(mesh.dof_coords), 0.0)
+    assert np.max(np.abs(U[vel] - exact[vel])) <= 1e-10          # the flow is in the FE space
+    assert np.max(np.abs(U - U_ref)) <= 1e-9 * np.max(np.abs(U_ref))
+    hp.close()
+
+
 def test_taylor_couette_curved_q2_cells_on_gpu(oracle):
     """examples/02-taylor-couette's geometry (MappingQ(2) on every cell of a hyper_shell,
     taylorcouette_gls.prm with `qmapping all = true`): Jacobian and residual entries of the CUDA

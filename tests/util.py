@@ -14,7 +14,11 @@ def hotpath_from_oracle_mesh(mesh, viscosity=1.0, force=None, srf=False, omega=(
                 mesh.constrained, mesh.rowptr, mesh.col, ptr, order, q_points=mesh.qpoints,
                 constraint_values=mesh.constraint_value,
                 geometry_per_q=getattr(mesh, "geometry_per_q", False),
-                mapping_laplacian=getattr(mesh, "map_lap", None))
+                mapping_laplacian=getattr(mesh, "map_lap", None),
+                constraint_ptr=getattr(mesh, "hang_ptr", None),
+                constraint_idx=getattr(mesh, "hang_idx", None),
+                constraint_weight=getattr(mesh, "hang_w", None),
+                constraint_inhomogeneity=getattr(mesh, "hang_inhomogeneity", None))
     hp.set_physics(viscosity, srf, omega)
     hp.set_forcing(force)
     return hp
