@@ -18,9 +18,11 @@
 //     the library assembles ghost-layer cells redundantly instead of compress(add));
 //   * geometry: affine cells -> one inverse Jacobian / determinant per cell; otherwise per
 //     quadrature point, with mapping_laplacian from the Jacobian gradients;
-//   * constraints: homogeneous Dirichlet lines of zero_constraints as a mask, inhomogeneities of
-//     nonzero_constraints as values.  Hanging-node lines are refused (GLSNS_ERR_UNSUPPORTED is
-//     the library's answer for them as well).
+//   * constraints: homogeneous Dirichlet lines of zero_constraints as a mask (1), inhomogeneities
+//     of nonzero_constraints as values; hanging-node lines (mask 2) as a CSR of (master, weight)
+//     taken from the CLOSED zero_constraints, their inhomogeneities from the closed
+//     nonzero_constraints; the cell colouring separates cells that share a master.  The library
+//     takes hanging-node lines on one rank only.
 #ifndef GLSNS_DEALII_ADAPTER_HPP
 #define GLSNS_DEALII_ADAPTER_HPP
 
@@ -69,7 +71,9 @@ namespace glsns
       std::vector<int32_t> cell_dofs, col_idx, color_ptr, color_cells, neighbor_rank, send_idx;
       std::vector<int64_t> row_ptr, send_ptr, recv_ptr;
       std::vector<double>  inv_jacobian, det_jacobian, cell_measure, q_points, constraint_values,
-        mapping_laplacian;
+        mapping_laplacian, constraint_weight, constraint_inhomogeneity;
+      std::vector<int64_t> constraint_ptr;
+      std::vector<int32_t> constraint_idx;
       std::vector<uint8_t> constrained;
       // numbering
       std::vector<types::global_dof_index> local_to_global; // owned first, then ghosts by owner
@@ -206,19 +210,34 @@ namespace glsns
           h.local_to_global[h.n_owned + i] = ghosts[i];
           h.ghost_local[ghosts[i]]         = (int32_t)(h.n_owned + i);
         }
-      // ---- constraints (Dirichlet lines only) ----
+      // ---- constraints: Dirichlet lines (1) and hanging-node lines (2) of the closed objects ----
       h.constrained.assign(h.n_dofs, 0), h.constraint_values.assign(h.n_dofs, 0.0);
+      h.constraint_ptr.assign(h.n_dofs + 1, 0), h.constraint_idx.clear(), h.constraint_weight.clear();
+      h.constraint_inhomogeneity.assign(h.n_dofs, 0.0);
+      bool any_hanging = false;
       for (int64_t i = 0; i < h.n_dofs; ++i)
         {
           const auto g = h.local_to_global[i];
           if (zero_constraints.is_constrained(g))
             {
-              const auto *entries = zero_constraints.get_constraint_entries(g);
-              if (entries && !entries->empty())
-                throw std::runtime_error("glsns: hanging-node constraint lines are not supported yet");
-              h.constrained[i] = 1;
+              // a line that had entries BEFORE close() is a hanging-node line even if all its
+              // masters were Dirichlet dofs and dropped out; a boundary-value line never has any
+              const auto *entries  = zero_constraints.get_constraint_entries(g);
+              const auto *entries_n = nonzero_constraints.get_constraint_entries(g);
+              const bool  hanging  = (entries && !entries->empty()) || (entries_n && !entries_n->empty());
+              h.constrained[i]     = hanging ? 2 : 1;
+              any_hanging          = any_hanging || hanging;
+              if (hanging && entries)
+                for (const auto &e : *entries)
+                  {
+                    h.constraint_idx.push_back(h.to_local(e.first));
+                    h.constraint_weight.push_back(e.second);
+                  }
+              if (hanging)
+                h.constraint_inhomogeneity[i] = nonzero_constraints.get_inhomogeneity(g);
             }
-          if (nonzero_constraints.is_constrained(g))
+          h.constraint_ptr[i + 1] = (int64_t)h.constraint_idx.size();
+          if (nonzero_constraints.is_constrained(g) && h.constrained[i] != 2)
             h.constraint_values[i] = nonzero_constraints.get_inhomogeneity(g);
         }
       // ---- cells: dofs in library order, geometry ----
@@ -300,31 +319,44 @@ namespace glsns
             o[k] = h.to_local(dsp.column_number(h.owned_begin + i, k));
           std::sort(o, o + (h.row_ptr[i + 1] - h.row_ptr[i]));
         }
-      // ---- colouring: greedy, cells of one colour share no dof ----
+      // ---- colouring: greedy, cells of one colour share no dof and no master of a dof ----
       {
         std::vector<int32_t>              color(nc, -1);
         std::vector<std::vector<int32_t>> dof_colors(h.n_dofs); // colours already used at a dof
         int32_t                           ncolor = 0;
+        std::vector<int32_t>              touched;
         for (std::size_t c = 0; c < nc; ++c)
           {
-            int32_t pick = 0;
-            for (bool clash = true; clash; ++pick)
+            touched.clear();
+            for (unsigned int i = 0; i < n; ++i)
               {
-                clash = false;
-                for (unsigned int i = 0; i < n && !clash; ++i)
-                  for (const int32_t used : dof_colors[h.cell_dofs[c * n + i]])
-                    if (used == pick)
-                      {
-                        clash = true;
-                        break;
-                      }
+                const int32_t d = h.cell_dofs[c * n + i];
+                touched.push_back(d);
+                for (int64_t k = h.constraint_ptr[d]; k < h.constraint_ptr[d + 1]; ++k)
+                  touched.push_back(h.constraint_idx[k]);
+              }
+            int32_t pick = 0;
+            for (;; ++pick)
+              {
+                bool clash = false;
+                for (const int32_t d : touched)
+                  {
+                    for (const int32_t used : dof_colors[d])
+                      if (used == pick)
+                        {
+                          clash = true;
+                          break;
+                        }
+                    if (clash)
+                      break;
+                  }
                 if (!clash)
                   break;
               }
             color[c] = pick;
             ncolor   = std::max(ncolor, pick + 1);
-            for (unsigned int i = 0; i < n; ++i)
-              dof_colors[h.cell_dofs[c * n + i]].push_back(pick);
+            for (const int32_t d : touched)
+              dof_colors[d].push_back(pick);
           }
         h.color_ptr.assign(ncolor + 1, 0);
         for (std::size_t c = 0; c < nc; ++c)
@@ -405,6 +437,13 @@ namespace glsns
       out.send_ptr = h.send_ptr.data(), out.send_idx = h.send_idx.data();
       out.recv_ptr          = h.recv_ptr.data();
       out.mapping_laplacian = affine ? nullptr : h.mapping_laplacian.data();
+      if (any_hanging)
+        {
+          out.constraint_ptr           = h.constraint_ptr.data();
+          out.constraint_idx           = h.constraint_idx.data();
+          out.constraint_weight        = h.constraint_weight.data();
+          out.constraint_inhomogeneity = h.constraint_inhomogeneity.data();
+        }
     }
   } // namespace dealii_adapter
 } // namespace glsns
