@@ -213,6 +213,8 @@ glsns_create(int32_t cuda_device, glsns_context **out)
   int sm = 0;
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cuda_device);
   ctx->n_sm = sm > 0 ? sm : 148;
+  if (const char *e = getenv("GLSNS_GMRES_LOOKAHEAD"))
+    ctx->gmres_lookahead = atoi(e) != 0;
   if (dev_alloc(ctx, ctx->counters, 4) != GLSNS_OK)
     {
       delete ctx;
@@ -252,12 +254,16 @@ glsns_destroy(glsns_context *ctx)
   ctx->hang_ptr.release(), ctx->hang_idx.release(), ctx->hang_w.release(), ctx->hang_list.release();
   ctx->hang_inhom.release();
   ctx->fgroups.release();
+  ctx->rowdesc.release();
   ctx->sgroups.release();
   ctx->rowptr.release();
   ctx->diag_pos.release();
   ctx->constrained.release();
   if (ctx->h_pinned)
     cudaFreeHost(ctx->h_pinned);
+  for (int k = 0; k < 2; ++k)
+    if (ctx->step_event[k])
+      cudaEventDestroy(ctx->step_event[k]);
   for (auto &t : ctx->timers)
     for (auto &p : t.pool)
       {

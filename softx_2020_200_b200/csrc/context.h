@@ -45,6 +45,7 @@ namespace glsns
                    // helper item: where the totals go (block position << 4 | row offset)
     int32_t fmask2; // group descriptor: the same for the distances 32 ...
     int32_t pad_;
+    int64_t gb;     // helper item: where the group's entry list starts in TrsvSweep::ord (e_off counts from there)
   };
 
   // One sweep (lower or upper) of the ILU application in stream form (trsv.cu).
@@ -54,13 +55,14 @@ namespace glsns
     DevBuf<TrsvItem>      gdesc;    // the groups of every block (a solver item's rs0 / len index it)
     DevBuf<int64_t>       blob_off; // byte offset of each item's blob in the stream
     DevBuf<int32_t>       next16;   // bytes/16 of the blob NSLOT items ahead (same warp)
+    DevBuf<uint16_t>      ord;      // per group: positions in the row of the entries its helper items take, in item order
     DevBuf<unsigned char> dir;      // per-warp directory
     DevBuf<unsigned char> stream;   // headers, indices and factor values in consumption order
     int64_t               n_items = 0, stream_bytes = 0;
     void
     release()
     {
-      items.release(), gdesc.release(), blob_off.release(), next16.release(), dir.release(), stream.release();
+      items.release(), gdesc.release(), blob_off.release(), next16.release(), ord.release(), dir.release(), stream.release();
       n_items = stream_bytes = 0;
     }
   };
@@ -131,6 +133,7 @@ struct glsns_context
   glsns::DevBuf<int64_t> hang_ptr;
   glsns::DevBuf<int32_t> hang_idx, hang_list;
   glsns::DevBuf<double>  hang_w, hang_inhom;
+  glsns::DevBuf<int4>    rowdesc; // per row: start, diagonal offset, length | rows left in its group << 16 (ILU factorisation)
   glsns::DevBuf<int2>    fgroups; // (first row, rows) of the row groups, by lower-sweep level
   glsns::DevBuf<int2>    sgroups; // every row in a group (diagonal-only rows too), by row: SpMV
   int64_t                n_sgroups = 0;
@@ -157,7 +160,9 @@ struct glsns_context
   glsns::DevBuf<int32_t> counters; // [0] ticket, [1] error flag
   glsns::DevBuf<int32_t> row_done; // factorisation flags
   int32_t               epoch = 0;
-  double               *h_pinned = nullptr; // 80 doubles
+  double               *h_pinned = nullptr; // 3 x 192 doubles: Hessenberg columns of two steps in flight, y
+  cudaEvent_t           step_event[2] = {nullptr, nullptr}; // GMRES: a step's column has reached the host
+  bool                  gmres_lookahead = true; // GLSNS_GMRES_LOOKAHEAD=0: one step on the stream at a time
   int32_t               n_sm = 148;
 
   // ---- communication ----

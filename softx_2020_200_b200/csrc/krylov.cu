@@ -297,7 +297,10 @@ namespace glsns
     GLSNS_TRY(dev_alloc(ctx, ctx->hbuf, 192));
     GLSNS_TRY(dev_alloc(ctx, ctx->ycoef, 64));
     if (!ctx->h_pinned)
-      GLSNS_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pinned, 192 * sizeof(double)));
+      GLSNS_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pinned, 3 * 192 * sizeof(double)));
+    for (int k = 0; k < 2; ++k)
+      if (!ctx->step_event[k])
+        GLSNS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->step_event[k], cudaEventDisableTiming));
     return GLSNS_OK;
   }
 
@@ -431,24 +434,37 @@ namespace glsns
         ctx->kernel_launches++;
         std::fill(g.begin(), g.end(), 0.0);
         g[0]  = beta;
-        int j = 0;
+        // One Arnoldi step needs nothing from the host (V[j + 1] is normalised on the device), so
+        // step j + 1 is put on the stream BEFORE the host waits for the Hessenberg column of step
+        // j: the stream never runs dry while the host does its Givens rotations and launches.  If
+        // step j turns out to be the last one, step j + 1 has run for nothing (it touches
+        // V[j + 2], w, zg and hbuf only, none of which the update below reads); the iteration
+        // count and every number the host sees are those of the unpipelined loop.
+        auto enqueue_step = [&](int jj) -> glsns_status {
+          timer_begin(ctx, T_TRSV);
+          GLSNS_TRY(launch_ilu_apply(ctx, V + (int64_t)jj * n, zg));
+          timer_end(ctx, T_TRSV);
+          GLSNS_TRY(halo_exchange(ctx, zg));
+          timer_begin(ctx, T_SPMV);
+          GLSNS_TRY(launch_spmv(ctx, zg, w));
+          timer_end(ctx, T_SPMV);
+          timer_begin(ctx, T_ORTHOG);
+          GLSNS_TRY(orthogonalise(ctx, jj + 1));
+          timer_end(ctx, T_ORTHOG);
+          GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 192 * (jj & 1), ctx->hbuf.p,
+                                          (64 + jj + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
+          GLSNS_CUDA(ctx, cudaEventRecord(ctx->step_event[jj & 1], st));
+          return GLSNS_OK;
+        };
+        int j = 0, queued = -1; // (the last step that is on the stream)
         for (; j < m && it < p->max_iterations; ++j)
           {
-            timer_begin(ctx, T_TRSV);
-            GLSNS_TRY(launch_ilu_apply(ctx, V + (int64_t)j * n, zg));
-            timer_end(ctx, T_TRSV);
-            GLSNS_TRY(halo_exchange(ctx, zg));
-            timer_begin(ctx, T_SPMV);
-            GLSNS_TRY(launch_spmv(ctx, zg, w));
-            timer_end(ctx, T_SPMV);
-            timer_begin(ctx, T_ORTHOG);
-            GLSNS_TRY(orthogonalise(ctx, j + 1));
-            timer_end(ctx, T_ORTHOG);
-            GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->hbuf.p, (64 + j + 2) * sizeof(double),
-                                            cudaMemcpyDeviceToHost, st));
-            GLSNS_CUDA(ctx, cudaStreamSynchronize(st));
-            timers_drain(ctx);
-            const double *h1 = ctx->h_pinned, *h2 = ctx->h_pinned + 64;
+            if (queued < j)
+              GLSNS_TRY(enqueue_step(queued = j));
+            if (ctx->gmres_lookahead && j + 1 < m && it + 1 < p->max_iterations)
+              GLSNS_TRY(enqueue_step(queued = j + 1));
+            GLSNS_CUDA(ctx, cudaEventSynchronize(ctx->step_event[j & 1]));
+            const double *h1 = ctx->h_pinned + 192 * (j & 1), *h2 = h1 + 64;
             for (int i = 0; i <= j; ++i)
               H[(size_t)i * m + j] = h1[i] + h2[i];
             H[(size_t)(j + 1) * m + j] = sqrt(norm2_after_projection(h2[j + 1], h2, j + 1));
@@ -483,9 +499,9 @@ namespace glsns
               s -= H[(size_t)i * m + k] * y[k];
             y[i] = s / H[(size_t)i * m + i];
           }
-        for (int i = 0; i < j; ++i)
-          ctx->h_pinned[i] = y[i];
-        GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->ycoef.p, ctx->h_pinned, sizeof(double) * j,
+        for (int i = 0; i < j; ++i) // (third slot: a step that ran ahead may still be writing one of the others)
+          ctx->h_pinned[384 + i] = y[i];
+        GLSNS_CUDA(ctx, cudaMemcpyAsync(ctx->ycoef.p, ctx->h_pinned + 384, sizeof(double) * j,
                                         cudaMemcpyHostToDevice, st));
         combine_kernel<<<grid, VB, 0, st>>>(n, V, n, j, ctx->ycoef.p, tv);
         ctx->kernel_launches++;
@@ -495,6 +511,7 @@ namespace glsns
         lincomb_kernel<<<grid, VB, 0, st>>>(n, 1.0, x, 1.0, zg, x);
         ctx->kernel_launches++;
         GLSNS_CUDA(ctx, cudaStreamSynchronize(st)); // h_pinned is reused next cycle
+        timers_drain(ctx);
       }
 
     // explicitly recomputed ||b - A x||, what SolverControl logs

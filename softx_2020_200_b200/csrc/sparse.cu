@@ -844,11 +844,34 @@ namespace glsns
     // (tests/test_gpu_parity.py compares them).
     constexpr int FR_PRE = 4; // 32-entry chunks of a run requested early
 
+    // Per row, everything a warp needs to know about a pivot row in ONE 16-byte load: where the
+    // row starts, where its diagonal is, how long it is and how many rows of its group follow
+    // it (a run of pivot rows never leaves a group; diagonal-only rows are runs of one).
+    // Without it a run cost up to six dependent round trips to L2 (grp_first of up to four
+    // rows one after the other, then rowptr / diag_pos, then the entries); now two.
+    __global__ void __launch_bounds__(256)
+    ilu_rowdesc_kernel(const int64_t n, const int64_t *__restrict__ rowptr,
+                       const int64_t *__restrict__ diag_pos, const int32_t *__restrict__ grp_first,
+                       int4 *__restrict__ rowdesc)
+    {
+      const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const int64_t rs0 = rowptr[k];
+      const int32_t gf  = grp_first[k];
+      int           rem = 1;
+      if (gf >= 0)
+        while (rem < 4 && k + rem < n && grp_first[k + rem] == gf)
+          ++rem;
+      rowdesc[k] = make_int4((int)(unsigned)(rs0 & 0xffffffffll), (int)(rs0 >> 32), (int)(diag_pos[k] - rs0),
+                             (int)(rowptr[k + 1] - rs0) | (rem << 16));
+    }
+
     __global__ void __launch_bounds__(320, 1)
     ilu_factor_runs_kernel(const int32_t n_groups, const int2 *__restrict__ groups,
                            const int64_t n, const int64_t *__restrict__ rowptr,
                            const int32_t *__restrict__ col, const int64_t *__restrict__ diag_pos,
-                           const int32_t *__restrict__ grp_first, double *lu, int *row_done,
+                           const int4 *__restrict__ rowdesc, double *lu, int *row_done,
                            const int epoch, int *counters, const int maxlen, const int hbits)
     {
       extern __shared__ __align__(16) unsigned char fg_smem[];
@@ -920,10 +943,11 @@ namespace glsns
             rc[st]           = 0;
             if (kk >= nl)
               return nl;
-            const int32_t k  = sc[kk];
-            const int32_t gf = grp_first[k];
-            int           c  = 1;
-            while (c < 4 && kk + c < nl && sc[kk + c] == k + c && grp_first[k + c] == gf)
+            const int32_t k   = sc[kk];
+            const int4    dsc = __ldg(rowdesc + k);
+            const int     rem = dsc.w >> 16;
+            int           c   = 1;
+            while (c < rem && kk + c < nl && sc[kk + c] == k + c)
               ++c;
             if (kk + c > first_unready)
               { // some row of the run was not final when last looked: wait for it
@@ -943,8 +967,8 @@ namespace glsns
                 scan_ready();
               }
             rc[st] = c, rkk[st] = kk;
-            const int64_t rs0 = rowptr[k], d0 = diag_pos[k] - rs0;
-            rlen[st]  = (int)(rowptr[k + 1] - rs0);
+            const int64_t rs0 = (int64_t)(unsigned)dsc.x | ((int64_t)dsc.y << 32), d0 = dsc.z;
+            rlen[st]  = dsc.w & 0xffff;
             rbase[st] = (int)d0 + c;
 #pragma unroll
             for (int b = 0; b < 4; ++b)
@@ -1489,7 +1513,7 @@ namespace glsns
         static const bool by_pivot_rows = getenv("GLSNS_ILU_BY_PIVOT_ROWS") != nullptr;
         const size_t per_warp_r = per_warp + 128;
         const int    warps_r    = (int)std::min<size_t>(10, (size_t)(227 * 1024) / per_warp_r);
-        if (warps_r >= 2 && ctx->n_groups > 0 && !by_rows && !by_pivot_rows && ctx->grp_first.p)
+        if (warps_r >= 2 && ctx->n_groups > 0 && !by_rows && !by_pivot_rows && ctx->grp_first.p && maxlen < 65536)
           {
             // rows of a group share one warp, and so do the pivot rows of a run
             if (ctx->n_diag_rows)
@@ -1500,10 +1524,13 @@ namespace glsns
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem));
             const int grid = (int)std::min<int64_t>((ctx->n_groups + warps_r - 1) / warps_r, ctx->n_sm);
+            GLSNS_TRY(dev_alloc(ctx, ctx->rowdesc, (size_t)n));
+            ilu_rowdesc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+              n, ctx->rowptr.p, ctx->diag_pos.p, ctx->grp_first.p, ctx->rowdesc.p);
             ilu_factor_runs_kernel<<<grid, warps_r * 32, smem, ctx->stream>>>(
               ctx->n_groups, ctx->fgroups.p, n, ctx->rowptr.p, ctx->col.p, ctx->diag_pos.p,
-              ctx->grp_first.p, ctx->lu.p, ctx->row_done.p, ctx->epoch, ctx->counters.p, maxlen, hbits);
-            ctx->kernel_launches += 3;
+              ctx->rowdesc.p, ctx->lu.p, ctx->row_done.p, ctx->epoch, ctx->counters.p, maxlen, hbits);
+            ctx->kernel_launches += 4;
           }
         else if (warps >= 2 && ctx->n_groups > 0 && !by_rows)
           {

@@ -87,11 +87,21 @@ namespace glsns
     //   helper item: r0 | flags | block position in the team's list << 4 | row offset in the
     //                block | bytes/16 of the blob NSLOT items ahead;
     //                then col 4*pad4(entries) | val 8*m*pad4(entries)
-    //   solver item (one per block): r0 | flags | - | bytes/16 of the blob NSLOT items ahead;
-    //                then the block's solved recurrence, TS_NC x 2R doubles (R = rows padded to 4)
+    //   solver item (one per block): r0 of the NEXT block of the list | its flags | rows of the
+    //                block TS_MBOX ahead | bytes/16 of the blob TS_SNSLOT items ahead; then the block's
+    //                solved recurrence lane by lane: 2R lanes (R = rows padded to 4) x TS_CSTR bytes
     constexpr int TS_OFF_COL0 = 16;
     constexpr int TS_OFF_C    = 16;
-    constexpr int TS_NSLOT     = 4; // ring slots of every warp (helper and solver)
+    constexpr int TS_CSTR     = 8 * TS_NC + 16; // bytes of one solver lane's coefficients (+ 16: conflict-free 128-bit loads)
+#ifndef GLSNS_TRSV_NSLOT
+#define GLSNS_TRSV_NSLOT 4
+#endif
+#ifndef GLSNS_TRSV_THREADS
+#define GLSNS_TRSV_THREADS 512
+#endif
+    constexpr int TS_NSLOT     = GLSNS_TRSV_NSLOT; // ring slots of a helper warp
+    constexpr int TS_MAXWARPS  = GLSNS_TRSV_THREADS / 32;
+    constexpr int TS_SNSLOT    = 5; // ring slots of a solver warp
     constexpr int TS_MAX_SLOTS = 9;
     constexpr int TS_SMEM_MAX  = 227 * 1024;
 
@@ -102,6 +112,7 @@ namespace glsns
     constexpr int IT_LAST   = 1 << 8;
     constexpr int IT_SOLVER = 1 << 9;
     constexpr int IT_GUEST  = 1 << 10;
+    constexpr int IT_YOUNG  = 1 << 11; // helper item of a group's YOUNG entries (posts in the second mailbox field)
     constexpr int TS_NWIN   = 4;
 
     __host__ __device__ inline int
@@ -113,7 +124,7 @@ namespace glsns
     blob_bytes(int flags)
     {
       const int m = flags & 31, c = pad4(flags >> 16);
-      return (flags & IT_SOLVER) ? TS_OFF_C + 16 * TS_NC * pad4(m) : TS_OFF_COL0 + 4 * c + 8 * m * c;
+      return (flags & IT_SOLVER) ? TS_OFF_C + TS_CSTR * 2 * pad4(m) : TS_OFF_COL0 + 4 * c + 8 * m * c;
     }
     // per-warp entry of the stream directory (64 bytes)
     struct TrsvWarpDir
@@ -121,9 +132,12 @@ namespace glsns
       int64_t offset;  // byte offset of the warp's first blob in the stream
       int32_t n_items;
       int32_t first16[TS_MAX_SLOTS]; // bytes/16 of the first NSLOT blobs
-      int32_t pad[4];
+      int32_t first_m[2];            // solver: rows of its first 8 blocks, 8 bits each
+      int32_t first_r0, first_flags; // solver: header of its first block
+      int32_t first_ym[4];           // solver: rows with a young post in its first 8 blocks, 16 bits each
+      int32_t pad[12];
     };
-    static_assert(sizeof(TrsvWarpDir) == 64, "directory entry");
+    static_assert(sizeof(TrsvWarpDir) == 128, "directory entry");
 
     __device__ __forceinline__ unsigned long long
     ld_relaxed_u64(const double *p)
@@ -201,7 +215,8 @@ namespace glsns
     __global__ void __launch_bounds__(256)
     trsv_pack_static_kernel(const int64_t n_items, const TrsvItem *__restrict__ items,
                             const int64_t *__restrict__ blob_off, const int32_t *__restrict__ next16,
-                            const int32_t *__restrict__ col, unsigned char *__restrict__ stream)
+                            const int32_t *__restrict__ col, const uint16_t *__restrict__ ord,
+                            unsigned char *__restrict__ stream)
     {
       const int64_t it   = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       const int     lane = threadIdx.x & 31;
@@ -210,13 +225,14 @@ namespace glsns
       const TrsvItem d = items[it];
       unsigned char *B = stream + blob_off[it];
       if (lane == 0)
-        *reinterpret_cast<int4 *>(B) = make_int4(d.r0, d.flags, d.fmask, next16[it]);
+        *reinterpret_cast<int4 *>(B) = (d.flags & IT_SOLVER) ? make_int4(d.e_off, d.nlow, d.pad_, next16[it]) :
+                                                              make_int4(d.r0, d.flags, d.fmask, next16[it]);
       if (d.flags & IT_SOLVER)
         return;
       const int cntc = d.flags >> 16, cp = pad4(cntc);
       int32_t  *bc   = reinterpret_cast<int32_t *>(B + TS_OFF_COL0);
       for (int k = lane; k < cp; k += 32)
-        bc[k] = k < cntc ? col[d.rs0 + d.e_off + k] : d.r0; // padding: any valid index
+        bc[k] = k < cntc ? col[d.rs0 + ord[d.gb + d.e_off + k]] : d.r0; // padding: any valid index
     }
 
     // values (after every factorisation)
@@ -225,7 +241,7 @@ namespace glsns
     trsv_pack_values_kernel(const int64_t n_items, const TrsvItem *__restrict__ items,
                             const TrsvItem *__restrict__ gdesc,
                             const int64_t *__restrict__ blob_off, const double *__restrict__ lu,
-                            unsigned char *__restrict__ stream)
+                            const uint16_t *__restrict__ ord, unsigned char *__restrict__ stream)
     {
       __shared__ double TF[4][TS_BR * TS_BR + TS_BR * TS_WIN]; // per warp: T [16][16], F [16][TS_WIN]
       const int64_t it   = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -240,7 +256,7 @@ namespace glsns
           double *bv = reinterpret_cast<double *>(B + TS_OFF_COL0 + 4 * cp);
           for (int a = 0; a < m; ++a)
             for (int k = lane; k < cp; k += 32)
-              bv[a * cp + k] = k < cntc ? __ldcs(lu + d.rs0 + (int64_t)a * d.len + d.e_off + k) : 0.0;
+              bv[a * cp + k] = k < cntc ? __ldcs(lu + d.rs0 + (int64_t)a * d.len + ord[d.gb + d.e_off + k]) : 0.0;
           return;
         }
       // Solver blob of a BLOCK (<= 4 consecutive groups of one chain, rows [r0, r0 + m)).
@@ -284,9 +300,10 @@ namespace glsns
         }
       __syncwarp();
       // one column per lane and pass: columns 0 .. 15 are those of M, 16 .. 16 + TS_WIN - 1 of G.
-      // Layout the solver reads without bank conflicts: C[jj][2 a + hh]; jj < TS_WH:
+      // Layout: the TS_NC coefficients of solver lane (a, hh) = 2 a + hh are contiguous (the lane
+      // reads them with 128-bit loads at fixed offsets), lanes TS_CSTR bytes apart; jj < TS_WH:
       // G[a][TS_WH hh + jj] (the chain row at distance TS_WH hh + jj), jj >= TS_WH:
-      // M[a][8 hh + jj - TS_WH]
+      // M[a][8 hh + jj - TS_WH].  Rows the block does not have (padding to 4) are zero.
       const int R2 = 2 * pad4(m);
       double   *C  = reinterpret_cast<double *>(B + TS_OFF_C);
       for (int c = lane; c < TS_BR + TS_WIN; c += 32)
@@ -321,7 +338,7 @@ namespace glsns
 #pragma unroll
           for (int a = 0; a < TS_BR; ++a)
             if (2 * a < R2)
-              C[jj * R2 + 2 * a + hh] = y[a];
+              C[(2 * a + hh) * (TS_CSTR / 8) + jj] = a < m ? y[a] : 0.0;
         }
     }
 
@@ -340,16 +357,20 @@ namespace glsns
     //     solved ahead of time; publish.  The chain advances 16 rows per step.
     constexpr int TS_MBOX  = 8;  // mailbox entries (blocks) per team
     constexpr int TS_HSLOT = TS_OFF_COL0 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 2320 (64-entry items)
-    constexpr int TS_SSLOT = TS_OFF_C + 16 * TS_NC * TS_BR;                 // 8208 (48-row window)
-    // team area: windows 4 x 512 | mailbox 8 x 128 | solved counter 16 | barriers
-    constexpr int TS_OFF_MBOX  = 8 * TS_HIST * TS_NWIN;
-    constexpr int TS_TEAM_AREA = TS_OFF_MBOX + 1536;
-    static_assert(TS_MBOX == 8 && TS_NWIN == 4 &&
-                    TS_OFF_MBOX + 128 * TS_MBOX + 16 + 8 * 12 * TS_NSLOT <= TS_TEAM_AREA,
+    constexpr int TS_SSLOT = TS_OFF_C + TS_CSTR * 2 * TS_BR;                // 8720 (48-row window)
+    // team area: windows 4 x 1024 (every row twice, TS_HIST apart: a lane reads its part of a
+    // window at fixed offsets from one base, no wrap-around) | mailbox 8 x 128 | solved counter
+    // 16 | barriers.  A mailbox entry has two fields of 16 totals: those of the old entries (with
+    // the right-hand side) and those of the young ones
+    constexpr int TS_MENT      = 2 * TS_BR; // doubles per mailbox entry
+    constexpr int TS_OFF_MBOX  = 2 * 8 * TS_HIST * TS_NWIN;
+    constexpr int TS_TEAM_AREA = TS_OFF_MBOX + 8 * TS_MENT * TS_MBOX + 512;
+    static_assert(TS_MBOX == 8 && TS_NWIN == 4 && TS_MENT == 32 &&
+                    TS_OFF_MBOX + 8 * TS_MENT * TS_MBOX + 16 + 8 * (11 * TS_NSLOT + TS_SNSLOT) <= TS_TEAM_AREA,
                   "team area");
 
-    template <bool UPPER>
-    __global__ void __launch_bounds__(512, 1)
+    template <bool UPPER, bool TRACE>
+    __global__ void __launch_bounds__(GLSNS_TRSV_THREADS, 1)
     trsv_team_kernel(const TrsvWarpDir *__restrict__ dir, const unsigned char *__restrict__ stream,
                      const double *__restrict__ rhs_vec, double *x, int *counters,
                      unsigned long long *trace, const int64_t trace_n, const int K_gate /* helpers per team */)
@@ -383,14 +404,14 @@ namespace glsns
       if (team_in_cta >= n_teams_cta || role > K)
         return;
       const int64_t team      = (int64_t)team_in_cta * gridDim.x + blockIdx.x; // consecutive lists on different SMs
-      const size_t  team_smem = (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_NSLOT * TS_SSLOT + TS_TEAM_AREA;
+      const size_t  team_smem = (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_SNSLOT * TS_SSLOT + TS_TEAM_AREA;
       unsigned char *T0   = smem_all + (size_t)team_in_cta * team_smem;
-      unsigned char *area = T0 + (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_NSLOT * TS_SSLOT;
-      double        *wsm_all = reinterpret_cast<double *>(area);         // [TS_NWIN][64] chain windows by row & 63
-      double        *mbox = reinterpret_cast<double *>(area + TS_OFF_MBOX); // [TS_MBOX][16], all-ones = empty
-      volatile int  *done = reinterpret_cast<volatile int *>(area + TS_OFF_MBOX + 128 * TS_MBOX); // blocks solved
+      unsigned char *area = T0 + (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_SNSLOT * TS_SSLOT;
+      double        *wsm_all = reinterpret_cast<double *>(area);         // [TS_NWIN][2][64] chain windows by row & 63
+      double        *mbox = reinterpret_cast<double *>(area + TS_OFF_MBOX); // [TS_MBOX][2][16], all-ones = empty
+      volatile int  *done = reinterpret_cast<volatile int *>(area + TS_OFF_MBOX + 8 * TS_MENT * TS_MBOX); // blocks solved
       unsigned long long *bars_all =
-        reinterpret_cast<unsigned long long *>(area + TS_OFF_MBOX + 128 * TS_MBOX + 16);
+        reinterpret_cast<unsigned long long *>(area + TS_OFF_MBOX + 8 * TS_MENT * TS_MBOX + 16);
       const TrsvWarpDir  *D        = dir + team * (K + 1) + role;
       const int64_t       n_items  = D->n_items;
       unsigned long long  policy;
@@ -399,11 +420,17 @@ namespace glsns
       // visible to the helpers by the one CTA barrier of the kernel
       if (role == 0)
         {
-          for (int k = lane; k < TS_NWIN * TS_HIST; k += 32)
+          for (int k = lane; k < 2 * TS_NWIN * TS_HIST; k += 32)
             wsm_all[k] = 0.0;
+          // (entries of rows a block does not have hold 0, so that the solver needs no mask)
+          const TrsvWarpDir *D0 = dir + ((int64_t)team_in_cta * gridDim.x + blockIdx.x) * (K + 1);
 #pragma unroll
-          for (int k = 0; k < TS_MBOX * TS_BR / 32; ++k)
-            reinterpret_cast<unsigned long long *>(mbox)[lane + 32 * k] = SENTINEL;
+          for (int e = 0; e < TS_MBOX; ++e)
+            {
+              const int me = (D0->first_m[e >> 2] >> (8 * (e & 3))) & 255, ym = (D0->first_ym[e >> 1] >> (16 * (e & 1))) & 0xffff;
+              reinterpret_cast<unsigned long long *>(mbox)[lane + TS_MENT * e] =
+                (lane < TS_BR ? lane < me : (ym >> (lane - TS_BR)) & 1) ? SENTINEL : 0ull;
+            }
           if (lane == 0)
             *done = 0;
         }
@@ -417,21 +444,31 @@ namespace glsns
           // =============================== solver ===============================
           // One item per BLOCK (<= 16 rows): out = -(M totals + G w), the recurrence of the
           // whole block solved ahead of time (trsv_pack_values_kernel).  Lane (a, hh) =
-          // (lane >> 1, lane & 1) takes row a and the columns 8 hh .. 8 hh + 7 of both G
-          // (window rows r0-1-d / r0+m+d at distance d) and M (totals of the block's own
-          // rows).  Coefficients of absent couplings are exactly zero and the window only
-          // ever holds finite numbers, so the window part needs no masking; the totals of
-          // rows the block does not have are masked (their mailbox entries stay empty).
-          unsigned char      *ring = T0 + (size_t)K * TS_NSLOT * TS_HSLOT;
-          unsigned long long *bars = bars_all + K * TS_NSLOT;
+          // (lane >> 1, lane & 1) takes row a and, of G, the chain rows at distance TS_WH hh ..
+          // TS_WH hh + TS_WH - 1 from the block (window rows r0-1-d / r0+m+d), of M the columns
+          // 8 hh .. 8 hh + 7 (totals of the block's own rows).  Coefficients of absent couplings
+          // and rows are exactly zero, a window only ever holds finite numbers and the mailbox
+          // entries of rows a block does not have hold 0: nothing is masked.
+          //
+          // This loop is the critical path of a sweep (~1700 of its ~2000 hops are chain steps)
+          // and one warp's instruction stream: what counts is the NUMBER of instructions between
+          // two publications.  Round 2 started with 485 SASS instructions per block, 32 of them
+          // DFMA and 66 loads (the rest: addresses of loads with a run-time stride, modulo
+          // arithmetic of the circular window, zeroing of predicated loads, masks).  Now every
+          // load is base + immediate: the coefficients lie lane by lane (8 x 128-bit loads of G, 4
+          // of M), the window keeps every row twice (no wrap-around), a block's header arrives
+          // with the block before it (the window loads go out before the ring is even looked at).
+          const unsigned      ring0 = (unsigned)__cvta_generic_to_shared(T0 + (size_t)K * TS_NSLOT * TS_HSLOT);
+          unsigned char      *ring  = T0 + (size_t)K * TS_NSLOT * TS_HSLOT;
+          unsigned long long *bars  = bars_all + K * TS_NSLOT;
           int64_t             n_iss = 0;
           if (lane == 0)
             {
-              for (int s = 0; s < TS_NSLOT; ++s)
+              for (int s = 0; s < TS_SNSLOT; ++s)
                 mbar_init(bars + s, 1);
               asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              for (int s = 0; s < TS_NSLOT && s < n_items; ++s)
+              for (int s = 0; s < TS_SNSLOT && s < n_items; ++s)
                 {
                   const unsigned bytes = 16u * (unsigned)D->first16[s];
                   mbar_expect_tx(bars + s, bytes);
@@ -445,98 +482,125 @@ namespace glsns
           unsigned phase = 0;
           long long tstage[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64(); // debugging aid (trace)
 #define TS_TICK(k)                              \
-  if (trace)                                    \
+  if (TRACE)                                    \
     {                                           \
       const long long now_ = clock64();         \
       tstage[k] += now_ - tlast;                \
       tlast = now_;                             \
     }
-          const int a = lane >> 1, hh = lane & 1;
+          const int      a = lane >> 1, hh = lane & 1;
+          const unsigned wsm0  = (unsigned)__cvta_generic_to_shared(wsm_all);
+          const unsigned mbox0 = (unsigned)__cvta_generic_to_shared(mbox);
+          int            r0 = D->first_r0, fl = D->first_flags; // header of the block at hand
           for (int64_t g = 0; g < n_items; ++g)
             {
+              const int m = fl & 31;
+              // the window: what the chain waits for (loads at fixed offsets from one base)
+              const unsigned wwin = wsm0 + 16 * TS_HIST * ((fl >> 12) & (TS_NWIN - 1));
+              const double *wp = wsm_all + 2 * TS_HIST * ((fl >> 12) & (TS_NWIN - 1)) +
+                                 (UPPER ? ((r0 + m) & (TS_HIST - 1)) + TS_WH * hh :
+                                          ((r0 - 1) & (TS_HIST - 1)) + TS_HIST - TS_WH * hh);
+              double w[TS_WH];
+#pragma unroll
+              for (int j = 0; j < TS_WH; ++j)
+                w[j] = wp[UPPER ? j : -j];
               while (!mbar_try_wait(bars + slot, phase))
                 ;
               TS_TICK(0)
-              const unsigned char *S  = ring + (size_t)slot * TS_SSLOT;
-              const int4           h  = *reinterpret_cast<const int4 *>(S);
-              const int            r0 = h.x, m = h.y & 31, R2 = 2 * pad4(m);
-              double              *wsm = wsm_all + TS_HIST * ((h.y >> 12) & (TS_NWIN - 1));
-              const double        *C   = reinterpret_cast<const double *>(S + TS_OFF_C) + lane;
-              const bool           on  = lane < R2;
-              // the window part first: it is what the chain waits for (lane (a, hh) takes the
-              // chain rows at distance TS_WH hh ... TS_WH hh + TS_WH - 1 from the block)
+              const unsigned S = ring0 + (unsigned)slot * TS_SSLOT;
+              int4           h; // r0 and flags of the next block | rows of the block TS_MBOX ahead | next blob
+              asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(S));
+              const double2 *cl = reinterpret_cast<const double2 *>(ring + (size_t)slot * TS_SSLOT + TS_OFF_C +
+                                                                    (size_t)lane * TS_CSTR);
+              double         c[TS_NC];
+#pragma unroll
+              for (int j = 0; j < TS_NC; j += 2)
+                {
+                  const double2 v = cl[j >> 1];
+                  c[j] = v.x, c[j + 1] = v.y;
+                }
               double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-              {
-                double cg[TS_WH];
 #pragma unroll
-                for (int j = 0; j < TS_WH; ++j)
-                  cg[j] = on ? C[j * R2] : 0.0;
-                const int wb = UPPER ? r0 + m + TS_WH * hh : r0 - 1 - TS_WH * hh;
-#pragma unroll
-                for (int j = 0; j < TS_WH; j += 4)
-                  {
-                    p0 += cg[j] * wsm[(UPPER ? wb + j : wb - j) & (TS_HIST - 1)];
-                    p1 += cg[j + 1] * wsm[(UPPER ? wb + j + 1 : wb - j - 1) & (TS_HIST - 1)];
-                    p2 += cg[j + 2] * wsm[(UPPER ? wb + j + 2 : wb - j - 2) & (TS_HIST - 1)];
-                    p3 += cg[j + 3] * wsm[(UPPER ? wb + j + 3 : wb - j - 3) & (TS_HIST - 1)];
-                  }
-              }
-              double cm[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                cm[j] = on ? C[(j + TS_WH) * R2] : 0.0;
+              for (int j = 0; j < TS_WH; j += 4)
+                {
+                  p0 += c[j] * w[j];
+                  p1 += c[j + 1] * w[j + 1];
+                  p2 += c[j + 2] * w[j + 2];
+                  p3 += c[j + 3] * w[j + 3];
+                }
               TS_TICK(1)
               // totals of everything else (minus the right-hand side), from the helpers: a
               // mailbox entry carries its own readiness (all-ones pattern = empty)
-              const int mb = (int)(g & (TS_MBOX - 1));
-              volatile unsigned long long *mv =
-                reinterpret_cast<volatile unsigned long long *>(mbox + mb * TS_BR);
+              const unsigned mv = mbox0 + 8 * TS_MENT * (unsigned)(g & (TS_MBOX - 1));
               {
                 long long spins = 0;
-                while (!__all_sync(0xffffffffu, (lane & 15) >= m || mv[lane & 15] != SENTINEL))
-                  if ((++spins & 4095) == 0 &&
-                      (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
-                    {
-                      atomicExch(&counters[1], 2);
+                for (;;)
+                  {
+                    unsigned long long b;
+                    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(b) : "r"(mv + 8 * lane));
+                    if (__all_sync(0xffffffffu, b != SENTINEL))
                       break;
-                    }
+                    if ((++spins & 4095) == 0 &&
+                        (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
+                      {
+                        atomicExch(&counters[1], 2);
+                        break;
+                      }
+                  }
               }
               TS_TICK(2)
               {
-                const volatile double *tt = mbox + mb * TS_BR + 8 * hh;
-                const int     mr = m - 8 * hh; // rows of this half that exist
+                double t[8], ty[8];
+                const unsigned tv = mv + 64 * hh;
+                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2];" : "=d"(t[0]), "=d"(t[1]) : "r"(tv));
+                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(t[2]), "=d"(t[3]) : "r"(tv));
+                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+32];" : "=d"(t[4]), "=d"(t[5]) : "r"(tv));
+                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+48];" : "=d"(t[6]), "=d"(t[7]) : "r"(tv));
+                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+128];" : "=d"(ty[0]), "=d"(ty[1]) : "r"(tv));
+                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+144];" : "=d"(ty[2]), "=d"(ty[3]) : "r"(tv));
+                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+160];" : "=d"(ty[4]), "=d"(ty[5]) : "r"(tv));
+                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+176];" : "=d"(ty[6]), "=d"(ty[7]) : "r"(tv));
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  t[j] += ty[j];
 #pragma unroll
                 for (int j = 0; j < 8; j += 4)
                   {
-                    p0 += cm[j] * (j < mr ? tt[j] : 0.0);
-                    p1 += cm[j + 1] * (j + 1 < mr ? tt[j + 1] : 0.0);
-                    p2 += cm[j + 2] * (j + 2 < mr ? tt[j + 2] : 0.0);
-                    p3 += cm[j + 3] * (j + 3 < mr ? tt[j + 3] : 0.0);
+                    p0 += c[TS_WH + j] * t[j];
+                    p1 += c[TS_WH + j + 1] * t[j + 1];
+                    p2 += c[TS_WH + j + 2] * t[j + 2];
+                    p3 += c[TS_WH + j + 3] * t[j + 3];
                   }
               }
               double p = (p0 + p1) + (p2 + p3);
-              __syncwarp();
-              if (lane < TS_BR) // hand the entry back: empty it, then let block g + TS_MBOX in
-                mv[lane] = SENTINEL;
-              if (lane == 0)
-                *done = (int)g + 1;
               p += __shfl_xor_sync(0xffffffffu, p, 1);
               if (hh == 0 && a < m)
                 {
                   const double v = -p;
                   st_result(x + r0 + a, v);
-                  if (!(h.y & IT_GUEST))
-                    wsm[(r0 + a) & (TS_HIST - 1)] = v;
-                  if (trace) // debugging aid (glsns_ilu_apply_trace): when was the row published
+                  if (!(fl & IT_GUEST))
+                    {
+                      const unsigned wa = wwin + 8 * ((r0 + a) & (TS_HIST - 1));
+                      asm volatile("st.shared.f64 [%0], %1;\n\tst.shared.f64 [%0+512], %1;" ::"r"(wa), "d"(v) : "memory");
+                      static_assert(8 * TS_HIST == 512, "second copy of a window row");
+                    }
+                  if (TRACE) // debugging aid (glsns_ilu_apply_trace): when was the row published
                     {
                       unsigned long long tns;
                       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
                       trace[r0 + a] = tns;
                     }
                 }
-              __syncwarp();
+              __syncwarp(); // the window rows are written, the mailbox entry is read
+              // hand the entry back: empty it for the block TS_MBOX ahead (0 in the rows that
+              // block does not have), then let that block in
+              asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(mv + 8 * lane),
+                           "l"((lane < TS_BR ? lane < (h.z & 255) : ((h.z >> 8) >> (lane - TS_BR)) & 1) ? SENTINEL : 0ull)
+                           : "memory");
+              if (lane == 0)
+                *done = (int)g + 1;
               TS_TICK(3)
-              // the slot is used up: refill it with the block TS_NSLOT ahead
+              // the slot is used up: refill it with the block TS_SNSLOT ahead
               if (lane == 0 && n_iss < n_items)
                 {
                   const unsigned bytes = 16u * (unsigned)h.w;
@@ -545,12 +609,14 @@ namespace glsns
                   src += bytes;
                   ++n_iss;
                 }
-              slot = slot + 1 == TS_NSLOT ? 0 : slot + 1;
+              r0   = h.x;
+              fl   = h.y;
+              slot = slot + 1 == TS_SNSLOT ? 0 : slot + 1;
               phase ^= slot == 0;
               TS_TICK(4)
             }
-          if (trace && lane == 0 && (team + 1) * 8 <= trace_n)
-            { // cycles in: ring wait, window product, mailbox wait, totals+publish, release+refill
+          if (TRACE && lane == 0 && (team + 1) * 8 <= trace_n)
+            { // cycles in: ring wait (with the window loads), product, mailbox wait, totals+publish, release+refill
               for (int k = 0; k < 6; ++k)
                 trace[2 * trace_n + team * 8 + k] = (unsigned long long)tstage[k];
               trace[2 * trace_n + team * 8 + 6] = (unsigned long long)n_items;
@@ -626,7 +692,7 @@ namespace glsns
             for (int u = 0; u < TS_U; ++u)
               if (pendN & (1u << u))
                 bN[u] = ld_relaxed_u64(x + cN[u]);
-            if ((flags & IT_LAST) && lane < (flags & 31))
+            if ((flags & (IT_LAST | IT_YOUNG)) == IT_LAST && lane < (flags & 31))
               rS[kg] = rhs_vec[h.x + lane];
             slotG = slotG + 1 == TS_NSLOT ? 0 : slotG + 1;
             phaseG ^= slotG == 0;
@@ -640,7 +706,7 @@ namespace glsns
             const double        *sval  = reinterpret_cast<const double *>(S + TS_OFF_COL0 + 4 * cp);
             long long            spins = 0;
             unsigned long long   t_rs = 0, t_det = 0; // debugging aid (trace)
-            if (trace)
+            if (TRACE)
               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_rs));
             for (;;)
               {
@@ -658,7 +724,7 @@ namespace glsns
                     }
                 if (!__any_sync(0xffffffffu, pendG != 0))
                   break;
-                if (trace)
+                if (TRACE)
                   {
                     n_waited += spins == 0;
                     ++n_rounds;
@@ -688,16 +754,19 @@ namespace glsns
                     break;
                   }
               }
-            if (trace)
+            if (TRACE)
               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_det));
             if (flags & IT_LAST)
               {
                 // the group is complete: fold in the right-hand side, total over the
                 // warp, post in the mailbox once the solver has freed the entry
+                if (!(flags & IT_YOUNG))
+                  {
 #pragma unroll
-                for (int a = 0; a < TRSV_G; ++a)
-                  if (lane == a && a < m)
-                    acc[a] -= rS[kr];
+                    for (int a = 0; a < TRSV_G; ++a)
+                      if (lane == a && a < m)
+                        acc[a] -= rS[kr];
+                  }
                 // four totals over 32 lanes in 6 shuffles: halve the number of rows a lane
                 // carries while the partners are 16 and 8 lanes apart, then sum over the
                 // rest; lane 8 a ends up with the total of row a
@@ -716,7 +785,7 @@ namespace glsns
                 // (header: position of the group's block in the team's list << 4 | row offset)
                 const int bseq = h.z >> 4, boff = h.z & 15;
                 volatile unsigned long long *mv = reinterpret_cast<volatile unsigned long long *>(
-                  mbox + (bseq & (TS_MBOX - 1)) * TS_BR + boff);
+                  mbox + (bseq & (TS_MBOX - 1)) * TS_MENT + ((flags & IT_YOUNG) ? TS_BR : 0) + boff);
                 spins = 0;
                 // the entry is this block's once the solver is within TS_MBOX blocks of it
                 while (*done + TS_MBOX <= bseq)
@@ -732,7 +801,7 @@ namespace glsns
                     if (b == SENTINEL)
                       b = 0x7FF8000000000000ull;
                     mv[lane >> 3] = b;
-                    if (trace) // debugging aid: when were the row's totals posted
+                    if (TRACE) // debugging aid: when were the row's totals posted
                       {
                         unsigned long long tns;
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
@@ -765,7 +834,7 @@ namespace glsns
           if (it + 2 < n_items + 2)
             step(std::integral_constant<int, 2>(), it + 2);
         }
-      if (trace && 8 * (int64_t)gridDim.x * n_teams_cta + (team + 1) * 4 <= trace_n)
+      if (TRACE && 8 * (int64_t)gridDim.x * n_teams_cta + (team + 1) * 4 <= trace_n)
         { // per helper lane: items that had to wait, polling rounds, entries re-read
           for (int o = 16; o > 0; o >>= 1)
             n_polled += __shfl_xor_sync(0xffffffffu, n_polled, o);
@@ -808,7 +877,7 @@ namespace glsns
     size_t
     team_smem_bytes(int helpers)
     {
-      return (size_t)helpers * TS_NSLOT * TS_HSLOT + (size_t)TS_NSLOT * TS_SSLOT + TS_TEAM_AREA;
+      return (size_t)helpers * TS_NSLOT * TS_HSLOT + (size_t)TS_SNSLOT * TS_SSLOT + TS_TEAM_AREA;
     }
 
     TrsvConfig
@@ -823,8 +892,8 @@ namespace glsns
         if (getenv("GLSNS_TRSV_LAYOUT"))
           t.layout = std::max(0, std::min(2, atoi(getenv("GLSNS_TRSV_LAYOUT"))));
         t.helpers = std::max(1, std::min(11, t.helpers));
-        t.teams   = std::max(1, std::min(16 / (t.helpers + 1), t.teams));
-        if (t.warps() > 16 || (t.layout == 2 && t.teams > 4))
+        t.teams   = std::max(1, std::min(TS_MAXWARPS / (t.helpers + 1), t.teams));
+        if (t.warps() > TS_MAXWARPS || (t.layout == 2 && t.teams > 4))
           t.layout = 1;
         while (t.teams > 1 && t.teams * team_smem_bytes(t.helpers) > (size_t)TS_SMEM_MAX)
           --t.teams;
@@ -840,7 +909,7 @@ namespace glsns
     {
       const TrsvConfig cfg  = trsv_config();
       const size_t     smem = cfg.teams * team_smem_bytes(cfg.helpers);
-      auto             kern = trsv_team_kernel<UPPER>;
+      auto             kern = trace ? trsv_team_kernel<UPPER, true> : trsv_team_kernel<UPPER, false>;
       GLSNS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
       int  *counters = ctx->counters.p;
@@ -1206,9 +1275,66 @@ namespace glsns
                 (long long)NW, (long long)n_heads, (long long)n_steals, (long long)n_interrupted);
       // ---- item lists: per team one solver list (one item per block) and K helper lists
       // (the team's groups round-robin, <= TS_CH entries per item) ----
+      // YOUNG entries.  The sweep is a pipeline of chains: a block's inputs from other chains
+      // were published anywhere between a hop and many levels before it is solved, and the
+      // few that are still in flight when the helpers get to the group (2-4 % of the entries;
+      // 70 % of the groups have none) used to stall a helper's whole list behind them: totals
+      // that depended on old entries alone were posted late, and the variance of that delay
+      // (p50 1.7-2.4 us, p90 6 us) is what the critical path is made of.  So a group's entries
+      // are split by the AGE of the row they refer to (block levels between the two blocks):
+      // the old ones go to the team's bulk helpers, which then never wait for anything recent
+      // and run ahead of the solver; the young ones (age <= young_age) form small items of
+      // their own, served by dedicated helpers that do nothing else, and are posted in a
+      // second mailbox field.  `ord` lists, group by group, the positions (in the row) of the
+      // entries the helpers take: old ones first, young ones behind, each oldest first.
+      const int32_t young_age = getenv("GLSNS_TRSV_YOUNG") ? atoi(getenv("GLSNS_TRSV_YOUNG")) : 2;
+      const int     KY = young_age > 0 && K >= 3 ?
+                           std::max(1, std::min(K - 2, getenv("GLSNS_TRSV_YOUNG_HELPERS") ? atoi(getenv("GLSNS_TRSV_YOUNG_HELPERS")) : 2)) :
+                           0;
+      const int     KB = K - KY; // bulk helpers
+      std::vector<int64_t>  gbase(ng + 1, 0);
+      std::vector<int32_t>  n_young(ng, 0);
+      for (int64_t g = 0; g < ng; ++g)
+        gbase[g + 1] = gbase[g] + cnt[g];
+      std::vector<uint16_t> ord((size_t)std::max<int64_t>(gbase[ng], 1));
+      int64_t               n_young_total = 0, n_young_groups = 0;
+      for (int64_t g = 0; g < ng; ++g)
+        {
+          const int64_t rs = rowptr[grp_ptr[g]], k0 = rs + e_off[g], k1 = k0 + cnt[g];
+          const int32_t b  = blk_of[g];
+          uint16_t     *o  = ord.data() + gbase[g];
+          int32_t       no = 0, ny = 0;
+          // oldest first: ascending columns in the lower sweep, descending in the upper one
+          auto young = [&](int64_t k) {
+            const int32_t dg = grp_of[col[k]];
+            return KY > 0 && dg >= 0 && blev[b] - blev[blk_of[dg]] <= young_age;
+          };
+          for (int64_t kk = 0; kk < cnt[g]; ++kk)
+            {
+              const int64_t k = upper ? k1 - 1 - kk : k0 + kk;
+              if (!young(k))
+                o[no++] = (uint16_t)(k - rs);
+            }
+          for (int64_t kk = 0; kk < cnt[g]; ++kk)
+            {
+              const int64_t k = upper ? k1 - 1 - kk : k0 + kk;
+              if (young(k))
+                o[no + ny++] = (uint16_t)(k - rs);
+            }
+          n_young[g] = ny;
+          n_young_total += ny;
+          n_young_groups += ny > 0;
+        }
+      if (getenv("GLSNS_TRSV_DEBUG"))
+        fprintf(stderr, "trsv_analyse %s: young age %d: %lld of %lld helper entries (%.2f %%) in %lld of %lld groups; %d bulk + %d young helpers\n",
+                upper ? "upper" : "lower", young_age, (long long)n_young_total, (long long)gbase[ng],
+                100.0 * n_young_total / std::max<int64_t>(gbase[ng], 1), (long long)n_young_groups, (long long)ng, KB, KY);
+      // ---- item lists: per team one solver list (one item per block), KB bulk helper lists (the
+      // team's groups round-robin, <= TS_CH old entries per item) and KY young helper lists ----
       const int64_t        NWARP = NW * (K + 1);
-      std::vector<int64_t> n_it(NWARP + 1, 0), team_blocks(NW, 0), team_groups(NW, 0);
-      std::vector<int32_t> helper_of(ng);
+      std::vector<int64_t> n_it(NWARP + 1, 0), team_blocks(NW, 0), team_groups(NW, 0), team_ygroups(NW, 0);
+      std::vector<int32_t> helper_of(ng), yhelper_of(ng, -1), b_ymask(nb, 0);
+      auto chunks = [](int32_t c) { return (c + TS_CH - 1) / TS_CH; };
       for (int64_t t = 0; t < nb; ++t)
         {
           const int32_t b  = border[t];
@@ -1218,8 +1344,14 @@ namespace glsns
           for (int32_t q = 0; q < b_ng[b]; ++q)
             {
               const int64_t g = group_of_block(b, q);
-              helper_of[g]    = (int32_t)(team_groups[tm]++ % K);
-              n_it[tm * (K + 1) + 1 + helper_of[g] + 1] += std::max<int64_t>(1, (cnt[g] + TS_CH - 1) / TS_CH);
+              helper_of[g]    = (int32_t)(team_groups[tm]++ % KB);
+              n_it[tm * (K + 1) + 1 + helper_of[g] + 1] += std::max(1, chunks(cnt[g] - n_young[g]));
+              if (n_young[g])
+                {
+                  yhelper_of[g] = KB + (int32_t)(team_ygroups[tm]++ % KY);
+                  n_it[tm * (K + 1) + 1 + yhelper_of[g] + 1] += chunks(n_young[g]);
+                  b_ymask[b] |= ((1 << grp_m[g]) - 1) << (grp_ptr[g] - b_r0[b]);
+                }
             }
         }
       for (int64_t w = 0; w < NWARP; ++w)
@@ -1235,6 +1367,7 @@ namespace glsns
             TrsvItem &it = items[(size_t)fill[tm * (K + 1)]++];
             it.rs0 = n_gdesc, it.r0 = b_r0[b], it.len = b_ng[b], it.e_off = 0, it.nlow = 0, it.fmask = 0;
             it.flags = b_m[b] | IT_SOLVER | (is_primary[b] ? 0 : IT_GUEST) | ((slot_of[b] % TS_NWIN) << 12);
+            it.gb    = b_ymask[b]; // (solver item: the rows of the block that get a young post)
           }
           for (int32_t q = 0; q < b_ng[b]; ++q)
             {
@@ -1247,23 +1380,26 @@ namespace glsns
                 gd.nlow = (int32_t)(diag[i] - rowptr[i]);
                 gd.fmask = (int32_t)(uint32_t)fmask[g], gd.fmask2 = (int32_t)(uint32_t)(fmask[g] >> 32);
               }
-              const int32_t nchunk = std::max(1, (cnt[g] + TS_CH - 1) / TS_CH);
-              for (int32_t c = 0; c < nchunk; ++c)
-                {
-                  TrsvItem  &it   = items[(size_t)fill[tm * (K + 1) + 1 + helper_of[g]]++];
-                  // (the entries solved last come last: the upper sweep takes the chunks of a
-                  // row from the far end, so that a helper waits on the group's final item only)
-                  const int  ch   = upper ? nchunk - 1 - c : c;
-                  const int  cntc = std::max(0, std::min(TS_CH, cnt[g] - ch * TS_CH));
-                  const bool last = c == nchunk - 1;
-                  it.rs0   = rowptr[i];
-                  it.r0    = (int32_t)i;
-                  it.len   = len;
-                  it.e_off = e_off[g] + ch * TS_CH;
-                  it.flags = m | (last ? IT_LAST : 0) | (cntc << 16);
-                  it.nlow  = (int32_t)(diag[i] - rowptr[i]);
-                  it.fmask = (bseq[b] << 4) | (int32_t)(i - b_r0[b]); // where its totals go
-                }
+              // entries [first, first + count) of the group's list in `ord`, <= TS_CH per item
+              auto emit = [&](const int32_t helper, const int32_t first, const int32_t count, const int extra) {
+                const int32_t nchunk = std::max(1, chunks(count));
+                for (int32_t c = 0; c < nchunk; ++c)
+                  {
+                    TrsvItem  &it   = items[(size_t)fill[tm * (K + 1) + 1 + helper]++];
+                    const int  cntc = std::max(0, std::min(TS_CH, count - c * TS_CH));
+                    it.rs0   = rowptr[i];
+                    it.r0    = (int32_t)i;
+                    it.len   = len;
+                    it.e_off = first + c * TS_CH;
+                    it.gb    = gbase[g];
+                    it.flags = m | (c == nchunk - 1 ? IT_LAST : 0) | extra | (cntc << 16);
+                    it.nlow  = (int32_t)(diag[i] - rowptr[i]);
+                    it.fmask = (bseq[b] << 4) | (int32_t)(i - b_r0[b]); // where its totals go
+                  }
+              };
+              emit(helper_of[g], 0, cnt[g] - n_young[g], 0);
+              if (n_young[g])
+                emit(yhelper_of[g], cnt[g] - n_young[g], n_young[g], IT_YOUNG);
             }
         }
       std::vector<int32_t> &row_warp = upper ? ctx->trsv_row_warp_u : ctx->trsv_row_warp_l;
@@ -1283,16 +1419,36 @@ namespace glsns
           memset(&D, 0, sizeof(D));
           D.offset  = off;
           D.n_items = (int32_t)(n_it[w + 1] - n_it[w]);
+          if (w % (K + 1) == 0)
+            { // a solver's list: every block's header travels with the block before it
+              D.first_m[0] = D.first_m[1] = 0x10101010;
+              for (int64_t k = n_it[w]; k < n_it[w + 1]; ++k)
+                {
+                  TrsvItem &it = items[(size_t)k];
+                  const int64_t j = k - n_it[w];
+                  if (j < TS_MBOX)
+                    {
+                      D.first_m[j >> 2] = (D.first_m[j >> 2] & ~(255 << (8 * (j & 3)))) | ((it.flags & 31) << (8 * (j & 3)));
+                      D.first_ym[j >> 1] |= ((int32_t)it.gb & 0xffff) << (16 * (j & 1));
+                    }
+                  if (j == 0)
+                    D.first_r0 = it.r0, D.first_flags = it.flags;
+                  it.e_off = k + 1 < n_it[w + 1] ? items[(size_t)k + 1].r0 : 0;
+                  it.nlow  = k + 1 < n_it[w + 1] ? items[(size_t)k + 1].flags : 0;
+                  it.pad_  = k + TS_MBOX < n_it[w + 1] ? (items[(size_t)k + TS_MBOX].flags & 31) | ((int32_t)items[(size_t)k + TS_MBOX].gb << 8) : TS_BR;
+                }
+            }
           for (int64_t k = n_it[w]; k < n_it[w + 1]; ++k)
             {
               const int32_t b16 = blob_bytes(items[(size_t)k].flags) / 16;
               blob_off[(size_t)k] = off;
               off += 16 * (int64_t)b16;
-              const int64_t j = k - n_it[w];
-              if (j < TS_NSLOT)
+              const int64_t j  = k - n_it[w];
+              const int     ns = w % (K + 1) == 0 ? TS_SNSLOT : TS_NSLOT; // (a team's first list is its solver's)
+              if (j < ns)
                 D.first16[j] = b16;
               else
-                next16[(size_t)(k - TS_NSLOT)] = b16;
+                next16[(size_t)(k - ns)] = b16;
             }
         }
       sw.n_items      = nit;
@@ -1301,6 +1457,7 @@ namespace glsns
       GLSNS_TRY(dev_upload(ctx, sw.gdesc, gdesc.data(), gdesc.size()));
       GLSNS_TRY(dev_upload(ctx, sw.blob_off, blob_off.data(), blob_off.size()));
       GLSNS_TRY(dev_upload(ctx, sw.next16, next16.data(), next16.size()));
+      GLSNS_TRY(dev_upload(ctx, sw.ord, ord.data(), ord.size()));
       GLSNS_TRY(dev_upload(ctx, sw.dir, reinterpret_cast<const unsigned char *>(dirv.data()),
                            dirv.size() * sizeof(TrsvWarpDir)));
       GLSNS_TRY(dev_alloc(ctx, sw.stream, (size_t)std::max<int64_t>(off, 16)));
@@ -1310,7 +1467,7 @@ namespace glsns
       if (nit)
         {
           trsv_pack_static_kernel<<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            nit, sw.items.p, sw.blob_off.p, sw.next16.p, ctx->col.p, sw.stream.p);
+            nit, sw.items.p, sw.blob_off.p, sw.next16.p, ctx->col.p, sw.ord.p, sw.stream.p);
           ctx->kernel_launches++;
           GLSNS_CUDA(ctx, cudaGetLastError());
         }
@@ -1438,7 +1595,7 @@ namespace glsns
         const int64_t nit = ctx->trsv_l.n_items;
         trsv_pack_values_kernel<false><<<(unsigned)((nit * 32 + 127) / 128), 128, 0, ctx->stream>>>(
           nit, ctx->trsv_l.items.p, ctx->trsv_l.gdesc.p, ctx->trsv_l.blob_off.p, ctx->lu.p,
-          ctx->trsv_l.stream.p);
+          ctx->trsv_l.ord.p, ctx->trsv_l.stream.p);
         ctx->kernel_launches++;
       }
     if (ctx->trsv_u.n_items)
@@ -1446,7 +1603,7 @@ namespace glsns
         const int64_t nit = ctx->trsv_u.n_items;
         trsv_pack_values_kernel<true><<<(unsigned)((nit * 32 + 127) / 128), 128, 0, ctx->stream>>>(
           nit, ctx->trsv_u.items.p, ctx->trsv_u.gdesc.p, ctx->trsv_u.blob_off.p, ctx->lu.p,
-          ctx->trsv_u.stream.p);
+          ctx->trsv_u.ord.p, ctx->trsv_u.stream.p);
         ctx->kernel_launches++;
       }
     GLSNS_CUDA(ctx, cudaGetLastError());
