@@ -45,7 +45,6 @@ namespace glsns
                    // helper item: where the totals go (block position << 4 | row offset)
     int32_t fmask2; // group descriptor: the same for the distances 32 ...
     int32_t pad_;
-    int64_t gb;     // helper item: where the group's entry list starts in TrsvSweep::ord (e_off counts from there)
   };
 
   // One sweep (lower or upper) of the ILU application in stream form (trsv.cu).
@@ -53,16 +52,16 @@ namespace glsns
   {
     DevBuf<TrsvItem>      items;    // per-warp item lists, concatenated
     DevBuf<TrsvItem>      gdesc;    // the groups of every block (a solver item's rs0 / len index it)
-    DevBuf<int64_t>       blob_off; // byte offset of each item's blob in the stream
+    DevBuf<int64_t>       blob_off; // byte offset of each item's blob in the stream (helper item: its indices)
+    DevBuf<int64_t>       blob_off_v; // helper item: byte offset of its values
     DevBuf<int32_t>       next16;   // bytes/16 of the blob NSLOT items ahead (same warp)
-    DevBuf<uint16_t>      ord;      // per group: positions in the row of the entries its helper items take, in item order
     DevBuf<unsigned char> dir;      // per-warp directory
     DevBuf<unsigned char> stream;   // headers, indices and factor values in consumption order
     int64_t               n_items = 0, stream_bytes = 0;
     void
     release()
     {
-      items.release(), gdesc.release(), blob_off.release(), next16.release(), ord.release(), dir.release(), stream.release();
+      items.release(), gdesc.release(), blob_off.release(), blob_off_v.release(), next16.release(), dir.release(), stream.release();
       n_items = stream_bytes = 0;
     }
   };

@@ -84,9 +84,11 @@ namespace glsns
     static_assert(TS_BR == TRSV_G * TS_BG && TS_WIN % 8 == 0 && TS_WIN >= 16 && TS_WIN + TS_BR <= TS_HIST,
                   "blocks of 16 rows; the window and the block being written share the history");
     // item blob (bytes, 16-byte aligned), first 16 bytes = header
-    //   helper item: r0 | flags | block position in the team's list << 4 | row offset in the
-    //                block | bytes/16 of the blob NSLOT items ahead;
-    //                then col 4*pad4(entries) | val 8*m*pad4(entries)
+    //   helper item, two blobs in two streams:
+    //                indices: r0 | flags | block position in the team's list << 4 | row offset in the
+    //                block | bytes/16 of the index blob TS_NCS items ahead | bytes/16 of the value
+    //                blob TS_NVS items ahead << 8; then col 4*pad4(entries)
+    //                values: val 8*m*pad4(entries) (at least 16 bytes)
     //   solver item (one per block): r0 of the NEXT block of the list | its flags | rows of the
     //                block TS_MBOX ahead | bytes/16 of the blob TS_SNSLOT items ahead; then the block's
     //                solved recurrence lane by lane: 2R lanes (R = rows padded to 4) x TS_CSTR bytes
@@ -99,9 +101,24 @@ namespace glsns
 #ifndef GLSNS_TRSV_THREADS
 #define GLSNS_TRSV_THREADS 512
 #endif
-    constexpr int TS_NSLOT     = GLSNS_TRSV_NSLOT; // ring slots of a helper warp
+    constexpr int TS_NCS       = 8;                // ring slots of a helper warp: column indices (+ header)
+    constexpr int TS_NVS       = GLSNS_TRSV_NSLOT; // ring slots of a helper warp: factor entries
     constexpr int TS_MAXWARPS  = GLSNS_TRSV_THREADS / 32;
-    constexpr int TS_SNSLOT    = 5; // ring slots of a solver warp
+#ifndef GLSNS_TRSV_POLL_REFRESH
+#define GLSNS_TRSV_POLL_REFRESH 1
+#endif
+#ifndef GLSNS_TRSV_POLL_SLEEP
+#define GLSNS_TRSV_POLL_SLEEP 0
+#endif
+#ifndef GLSNS_TRSV_REFRESH
+#define GLSNS_TRSV_REFRESH 0
+#endif
+#ifndef GLSNS_TRSV_DEPTH
+#define GLSNS_TRSV_DEPTH 2
+#endif
+    constexpr int TS_D = GLSNS_TRSV_DEPTH; // items a helper has in flight between requesting and using the solution entries
+    static_assert(TS_D >= 2 && TS_D <= 4 && TS_D < TS_NCS, "pipeline depth of the helpers");
+    constexpr int TS_SNSLOT    = 4; // ring slots of a solver warp
     constexpr int TS_MAX_SLOTS = 9;
     constexpr int TS_SMEM_MAX  = 227 * 1024;
 
@@ -112,7 +129,6 @@ namespace glsns
     constexpr int IT_LAST   = 1 << 8;
     constexpr int IT_SOLVER = 1 << 9;
     constexpr int IT_GUEST  = 1 << 10;
-    constexpr int IT_YOUNG  = 1 << 11; // helper item of a group's YOUNG entries (posts in the second mailbox field)
     constexpr int TS_NWIN   = 4;
 
     __host__ __device__ inline int
@@ -124,7 +140,13 @@ namespace glsns
     blob_bytes(int flags)
     {
       const int m = flags & 31, c = pad4(flags >> 16);
-      return (flags & IT_SOLVER) ? TS_OFF_C + TS_CSTR * 2 * pad4(m) : TS_OFF_COL0 + 4 * c + 8 * m * c;
+      return (flags & IT_SOLVER) ? TS_OFF_C + TS_CSTR * 2 * pad4(m) : TS_OFF_COL0 + 4 * c;
+    }
+    __host__ __device__ inline int
+    value_blob_bytes(int flags) // helper items only
+    {
+      const int m = flags & 31, c = pad4(flags >> 16);
+      return 8 * m * c > 16 ? 8 * m * c : 16;
     }
     // per-warp entry of the stream directory (64 bytes)
     struct TrsvWarpDir
@@ -134,9 +156,11 @@ namespace glsns
       int32_t first16[TS_MAX_SLOTS]; // bytes/16 of the first NSLOT blobs
       int32_t first_m[2];            // solver: rows of its first 8 blocks, 8 bits each
       int32_t first_r0, first_flags; // solver: header of its first block
-      int32_t first_ym[4];           // solver: rows with a young post in its first 8 blocks, 16 bits each
-      int32_t pad[12];
+      int64_t offset_v;              // helper: byte offset of its first value blob
+      int32_t firstv16[4];           // helper: bytes/16 of its first TS_NVS value blobs
+      int32_t pad[10];
     };
+    static_assert(TS_NVS <= 4 && TS_NCS <= TS_MAX_SLOTS, "directory entry");
     static_assert(sizeof(TrsvWarpDir) == 128, "directory entry");
 
     __device__ __forceinline__ unsigned long long
@@ -215,8 +239,7 @@ namespace glsns
     __global__ void __launch_bounds__(256)
     trsv_pack_static_kernel(const int64_t n_items, const TrsvItem *__restrict__ items,
                             const int64_t *__restrict__ blob_off, const int32_t *__restrict__ next16,
-                            const int32_t *__restrict__ col, const uint16_t *__restrict__ ord,
-                            unsigned char *__restrict__ stream)
+                            const int32_t *__restrict__ col, unsigned char *__restrict__ stream)
     {
       const int64_t it   = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       const int     lane = threadIdx.x & 31;
@@ -232,7 +255,7 @@ namespace glsns
       const int cntc = d.flags >> 16, cp = pad4(cntc);
       int32_t  *bc   = reinterpret_cast<int32_t *>(B + TS_OFF_COL0);
       for (int k = lane; k < cp; k += 32)
-        bc[k] = k < cntc ? col[d.rs0 + ord[d.gb + d.e_off + k]] : d.r0; // padding: any valid index
+        bc[k] = k < cntc ? col[d.rs0 + d.e_off + k] : d.r0; // padding: any valid index
     }
 
     // values (after every factorisation)
@@ -240,8 +263,8 @@ namespace glsns
     __global__ void __launch_bounds__(128)
     trsv_pack_values_kernel(const int64_t n_items, const TrsvItem *__restrict__ items,
                             const TrsvItem *__restrict__ gdesc,
-                            const int64_t *__restrict__ blob_off, const double *__restrict__ lu,
-                            const uint16_t *__restrict__ ord, unsigned char *__restrict__ stream)
+                            const int64_t *__restrict__ blob_off, const int64_t *__restrict__ blob_off_v,
+                            const double *__restrict__ lu, unsigned char *__restrict__ stream)
     {
       __shared__ double TF[4][TS_BR * TS_BR + TS_BR * TS_WIN]; // per warp: T [16][16], F [16][TS_WIN]
       const int64_t it   = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -253,10 +276,12 @@ namespace glsns
       const int      m = d.flags & 31, cntc = d.flags >> 16, cp = pad4(cntc);
       if (!(d.flags & IT_SOLVER))
         {
-          double *bv = reinterpret_cast<double *>(B + TS_OFF_COL0 + 4 * cp);
+          double *bv = reinterpret_cast<double *>(stream + blob_off_v[it]);
+          if (m * cp == 0 && lane < 2)
+            bv[lane] = 0.0;
           for (int a = 0; a < m; ++a)
             for (int k = lane; k < cp; k += 32)
-              bv[a * cp + k] = k < cntc ? __ldcs(lu + d.rs0 + (int64_t)a * d.len + ord[d.gb + d.e_off + k]) : 0.0;
+              bv[a * cp + k] = k < cntc ? __ldcs(lu + d.rs0 + (int64_t)a * d.len + d.e_off + k) : 0.0;
           return;
         }
       // Solver blob of a BLOCK (<= 4 consecutive groups of one chain, rows [r0, r0 + m)).
@@ -356,18 +381,17 @@ namespace glsns
     //     block (kept in a tiny shared-memory window) and M, G the block's recurrence
     //     solved ahead of time; publish.  The chain advances 16 rows per step.
     constexpr int TS_MBOX  = 8;  // mailbox entries (blocks) per team
-    constexpr int TS_HSLOT = TS_OFF_COL0 + 4 * TS_CH + 8 * TRSV_G * TS_CH; // 2320 (64-entry items)
+    constexpr int TS_CSLOT  = TS_OFF_COL0 + 4 * TS_CH;                      // 272 (64-entry items)
+    constexpr int TS_VSLOT  = 8 * TRSV_G * TS_CH;                           // 2048
+    constexpr int TS_HBYTES = TS_NCS * TS_CSLOT + TS_NVS * TS_VSLOT;        // rings of one helper
     constexpr int TS_SSLOT = TS_OFF_C + TS_CSTR * 2 * TS_BR;                // 8720 (48-row window)
     // team area: windows 4 x 1024 (every row twice, TS_HIST apart: a lane reads its part of a
     // window at fixed offsets from one base, no wrap-around) | mailbox 8 x 128 | solved counter
-    // 16 | barriers.  A mailbox entry has two fields of 16 totals: those of the old entries (with
-    // the right-hand side) and those of the young ones
-    constexpr int TS_MENT      = 2 * TS_BR; // doubles per mailbox entry
+    // 16 | barriers
+    constexpr int TS_MENT      = TS_BR; // doubles per mailbox entry
     constexpr int TS_OFF_MBOX  = 2 * 8 * TS_HIST * TS_NWIN;
-    constexpr int TS_TEAM_AREA = TS_OFF_MBOX + 8 * TS_MENT * TS_MBOX + 512;
-    static_assert(TS_MBOX == 8 && TS_NWIN == 4 && TS_MENT == 32 &&
-                    TS_OFF_MBOX + 8 * TS_MENT * TS_MBOX + 16 + 8 * (11 * TS_NSLOT + TS_SNSLOT) <= TS_TEAM_AREA,
-                  "team area");
+    constexpr int TS_TEAM_AREA = TS_OFF_MBOX + 8 * TS_MENT * TS_MBOX + 16 + 8 * (11 * (TS_NCS + TS_NVS) + TS_SNSLOT) + 16;
+    static_assert(TS_MBOX == 8 && TS_NWIN == 4 && TS_MENT == 16 && TS_TEAM_AREA % 16 == 0, "team area");
 
     template <bool UPPER, bool TRACE>
     __global__ void __launch_bounds__(GLSNS_TRSV_THREADS, 1)
@@ -404,11 +428,11 @@ namespace glsns
       if (team_in_cta >= n_teams_cta || role > K)
         return;
       const int64_t team      = (int64_t)team_in_cta * gridDim.x + blockIdx.x; // consecutive lists on different SMs
-      const size_t  team_smem = (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_SNSLOT * TS_SSLOT + TS_TEAM_AREA;
+      const size_t  team_smem = (size_t)K * TS_HBYTES + (size_t)TS_SNSLOT * TS_SSLOT + TS_TEAM_AREA;
       unsigned char *T0   = smem_all + (size_t)team_in_cta * team_smem;
-      unsigned char *area = T0 + (size_t)K * TS_NSLOT * TS_HSLOT + (size_t)TS_SNSLOT * TS_SSLOT;
+      unsigned char *area = T0 + (size_t)K * TS_HBYTES + (size_t)TS_SNSLOT * TS_SSLOT;
       double        *wsm_all = reinterpret_cast<double *>(area);         // [TS_NWIN][2][64] chain windows by row & 63
-      double        *mbox = reinterpret_cast<double *>(area + TS_OFF_MBOX); // [TS_MBOX][2][16], all-ones = empty
+      double        *mbox = reinterpret_cast<double *>(area + TS_OFF_MBOX); // [TS_MBOX][16], all-ones = empty
       volatile int  *done = reinterpret_cast<volatile int *>(area + TS_OFF_MBOX + 8 * TS_MENT * TS_MBOX); // blocks solved
       unsigned long long *bars_all =
         reinterpret_cast<unsigned long long *>(area + TS_OFF_MBOX + 8 * TS_MENT * TS_MBOX + 16);
@@ -425,11 +449,10 @@ namespace glsns
           // (entries of rows a block does not have hold 0, so that the solver needs no mask)
           const TrsvWarpDir *D0 = dir + ((int64_t)team_in_cta * gridDim.x + blockIdx.x) * (K + 1);
 #pragma unroll
-          for (int e = 0; e < TS_MBOX; ++e)
+          for (int k = 0; k < TS_MBOX * TS_BR / 32; ++k)
             {
-              const int me = (D0->first_m[e >> 2] >> (8 * (e & 3))) & 255, ym = (D0->first_ym[e >> 1] >> (16 * (e & 1))) & 0xffff;
-              reinterpret_cast<unsigned long long *>(mbox)[lane + TS_MENT * e] =
-                (lane < TS_BR ? lane < me : (ym >> (lane - TS_BR)) & 1) ? SENTINEL : 0ull;
+              const int e = 2 * k + (lane >> 4), me = (D0->first_m[e >> 2] >> (8 * (e & 3))) & 255;
+              reinterpret_cast<unsigned long long *>(mbox)[lane + 32 * k] = (lane & 15) < me ? SENTINEL : 0ull;
             }
           if (lane == 0)
             *done = 0;
@@ -458,9 +481,9 @@ namespace glsns
           // load is base + immediate: the coefficients lie lane by lane (8 x 128-bit loads of G, 4
           // of M), the window keeps every row twice (no wrap-around), a block's header arrives
           // with the block before it (the window loads go out before the ring is even looked at).
-          const unsigned      ring0 = (unsigned)__cvta_generic_to_shared(T0 + (size_t)K * TS_NSLOT * TS_HSLOT);
-          unsigned char      *ring  = T0 + (size_t)K * TS_NSLOT * TS_HSLOT;
-          unsigned long long *bars  = bars_all + K * TS_NSLOT;
+          const unsigned      ring0 = (unsigned)__cvta_generic_to_shared(T0 + (size_t)K * TS_HBYTES);
+          unsigned char      *ring  = T0 + (size_t)K * TS_HBYTES;
+          unsigned long long *bars  = bars_all + K * (TS_NCS + TS_NVS);
           int64_t             n_iss = 0;
           if (lane == 0)
             {
@@ -537,7 +560,7 @@ namespace glsns
                 for (;;)
                   {
                     unsigned long long b;
-                    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(b) : "r"(mv + 8 * lane));
+                    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(b) : "r"(mv + 8 * (lane & 15)));
                     if (__all_sync(0xffffffffu, b != SENTINEL))
                       break;
                     if ((++spins & 4095) == 0 &&
@@ -550,19 +573,12 @@ namespace glsns
               }
               TS_TICK(2)
               {
-                double t[8], ty[8];
+                double t[8];
                 const unsigned tv = mv + 64 * hh;
                 asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2];" : "=d"(t[0]), "=d"(t[1]) : "r"(tv));
                 asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(t[2]), "=d"(t[3]) : "r"(tv));
                 asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+32];" : "=d"(t[4]), "=d"(t[5]) : "r"(tv));
                 asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+48];" : "=d"(t[6]), "=d"(t[7]) : "r"(tv));
-                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+128];" : "=d"(ty[0]), "=d"(ty[1]) : "r"(tv));
-                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+144];" : "=d"(ty[2]), "=d"(ty[3]) : "r"(tv));
-                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+160];" : "=d"(ty[4]), "=d"(ty[5]) : "r"(tv));
-                asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2+176];" : "=d"(ty[6]), "=d"(ty[7]) : "r"(tv));
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  t[j] += ty[j];
 #pragma unroll
                 for (int j = 0; j < 8; j += 4)
                   {
@@ -594,9 +610,8 @@ namespace glsns
               __syncwarp(); // the window rows are written, the mailbox entry is read
               // hand the entry back: empty it for the block TS_MBOX ahead (0 in the rows that
               // block does not have), then let that block in
-              asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(mv + 8 * lane),
-                           "l"((lane < TS_BR ? lane < (h.z & 255) : ((h.z >> 8) >> (lane - TS_BR)) & 1) ? SENTINEL : 0ull)
-                           : "memory");
+              if (lane < TS_BR)
+                asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(mv + 8 * lane), "l"(lane < h.z ? SENTINEL : 0ull) : "memory");
               if (lane == 0)
                 *done = (int)g + 1;
               TS_TICK(3)
@@ -626,58 +641,90 @@ namespace glsns
         }
 
       // =============================== helper ===============================
-      const int           hid  = role - 1;
-      unsigned char      *ring = T0 + (size_t)hid * TS_NSLOT * TS_HSLOT;
-      unsigned long long *bars = bars_all + hid * TS_NSLOT;
-      int64_t             n_iss = 0;
+      // A helper's rate is set by the latency of its gathers: an item (<= 64 entries of a group)
+      // is requested in stage G and consumed TS_D steps later in stage R, so a helper has TS_D
+      // items' worth of solution entries in flight and finishes one item every latency / TS_D.
+      // With the whole blob (indices + values) in one ring the depth was 2 -- 0.5 us per item,
+      // 0.7 us per block with 7 helpers, which is what a chain step took (trace, p10) however
+      // lean the solver warp was.  So the column indices (272 B) and the factor entries (2 KB)
+      // travel in rings of their own: the indices are needed in G only (their slot is refilled
+      // at once, 8 slots), the values in R only (4 slots), and the depth is a matter of
+      // registers (one set per item in flight), not of shared memory.
+      const int           hid   = role - 1;
+      unsigned char      *cring = T0 + (size_t)hid * TS_HBYTES, *vring = cring + TS_NCS * TS_CSLOT;
+      unsigned long long *cbar  = bars_all + hid * (TS_NCS + TS_NVS), *vbar = cbar + TS_NCS;
+      const unsigned char *srcv = stream + D->offset_v;
+      int64_t             n_issc = 0, n_issv = 0;
       if (lane == 0)
         {
-          for (int s = 0; s < TS_NSLOT; ++s)
-            mbar_init(bars + s, 1);
+          for (int s = 0; s < TS_NCS + TS_NVS; ++s)
+            mbar_init(cbar + s, 1);
           asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          for (int s = 0; s < TS_NSLOT && s < n_items; ++s)
+          for (int s = 0; s < TS_NCS && s < n_items; ++s)
             {
               const unsigned bytes = 16u * (unsigned)D->first16[s];
-              mbar_expect_tx(bars + s, bytes);
-              bulk_load(ring + (size_t)s * TS_HSLOT, src, bytes, bars + s, policy);
+              mbar_expect_tx(cbar + s, bytes);
+              bulk_load(cring + (size_t)s * TS_CSLOT, src, bytes, cbar + s, policy);
               src += bytes;
-              ++n_iss;
+              ++n_issc;
+            }
+          for (int s = 0; s < TS_NVS && s < n_items; ++s)
+            {
+              const unsigned bytes = 16u * (unsigned)D->firstv16[s];
+              mbar_expect_tx(vbar + s, bytes);
+              bulk_load(vring + (size_t)s * TS_VSLOT, srcv, bytes, vbar + s, policy);
+              srcv += bytes;
+              ++n_issv;
             }
         }
       __syncwarp();
-      // pipeline registers: three rotating sets (no copies: a copy would wait for the
-      // loads in flight), selected at compile time by the unrolled loop
-      int32_t            cS[3][TS_U];
-      unsigned long long bS[3][TS_U];
-      unsigned           pS[3] = {0, 0, 0};
-      double             rS[3] = {0, 0, 0}; // right-hand side of row r0 + lane
-      double             acc[TRSV_G];
+      // pipeline registers: TS_D + 1 rotating sets (no copies: a copy would wait for the loads
+      // in flight), selected at compile time by the unrolled loop
+      constexpr int      NS = TS_D + 1;
+      int32_t            cS[NS][TS_U];
+      unsigned long long bS[NS][TS_U];
+      unsigned           pS[NS];
+      int                fS[NS], zS[NS], wS[NS]; // header of the item: flags, where its totals go, sizes of the blobs ahead
+      int                xS[NS];                 // its first row (trace only)
+      double             rS[NS];                 // right-hand side of row r0 + lane
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+        pS[k] = 0, fS[k] = 0, zS[k] = 0, wS[k] = 0, xS[k] = 0, rS[k] = 0;
+      double acc[TRSV_G];
 #pragma unroll
       for (int a = 0; a < TRSV_G; ++a)
         acc[a] = 0;
       int      slotG = 0, slotR = 0;
-      unsigned phaseG = 0;
+      unsigned phaseG = 0, phaseR = 0;
       unsigned long long n_rounds = 0, n_polled = 0, n_waited = 0; // debugging aid (trace)
-      // one pipeline step: G(it) into set KG, R(it-2) from set (KG+1)%3
+      long long          hst[4] = {0, 0, 0, 0}; // trace: cycles waiting for indices, values, solution entries, a free mailbox entry
+      const long long    h_begin = TRACE ? clock64() : 0;
+#define HS_WAIT(k, stmt)                 \
+  {                                      \
+    long long c0_ = TRACE ? clock64() : 0; \
+    stmt;                                \
+    if (TRACE)                           \
+      hst[k] += clock64() - c0_;         \
+  }
+      // one pipeline step: G(it) into set KG, R(it - TS_D) from set (KG + 1) % NS
       auto step = [&](auto KG, const int64_t it) {
-        constexpr int      kg = decltype(KG)::value, kr = (kg + 1) % 3;
+        constexpr int      kg = decltype(KG)::value, kr = (kg + 1) % NS, k1 = (kg + 2) % NS, k2 = (kg + 3) % NS;
         int32_t(&cN)[TS_U]            = cS[kg];
         unsigned long long(&bN)[TS_U] = bS[kg];
         unsigned &pendN               = pS[kg];
         int32_t(&cG)[TS_U]            = cS[kr];
         unsigned long long(&bG)[TS_U] = bS[kr];
         unsigned &pendG               = pS[kr];
-        // ---- G(it): wait for the item, request the solution entries it refers to ----
+        // ---- G(it): wait for the indices, request the solution entries they refer to ----
         pendN = 0;
         if (it < n_items)
           {
-            while (!mbar_try_wait(bars + slotG, phaseG))
-              ;
-            const unsigned char *S     = ring + (size_t)slotG * TS_HSLOT;
-            const int4           h     = *reinterpret_cast<const int4 *>(S);
-            const int            flags = h.y, cntc = flags >> 16;
-            const int32_t       *scol  = reinterpret_cast<const int32_t *>(S + TS_OFF_COL0);
+            HS_WAIT(0, while (!mbar_try_wait(cbar + slotG, phaseG));)
+            unsigned char *S     = cring + (size_t)slotG * TS_CSLOT;
+            const int4     h     = *reinterpret_cast<const int4 *>(S);
+            const int      flags = h.y, cntc = flags >> 16;
+            const int32_t *scol  = reinterpret_cast<const int32_t *>(S + TS_OFF_COL0);
 #pragma unroll
             for (int u = 0; u < TS_U; ++u)
               {
@@ -692,22 +739,49 @@ namespace glsns
             for (int u = 0; u < TS_U; ++u)
               if (pendN & (1u << u))
                 bN[u] = ld_relaxed_u64(x + cN[u]);
-            if ((flags & (IT_LAST | IT_YOUNG)) == IT_LAST && lane < (flags & 31))
-              rS[kg] = rhs_vec[h.x + lane];
-            slotG = slotG + 1 == TS_NSLOT ? 0 : slotG + 1;
+            rS[kg] = 0.0; // (lane 8 a ends up with the total of row a: it takes that row's right-hand side)
+            if ((flags & IT_LAST) && (lane & 7) == 0 && (lane >> 3) < (flags & 31))
+              rS[kg] = rhs_vec[h.x + (lane >> 3)];
+            fS[kg] = flags, zS[kg] = h.z, wS[kg] = h.w;
+            if (TRACE)
+              xS[kg] = h.x;
+            __syncwarp(); // every lane has its indices: the slot takes the indices TS_NCS items ahead
+            if (lane == 0 && n_issc < n_items)
+              {
+                const unsigned bytes = 16u * (unsigned)(h.w & 255);
+                mbar_expect_tx(cbar + slotG, bytes);
+                bulk_load(S, src, bytes, cbar + slotG, policy);
+                src += bytes;
+                ++n_issc;
+              }
+            slotG = slotG + 1 == TS_NCS ? 0 : slotG + 1;
             phaseG ^= slotG == 0;
           }
-        // ---- R(it-2): entries not there yet are re-read until they are; multiply ----
-        if (it >= 2)
+#if GLSNS_TRSV_REFRESH
+        // the items between G and R: entries that were not there when last looked are requested
+        // again at every step, so that an item that reaches R has been looked at a step ago, not
+        // TS_D steps ago
+#pragma unroll
+        for (int u = 0; u < TS_U; ++u)
           {
-            const unsigned char *S     = ring + (size_t)slotR * TS_HSLOT;
-            const int4           h     = *reinterpret_cast<const int4 *>(S);
-            const int            flags = h.y, m = flags & 31, cp = pad4(flags >> 16);
-            const double        *sval  = reinterpret_cast<const double *>(S + TS_OFF_COL0 + 4 * cp);
+            if ((pS[k1] & (1u << u)) && bS[k1][u] == SENTINEL)
+              bS[k1][u] = ld_relaxed_u64(x + cS[k1][u]);
+            if (NS > 3 && (pS[k2] & (1u << u)) && bS[k2][u] == SENTINEL)
+              bS[k2][u] = ld_relaxed_u64(x + cS[k2][u]);
+          }
+#endif
+        // ---- R(it - TS_D): entries not there yet are re-read until they are; multiply ----
+        if (it >= TS_D)
+          {
+            const int    flags = fS[kr], m = flags & 31, cp = pad4(flags >> 16);
+            unsigned char *SV  = vring + (size_t)slotR * TS_VSLOT;
+            const double *sval = reinterpret_cast<const double *>(SV);
             long long            spins = 0;
             unsigned long long   t_rs = 0, t_det = 0; // debugging aid (trace)
             if (TRACE)
               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_rs));
+            HS_WAIT(1, while (!mbar_try_wait(vbar + slotR, phaseR));)
+            const long long cp0 = TRACE ? clock64() : 0;
             for (;;)
               {
 #pragma unroll
@@ -737,14 +811,19 @@ namespace glsns
                 // the entries of the two items behind this one that were not there when they
                 // were first read are refreshed in the same round trip: when this item is
                 // done, they need no round trip of their own
+#if GLSNS_TRSV_POLL_REFRESH
 #pragma unroll
                 for (int u = 0; u < TS_U; ++u)
                   {
-                    if ((pendN & (1u << u)) && bN[u] == SENTINEL)
-                      bN[u] = ld_relaxed_u64(x + cN[u]);
-                    if ((pS[(kg + 2) % 3] & (1u << u)) && bS[(kg + 2) % 3][u] == SENTINEL)
-                      bS[(kg + 2) % 3][u] = ld_relaxed_u64(x + cS[(kg + 2) % 3][u]);
+                    if ((pS[k1] & (1u << u)) && bS[k1][u] == SENTINEL)
+                      bS[k1][u] = ld_relaxed_u64(x + cS[k1][u]);
+                    if (NS > 3 && (pS[k2] & (1u << u)) && bS[k2][u] == SENTINEL)
+                      bS[k2][u] = ld_relaxed_u64(x + cS[k2][u]);
                   }
+#endif
+#if GLSNS_TRSV_POLL_SLEEP
+                __nanosleep(GLSNS_TRSV_POLL_SLEEP);
+#endif
                 // bug guard: give up after seconds of waiting, or as soon as another
                 // warp has given up (the host reports GLSNS_ERR_CUDA)
                 if ((++spins & 1023) == 0 &&
@@ -755,46 +834,47 @@ namespace glsns
                   }
               }
             if (TRACE)
-              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_det));
+              {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_det));
+                if (spins)
+                  hst[2] += clock64() - cp0;
+              }
             if (flags & IT_LAST)
               {
-                // the group is complete: fold in the right-hand side, total over the
-                // warp, post in the mailbox once the solver has freed the entry
-                if (!(flags & IT_YOUNG))
-                  {
-#pragma unroll
-                    for (int a = 0; a < TRSV_G; ++a)
-                      if (lane == a && a < m)
-                        acc[a] -= rS[kr];
-                  }
-                // four totals over 32 lanes in 6 shuffles: halve the number of rows a lane
-                // carries while the partners are 16 and 8 lanes apart, then sum over the
-                // rest; lane 8 a ends up with the total of row a
+                // the group is complete: total over the warp, fold in the right-hand side, post
+                // in the mailbox once the solver has freed the entry.  The four rows are
+                // transposed through shared memory (the item's value slot: its entries are
+                // used up) so that eight lanes share a row: lane (a, s) = (lane >> 3, lane & 7)
+                // adds four partial sums of row a, three shuffles do the rest -- a third of
+                // the instructions of reducing four values over 32 lanes with shuffles alone;
+                // lane 8 a ends up with the total of row a
                 double tot;
                 {
-                  const bool   h16 = lane & 16, h8 = lane & 8;
-                  const double s0 = h16 ? acc[0] : acc[2], s1 = h16 ? acc[1] : acc[3];
-                  double       k0 = h16 ? acc[2] : acc[0], k1 = h16 ? acc[3] : acc[1];
-                  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-                  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                  tot = (h8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+                  double *scr = reinterpret_cast<double *>(SV);
+                  __syncwarp();
+#pragma unroll
+                  for (int a = 0; a < TRSV_G; ++a)
+                    scr[a * 32 + lane] = acc[a];
+                  __syncwarp();
+                  const double2 v0 = reinterpret_cast<const double2 *>(scr)[2 * lane],
+                                v1 = reinterpret_cast<const double2 *>(scr)[2 * lane + 1];
+                  tot = (v0.x + v0.y) + (v1.x + v1.y);
                   tot += __shfl_xor_sync(0xffffffffu, tot, 4);
                   tot += __shfl_xor_sync(0xffffffffu, tot, 2);
                   tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                  tot -= rS[kr];
                 }
                 // (header: position of the group's block in the team's list << 4 | row offset)
-                const int bseq = h.z >> 4, boff = h.z & 15;
+                const int bseq = zS[kr] >> 4, boff = zS[kr] & 15;
                 volatile unsigned long long *mv = reinterpret_cast<volatile unsigned long long *>(
-                  mbox + (bseq & (TS_MBOX - 1)) * TS_MENT + ((flags & IT_YOUNG) ? TS_BR : 0) + boff);
+                  mbox + (bseq & (TS_MBOX - 1)) * TS_MENT + boff);
                 spins = 0;
                 // the entry is this block's once the solver is within TS_MBOX blocks of it
-                while (*done + TS_MBOX <= bseq)
-                  if ((++spins & 4095) == 0 &&
-                      (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0))
-                    {
-                      atomicExch(&counters[1], 2);
-                      break;
-                    }
+                HS_WAIT(3, while (*done + TS_MBOX <= bseq) if ((++spins & 4095) == 0 &&
+                                                               (spins > 64 * SPIN_LIMIT || *(volatile int *)(counters + 1) != 0)) {
+                  atomicExch(&counters[1], 2);
+                  break;
+                })
                 if ((lane & 7) == 0 && (lane >> 3) < m)
                   {
                     unsigned long long b = (unsigned long long)__double_as_longlong(tot);
@@ -805,36 +885,45 @@ namespace glsns
                       {
                         unsigned long long tns;
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-                        trace[4 * trace_n + h.x + (lane >> 3)] = tns;
-                        trace[6 * trace_n + h.x + (lane >> 3)] = t_rs;  // began the group's last item
-                        trace[8 * trace_n + h.x + (lane >> 3)] = t_det; // had all its inputs
+                        trace[4 * trace_n + xS[kr] + (lane >> 3)] = tns;
+                        trace[6 * trace_n + xS[kr] + (lane >> 3)] = t_rs;  // began the group's last item
+                        trace[8 * trace_n + xS[kr] + (lane >> 3)] = t_det; // had all its inputs
                       }
                   }
 #pragma unroll
                 for (int a = 0; a < TRSV_G; ++a)
                   acc[a] = 0;
               }
-            __syncwarp(); // every lane is done with the slot before it is refilled
-            if (lane == 0 && n_iss < n_items)
+            __syncwarp(); // every lane is done with the values before the slot is refilled
+            if (lane == 0 && n_issv < n_items)
               {
-                const unsigned bytes = 16u * (unsigned)h.w; // size of the item TS_NSLOT ahead
-                mbar_expect_tx(bars + slotR, bytes);
-                bulk_load(ring + (size_t)slotR * TS_HSLOT, src, bytes, bars + slotR, policy);
-                src += bytes;
-                ++n_iss;
+                const unsigned bytes = 16u * (unsigned)((wS[kr] >> 8) & 255); // the values TS_NVS items ahead
+                if (flags & IT_LAST) // (the slot served as scratch for the reduction: generic writes before the bulk copy)
+                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(vbar + slotR, bytes);
+                bulk_load(SV, srcv, bytes, vbar + slotR, policy);
+                srcv += bytes;
+                ++n_issv;
               }
-            slotR = slotR + 1 == TS_NSLOT ? 0 : slotR + 1;
+            slotR = slotR + 1 == TS_NVS ? 0 : slotR + 1;
+            phaseR ^= slotR == 0;
           }
       };
-      for (int64_t it = 0; it < n_items + 2; it += 3)
+      for (int64_t it = 0; it < n_items + TS_D; it += NS)
         {
           step(std::integral_constant<int, 0>(), it);
-          if (it + 1 < n_items + 2)
+          if (it + 1 < n_items + TS_D)
             step(std::integral_constant<int, 1>(), it + 1);
-          if (it + 2 < n_items + 2)
+          if (it + 2 < n_items + TS_D)
             step(std::integral_constant<int, 2>(), it + 2);
+          if constexpr (NS > 3)
+            if (it + 3 < n_items + TS_D)
+              step(std::integral_constant<int, 3>(), it + 3);
+          if constexpr (NS > 4)
+            if (it + 4 < n_items + TS_D)
+              step(std::integral_constant<int, 4>(), it + 4);
         }
-      if (TRACE && 8 * (int64_t)gridDim.x * n_teams_cta + (team + 1) * 4 <= trace_n)
+      if (TRACE && 20 * (int64_t)gridDim.x * n_teams_cta + (team + 1) * 8 <= trace_n)
         { // per helper lane: items that had to wait, polling rounds, entries re-read
           for (int o = 16; o > 0; o >>= 1)
             n_polled += __shfl_xor_sync(0xffffffffu, n_polled, o);
@@ -845,7 +934,13 @@ namespace glsns
               atomicAdd(hc + 1, n_waited);
               atomicAdd(hc + 2, n_rounds);
               atomicAdd(hc + 3, n_polled);
+              // cycles: waiting for indices, values, solution entries, a mailbox entry; all
+              unsigned long long *hs = trace + 2 * trace_n + 12 * (int64_t)gridDim.x * n_teams_cta + team * 8;
+              for (int k = 0; k < 4; ++k)
+                atomicAdd(hs + k, (unsigned long long)hst[k]);
+              atomicAdd(hs + 4, (unsigned long long)(clock64() - h_begin));
             }
+#undef HS_WAIT
         }
     }
 
@@ -877,7 +972,7 @@ namespace glsns
     size_t
     team_smem_bytes(int helpers)
     {
-      return (size_t)helpers * TS_NSLOT * TS_HSLOT + (size_t)TS_SNSLOT * TS_SSLOT + TS_TEAM_AREA;
+      return (size_t)helpers * TS_HBYTES + (size_t)TS_SNSLOT * TS_SSLOT + TS_TEAM_AREA;
     }
 
     TrsvConfig
@@ -1275,66 +1370,11 @@ namespace glsns
                 (long long)NW, (long long)n_heads, (long long)n_steals, (long long)n_interrupted);
       // ---- item lists: per team one solver list (one item per block) and K helper lists
       // (the team's groups round-robin, <= TS_CH entries per item) ----
-      // YOUNG entries.  The sweep is a pipeline of chains: a block's inputs from other chains
-      // were published anywhere between a hop and many levels before it is solved, and the
-      // few that are still in flight when the helpers get to the group (2-4 % of the entries;
-      // 70 % of the groups have none) used to stall a helper's whole list behind them: totals
-      // that depended on old entries alone were posted late, and the variance of that delay
-      // (p50 1.7-2.4 us, p90 6 us) is what the critical path is made of.  So a group's entries
-      // are split by the AGE of the row they refer to (block levels between the two blocks):
-      // the old ones go to the team's bulk helpers, which then never wait for anything recent
-      // and run ahead of the solver; the young ones (age <= young_age) form small items of
-      // their own, served by dedicated helpers that do nothing else, and are posted in a
-      // second mailbox field.  `ord` lists, group by group, the positions (in the row) of the
-      // entries the helpers take: old ones first, young ones behind, each oldest first.
-      const int32_t young_age = getenv("GLSNS_TRSV_YOUNG") ? atoi(getenv("GLSNS_TRSV_YOUNG")) : 2;
-      const int     KY = young_age > 0 && K >= 3 ?
-                           std::max(1, std::min(K - 2, getenv("GLSNS_TRSV_YOUNG_HELPERS") ? atoi(getenv("GLSNS_TRSV_YOUNG_HELPERS")) : 2)) :
-                           0;
-      const int     KB = K - KY; // bulk helpers
-      std::vector<int64_t>  gbase(ng + 1, 0);
-      std::vector<int32_t>  n_young(ng, 0);
-      for (int64_t g = 0; g < ng; ++g)
-        gbase[g + 1] = gbase[g] + cnt[g];
-      std::vector<uint16_t> ord((size_t)std::max<int64_t>(gbase[ng], 1));
-      int64_t               n_young_total = 0, n_young_groups = 0;
-      for (int64_t g = 0; g < ng; ++g)
-        {
-          const int64_t rs = rowptr[grp_ptr[g]], k0 = rs + e_off[g], k1 = k0 + cnt[g];
-          const int32_t b  = blk_of[g];
-          uint16_t     *o  = ord.data() + gbase[g];
-          int32_t       no = 0, ny = 0;
-          // oldest first: ascending columns in the lower sweep, descending in the upper one
-          auto young = [&](int64_t k) {
-            const int32_t dg = grp_of[col[k]];
-            return KY > 0 && dg >= 0 && blev[b] - blev[blk_of[dg]] <= young_age;
-          };
-          for (int64_t kk = 0; kk < cnt[g]; ++kk)
-            {
-              const int64_t k = upper ? k1 - 1 - kk : k0 + kk;
-              if (!young(k))
-                o[no++] = (uint16_t)(k - rs);
-            }
-          for (int64_t kk = 0; kk < cnt[g]; ++kk)
-            {
-              const int64_t k = upper ? k1 - 1 - kk : k0 + kk;
-              if (young(k))
-                o[no + ny++] = (uint16_t)(k - rs);
-            }
-          n_young[g] = ny;
-          n_young_total += ny;
-          n_young_groups += ny > 0;
-        }
-      if (getenv("GLSNS_TRSV_DEBUG"))
-        fprintf(stderr, "trsv_analyse %s: young age %d: %lld of %lld helper entries (%.2f %%) in %lld of %lld groups; %d bulk + %d young helpers\n",
-                upper ? "upper" : "lower", young_age, (long long)n_young_total, (long long)gbase[ng],
-                100.0 * n_young_total / std::max<int64_t>(gbase[ng], 1), (long long)n_young_groups, (long long)ng, KB, KY);
-      // ---- item lists: per team one solver list (one item per block), KB bulk helper lists (the
-      // team's groups round-robin, <= TS_CH old entries per item) and KY young helper lists ----
+      // ---- item lists: per team one solver list (one item per block) and K helper lists
+      // (the team's groups round-robin, <= TS_CH entries per item) ----
       const int64_t        NWARP = NW * (K + 1);
-      std::vector<int64_t> n_it(NWARP + 1, 0), team_blocks(NW, 0), team_groups(NW, 0), team_ygroups(NW, 0);
-      std::vector<int32_t> helper_of(ng), yhelper_of(ng, -1), b_ymask(nb, 0);
-      auto chunks = [](int32_t c) { return (c + TS_CH - 1) / TS_CH; };
+      std::vector<int64_t> n_it(NWARP + 1, 0), team_blocks(NW, 0), team_groups(NW, 0);
+      std::vector<int32_t> helper_of(ng);
       for (int64_t t = 0; t < nb; ++t)
         {
           const int32_t b  = border[t];
@@ -1344,14 +1384,8 @@ namespace glsns
           for (int32_t q = 0; q < b_ng[b]; ++q)
             {
               const int64_t g = group_of_block(b, q);
-              helper_of[g]    = (int32_t)(team_groups[tm]++ % KB);
-              n_it[tm * (K + 1) + 1 + helper_of[g] + 1] += std::max(1, chunks(cnt[g] - n_young[g]));
-              if (n_young[g])
-                {
-                  yhelper_of[g] = KB + (int32_t)(team_ygroups[tm]++ % KY);
-                  n_it[tm * (K + 1) + 1 + yhelper_of[g] + 1] += chunks(n_young[g]);
-                  b_ymask[b] |= ((1 << grp_m[g]) - 1) << (grp_ptr[g] - b_r0[b]);
-                }
+              helper_of[g]    = (int32_t)(team_groups[tm]++ % K);
+              n_it[tm * (K + 1) + 1 + helper_of[g] + 1] += std::max<int64_t>(1, (cnt[g] + TS_CH - 1) / TS_CH);
             }
         }
       for (int64_t w = 0; w < NWARP; ++w)
@@ -1367,7 +1401,6 @@ namespace glsns
             TrsvItem &it = items[(size_t)fill[tm * (K + 1)]++];
             it.rs0 = n_gdesc, it.r0 = b_r0[b], it.len = b_ng[b], it.e_off = 0, it.nlow = 0, it.fmask = 0;
             it.flags = b_m[b] | IT_SOLVER | (is_primary[b] ? 0 : IT_GUEST) | ((slot_of[b] % TS_NWIN) << 12);
-            it.gb    = b_ymask[b]; // (solver item: the rows of the block that get a young post)
           }
           for (int32_t q = 0; q < b_ng[b]; ++q)
             {
@@ -1380,26 +1413,23 @@ namespace glsns
                 gd.nlow = (int32_t)(diag[i] - rowptr[i]);
                 gd.fmask = (int32_t)(uint32_t)fmask[g], gd.fmask2 = (int32_t)(uint32_t)(fmask[g] >> 32);
               }
-              // entries [first, first + count) of the group's list in `ord`, <= TS_CH per item
-              auto emit = [&](const int32_t helper, const int32_t first, const int32_t count, const int extra) {
-                const int32_t nchunk = std::max(1, chunks(count));
-                for (int32_t c = 0; c < nchunk; ++c)
-                  {
-                    TrsvItem  &it   = items[(size_t)fill[tm * (K + 1) + 1 + helper]++];
-                    const int  cntc = std::max(0, std::min(TS_CH, count - c * TS_CH));
-                    it.rs0   = rowptr[i];
-                    it.r0    = (int32_t)i;
-                    it.len   = len;
-                    it.e_off = first + c * TS_CH;
-                    it.gb    = gbase[g];
-                    it.flags = m | (c == nchunk - 1 ? IT_LAST : 0) | extra | (cntc << 16);
-                    it.nlow  = (int32_t)(diag[i] - rowptr[i]);
-                    it.fmask = (bseq[b] << 4) | (int32_t)(i - b_r0[b]); // where its totals go
-                  }
-              };
-              emit(helper_of[g], 0, cnt[g] - n_young[g], 0);
-              if (n_young[g])
-                emit(yhelper_of[g], cnt[g] - n_young[g], n_young[g], IT_YOUNG);
+              const int32_t nchunk = std::max(1, (cnt[g] + TS_CH - 1) / TS_CH);
+              for (int32_t c = 0; c < nchunk; ++c)
+                {
+                  TrsvItem  &it   = items[(size_t)fill[tm * (K + 1) + 1 + helper_of[g]]++];
+                  // (the entries solved last come last: the upper sweep takes the chunks of a
+                  // row from the far end, so that a helper waits on the group's final item only)
+                  const int  ch   = upper ? nchunk - 1 - c : c;
+                  const int  cntc = std::max(0, std::min(TS_CH, cnt[g] - ch * TS_CH));
+                  const bool last = c == nchunk - 1;
+                  it.rs0   = rowptr[i];
+                  it.r0    = (int32_t)i;
+                  it.len   = len;
+                  it.e_off = e_off[g] + ch * TS_CH;
+                  it.flags = m | (last ? IT_LAST : 0) | (cntc << 16);
+                  it.nlow  = (int32_t)(diag[i] - rowptr[i]);
+                  it.fmask = (bseq[b] << 4) | (int32_t)(i - b_r0[b]); // where its totals go
+                }
             }
         }
       std::vector<int32_t> &row_warp = upper ? ctx->trsv_row_warp_u : ctx->trsv_row_warp_l;
@@ -1409,7 +1439,7 @@ namespace glsns
           row_warp[grp_ptr[g] + a] = team_of[blk_of[g]] | (fmask[g] ? 1 << 30 : 0);
       // stream layout: the blobs of one warp back to back, warps one after another
       const int64_t        nit = n_it[NWARP];
-      std::vector<int64_t> blob_off((size_t)nit);
+      std::vector<int64_t> blob_off((size_t)nit), blob_off_v((size_t)nit, 0);
       std::vector<int32_t> next16((size_t)nit, 0);
       std::vector<TrsvWarpDir> dirv((size_t)NWARP);
       int64_t              off = 0;
@@ -1427,28 +1457,41 @@ namespace glsns
                   TrsvItem &it = items[(size_t)k];
                   const int64_t j = k - n_it[w];
                   if (j < TS_MBOX)
-                    {
-                      D.first_m[j >> 2] = (D.first_m[j >> 2] & ~(255 << (8 * (j & 3)))) | ((it.flags & 31) << (8 * (j & 3)));
-                      D.first_ym[j >> 1] |= ((int32_t)it.gb & 0xffff) << (16 * (j & 1));
-                    }
+                    D.first_m[j >> 2] = (D.first_m[j >> 2] & ~(255 << (8 * (j & 3)))) | ((it.flags & 31) << (8 * (j & 3)));
                   if (j == 0)
                     D.first_r0 = it.r0, D.first_flags = it.flags;
                   it.e_off = k + 1 < n_it[w + 1] ? items[(size_t)k + 1].r0 : 0;
                   it.nlow  = k + 1 < n_it[w + 1] ? items[(size_t)k + 1].flags : 0;
-                  it.pad_  = k + TS_MBOX < n_it[w + 1] ? (items[(size_t)k + TS_MBOX].flags & 31) | ((int32_t)items[(size_t)k + TS_MBOX].gb << 8) : TS_BR;
+                  it.pad_  = k + TS_MBOX < n_it[w + 1] ? (items[(size_t)k + TS_MBOX].flags & 31) : TS_BR;
                 }
             }
+          const bool solver = w % (K + 1) == 0; // (a team's first list is its solver's)
           for (int64_t k = n_it[w]; k < n_it[w + 1]; ++k)
             {
               const int32_t b16 = blob_bytes(items[(size_t)k].flags) / 16;
               blob_off[(size_t)k] = off;
               off += 16 * (int64_t)b16;
               const int64_t j  = k - n_it[w];
-              const int     ns = w % (K + 1) == 0 ? TS_SNSLOT : TS_NSLOT; // (a team's first list is its solver's)
+              const int     ns = solver ? TS_SNSLOT : TS_NCS;
               if (j < ns)
                 D.first16[j] = b16;
               else
-                next16[(size_t)(k - ns)] = b16;
+                next16[(size_t)(k - ns)] |= b16;
+            }
+          if (!solver)
+            { // a helper's factor entries follow its indices, in a stream of their own
+              D.offset_v = off;
+              for (int64_t k = n_it[w]; k < n_it[w + 1]; ++k)
+                {
+                  const int32_t v16 = value_blob_bytes(items[(size_t)k].flags) / 16;
+                  blob_off_v[(size_t)k] = off;
+                  off += 16 * (int64_t)v16;
+                  const int64_t j = k - n_it[w];
+                  if (j < TS_NVS)
+                    D.firstv16[j] = v16;
+                  else
+                    next16[(size_t)(k - TS_NVS)] |= v16 << 8;
+                }
             }
         }
       sw.n_items      = nit;
@@ -1456,8 +1499,8 @@ namespace glsns
       GLSNS_TRY(dev_upload(ctx, sw.items, items.data(), items.size()));
       GLSNS_TRY(dev_upload(ctx, sw.gdesc, gdesc.data(), gdesc.size()));
       GLSNS_TRY(dev_upload(ctx, sw.blob_off, blob_off.data(), blob_off.size()));
+      GLSNS_TRY(dev_upload(ctx, sw.blob_off_v, blob_off_v.data(), blob_off_v.size()));
       GLSNS_TRY(dev_upload(ctx, sw.next16, next16.data(), next16.size()));
-      GLSNS_TRY(dev_upload(ctx, sw.ord, ord.data(), ord.size()));
       GLSNS_TRY(dev_upload(ctx, sw.dir, reinterpret_cast<const unsigned char *>(dirv.data()),
                            dirv.size() * sizeof(TrsvWarpDir)));
       GLSNS_TRY(dev_alloc(ctx, sw.stream, (size_t)std::max<int64_t>(off, 16)));
@@ -1467,7 +1510,7 @@ namespace glsns
       if (nit)
         {
           trsv_pack_static_kernel<<<(unsigned)((nit * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            nit, sw.items.p, sw.blob_off.p, sw.next16.p, ctx->col.p, sw.ord.p, sw.stream.p);
+            nit, sw.items.p, sw.blob_off.p, sw.next16.p, ctx->col.p, sw.stream.p);
           ctx->kernel_launches++;
           GLSNS_CUDA(ctx, cudaGetLastError());
         }
@@ -1594,16 +1637,16 @@ namespace glsns
       {
         const int64_t nit = ctx->trsv_l.n_items;
         trsv_pack_values_kernel<false><<<(unsigned)((nit * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-          nit, ctx->trsv_l.items.p, ctx->trsv_l.gdesc.p, ctx->trsv_l.blob_off.p, ctx->lu.p,
-          ctx->trsv_l.ord.p, ctx->trsv_l.stream.p);
+          nit, ctx->trsv_l.items.p, ctx->trsv_l.gdesc.p, ctx->trsv_l.blob_off.p, ctx->trsv_l.blob_off_v.p, ctx->lu.p,
+          ctx->trsv_l.stream.p);
         ctx->kernel_launches++;
       }
     if (ctx->trsv_u.n_items)
       {
         const int64_t nit = ctx->trsv_u.n_items;
         trsv_pack_values_kernel<true><<<(unsigned)((nit * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-          nit, ctx->trsv_u.items.p, ctx->trsv_u.gdesc.p, ctx->trsv_u.blob_off.p, ctx->lu.p,
-          ctx->trsv_u.ord.p, ctx->trsv_u.stream.p);
+          nit, ctx->trsv_u.items.p, ctx->trsv_u.gdesc.p, ctx->trsv_u.blob_off.p, ctx->trsv_u.blob_off_v.p, ctx->lu.p,
+          ctx->trsv_u.stream.p);
         ctx->kernel_launches++;
       }
     GLSNS_CUDA(ctx, cudaGetLastError());
@@ -1617,8 +1660,12 @@ namespace glsns
     const int64_t n = ctx->n_owned;
     if (n == 0)
       return GLSNS_OK;
-    GLSNS_CUDA(ctx, cudaMemsetAsync(ctx->ytmp.p, 0xFF, sizeof(double) * n, ctx->stream));
-    GLSNS_CUDA(ctx, cudaMemsetAsync(z, 0xFF, sizeof(double) * n, ctx->stream));
+    // (GLSNS_TRSV_NODEPS=1, a measuring aid: every entry counts as published from the start, so
+    // nothing ever waits for another team -- wrong results, and the time the machinery takes
+    // when the dependencies cost nothing)
+    static const int fill = getenv("GLSNS_TRSV_NODEPS") && atoi(getenv("GLSNS_TRSV_NODEPS")) ? 0 : 0xFF;
+    GLSNS_CUDA(ctx, cudaMemsetAsync(ctx->ytmp.p, fill, sizeof(double) * n, ctx->stream));
+    GLSNS_CUDA(ctx, cudaMemsetAsync(z, fill, sizeof(double) * n, ctx->stream));
     if (ctx->n_diag_rows)
       {
         trsv_diag_rows_kernel<<<(ctx->n_diag_rows + 255) / 256, 256, 0, ctx->stream>>>(

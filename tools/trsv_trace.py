@@ -96,13 +96,17 @@ for name, t, tp, w, upper in (("lower", tl, hp.last_trace_posts[0], wl, False),
                           "cross_helper_part_us": th / 1e3, "cross_solver_part_us": tsol / 1e3}
     out[name] = o
 for name, pl in zip(("lower", "upper"), hp.last_trace_polls):
-    nw = min(len(pl) // 12, int(__import__('os').environ.get('GLSNS_TRACE_TEAMS', 296)))
+    nw = min(len(pl) // 20, int(__import__('os').environ.get('GLSNS_TRACE_TEAMS', 296)))
     st = pl[:nw * 8].reshape(nw, 8).astype(np.float64)
     busy = st[st[:, 6] > 0]
     tot = busy[:, :5].sum(axis=0)
     out[name]["solver_cycles_per_block_[ring_wait,window,mailbox_wait,totals_publish,release_refill]"] = [float(v) for v in tot / busy[:, 6].sum()]
     hc = pl[nw * 8:nw * 12].reshape(nw, 4).astype(np.float64).sum(axis=0)
     out[name]["helpers_[items,items_that_waited,poll_rounds,entries_re_read]"] = [float(v) for v in hc]
+    hs = pl[nw * 12:nw * 20].reshape(nw, 8).astype(np.float64).sum(axis=0)
+    out[name]["helper_cycle_shares_[indices,values,solution_entries,mailbox_full,other]"] = \
+        [float(v / max(hs[4], 1)) for v in hs[:4]] + [float(1 - hs[:4].sum() / max(hs[4], 1))]
+    out[name]["helper_cycles_per_item"] = float(hs[4] / max(hc[0], 1))
     k = int(np.argmax(st[:, 6]))
     out[name]["busiest_solver_blocks_and_cycles_per_block"] = [float(st[k, 6])] + [float(v / st[k, 6]) for v in st[k, :5]]
 print(json.dumps(out, indent=1))
