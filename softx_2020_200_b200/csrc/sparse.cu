@@ -1117,6 +1117,249 @@ namespace glsns
         }
     }
 
+
+    // The same factorisation, one CTA of FC_T threads per group.  ilu_factor_runs_kernel gives a
+    // group to one warp, and a warp is a serial machine: 30-60 pivot runs one after the other,
+    // each a chain of dependent loads, a hash probe and a handful of FMAs per lane -- 8.3e10 warp
+    // instructions at 0.17 per scheduler and cycle with the 9 warps per SM that the staged
+    // groups (24 KB of shared memory each) leave room for (ncu, round 2).  Here the columns of
+    // a pivot run are dealt to FC_T threads (a run is then one or two entries per thread), the
+    // multipliers are computed by the first rows' threads between two CTA barriers, and eight
+    // CTAs of four warps are resident per SM.  Arithmetic per entry: unchanged (every entry of the
+    // group is updated by one thread per pivot, pivots in ascending order, one fused multiply-add
+    // each), so the factors are bitwise those of the other kernels.
+    constexpr int FC_T   = 128;
+    constexpr int FC_PRE = 2; // entries of a run per thread requested a run ahead
+
+    __global__ void __launch_bounds__(FC_T, 7)
+    ilu_factor_cta_kernel(const int32_t n_groups, const int2 *__restrict__ groups,
+                          const int64_t n, const int64_t *__restrict__ rowptr,
+                          const int32_t *__restrict__ col, const int64_t *__restrict__ diag_pos,
+                          const int4 *__restrict__ rowdesc, double *lu, int *row_done,
+                          const int epoch, int *counters, const int maxlen, const int hbits)
+    {
+      extern __shared__ __align__(16) unsigned char fc_smem[];
+      __shared__ int s_ticket;
+      const int tid = threadIdx.x;
+      const int hsize = 1 << hbits, hmask = hsize - 1;
+      double   *sv = reinterpret_cast<double *>(fc_smem);                          // [4][maxlen]
+      double   *l4 = reinterpret_cast<double *>(fc_smem + (size_t)maxlen * 32);    // [4 rows][4 pivots]
+      int32_t  *sc = reinterpret_cast<int32_t *>(fc_smem + (size_t)maxlen * 32 + 192); // [maxlen]
+      int32_t  *hkey = sc + maxlen;                                                // [hsize], -1 = empty
+      int16_t  *hpos = reinterpret_cast<int16_t *>(hkey + hsize);                  // [hsize]
+      auto hash = [&](int32_t j) { return (int)(((unsigned)j * 2654435761u) >> (32 - hbits)); };
+      // one pivot run: what every thread knows about it, its own entries, and (threads < 4: the
+      // rows of the group) the run's diagonal entries and inner couplings
+      struct Run
+      {
+        int     c, kk, rbase, rlen;
+        int64_t rs0;
+        int32_t cj[FC_PRE];
+        double  uv[4][FC_PRE];
+      };
+      for (;;)
+        {
+          if (tid == 0)
+            s_ticket = atomicAdd(&counters[0], 1);
+          __syncthreads();
+          const int t = s_ticket;
+          if (t >= n_groups)
+            break;
+          const int2    g  = groups[t];
+          const int     r0 = g.x, m = g.y;
+          const int64_t rs = rowptr[r0];
+          const int     len = (int)(rowptr[r0 + 1] - rs), nl = (int)(diag_pos[r0] - rs);
+          for (int k = tid; k < hsize; k += FC_T)
+            hkey[k] = -1;
+          __syncthreads();
+          for (int k = tid; k < len; k += FC_T)
+            {
+              const int32_t j = col[rs + k];
+              sc[k]           = j;
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                if (a < m)
+                  sv[a * maxlen + k] = lu[rs + (int64_t)a * len + k];
+              int s = hash(j);
+              while (atomicCAS(hkey + s, -1, j) != -1)
+                s = (s + 1) & hmask;
+              hpos[s] = (int16_t)k;
+            }
+          __syncthreads();
+          // the run that starts at pivot kk: wait until its rows are final (the first threads
+          // look, the barrier that follows tells the others), then request it
+          auto describe = [&](Run &R, const int kk) {
+            R.kk = kk, R.c = 0;
+            if (kk >= nl)
+              return;
+            const int32_t k   = sc[kk];
+            const int4    dsc = __ldg(rowdesc + k); // (staging all descriptors of a group in shared memory up front: measured slower, 385 -> 462 ms)
+            const int     rem = dsc.w >> 16;
+            int           c   = 1;
+            while (c < rem && kk + c < nl && sc[kk + c] == k + c)
+              ++c;
+            R.c    = c;
+            R.rs0  = (int64_t)(unsigned)dsc.x | ((int64_t)dsc.y << 32);
+            R.rlen = dsc.w & 0xffff;
+            R.rbase = dsc.z + c;
+          };
+          auto wait_ready = [&](const Run &R) { // threads 32 .. 35 (a warp that computes no multipliers)
+            if (tid >= 32 && tid < 32 + R.c)
+              {
+                const int32_t k = sc[R.kk] + (tid - 32);
+                long long spins = 0;
+                while (*(volatile int *)(row_done + k) != epoch)
+                  if (++spins > SPIN_LIMIT)
+                    {
+                      atomicExch(&counters[1], 2);
+                      break;
+                    }
+                __threadfence();
+              }
+          };
+          // (the run's diagonal entries and inner couplings, for the threads that compute the
+          // multipliers: one set -- they are used up before the next run is requested)
+          double rdiag[4], rin[6];
+          auto request = [&](Run &R) {
+            if (R.c == 0)
+              return;
+            const int d0 = R.rbase - R.c;
+            if (tid < 4)
+              {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                  rdiag[b] = b < R.c ? __ldcg(lu + R.rs0 + (int64_t)b * R.rlen + d0 + b) : 1.0;
+                int q = 0;
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+#pragma unroll
+                  for (int b2 = b + 1; b2 < 4; ++b2, ++q)
+                    rin[q] = b2 < R.c ? __ldcg(lu + R.rs0 + (int64_t)b * R.rlen + d0 + b2) : 0.0;
+              }
+#pragma unroll
+            for (int u = 0; u < FC_PRE; ++u)
+              {
+                const int o = R.rbase + tid + FC_T * u;
+                R.cj[u]     = o < R.rlen ? __ldg(col + R.rs0 + o) : 0x7fffffff;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                  R.uv[b][u] = (b < R.c && o < R.rlen) ? __ldcg(lu + R.rs0 + (int64_t)b * R.rlen + o) : 0.0;
+              }
+          };
+          auto apply = [&](const int c, const int32_t j, const double u0, const double u1, const double u2,
+                           const double u3) {
+            if (j >= n)
+              return; // ghost column (or past the end): outside the diagonal block
+            int s = hash(j);
+            for (;;)
+              {
+                const int32_t key = hkey[s];
+                if (key == j)
+                  {
+                    const int p = hpos[s];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                      if (a < m)
+                        {
+                          double v = sv[a * maxlen + p];
+                          v        = fma(-l4[a * 4 + 0], u0, v);
+                          if (c > 1)
+                            v = fma(-l4[a * 4 + 1], u1, v);
+                          if (c > 2)
+                            v = fma(-l4[a * 4 + 2], u2, v);
+                          if (c > 3)
+                            v = fma(-l4[a * 4 + 3], u3, v);
+                          sv[a * maxlen + p] = v;
+                        }
+                    return;
+                  }
+                if (key == -1)
+                  return; // not in the pattern: ILU(0) drops the fill
+                s = (s + 1) & hmask;
+              }
+          };
+          Run cur, nxt;
+          describe(cur, 0);
+          wait_ready(cur);
+          __syncthreads();
+          request(cur);
+          while (cur.c)
+            {
+              describe(nxt, cur.kk + cur.c);
+              // multipliers of the group's rows, pivot by pivot (scalar IKJ order)
+              if (tid < m)
+                {
+                  double *row = sv + tid * maxlen + cur.kk;
+                  int     q   = 0;
+#pragma unroll
+                  for (int b = 0; b < 4; ++b)
+                    {
+                      if (b < cur.c)
+                        {
+                          const double l = row[b] / rdiag[b];
+                          row[b]         = l;
+                          l4[tid * 4 + b] = l;
+#pragma unroll
+                          for (int b2 = b + 1; b2 < 4; ++b2)
+                            if (b2 < cur.c)
+                              row[b2] = fma(-l, rin[q + b2 - b - 1], row[b2]);
+                        }
+                      q += 3 - b;
+                    }
+                }
+              wait_ready(nxt);
+              __syncthreads();
+              request(nxt);
+              {
+                const int c = cur.c;
+#pragma unroll
+                for (int u = 0; u < FC_PRE; ++u)
+                  apply(c, cur.cj[u], cur.uv[0][u], cur.uv[1][u], cur.uv[2][u], cur.uv[3][u]);
+                for (int o = cur.rbase + tid + FC_T * FC_PRE; o < cur.rlen; o += FC_T)
+                  apply(c, __ldg(col + cur.rs0 + o), __ldcg(lu + cur.rs0 + o),
+                        c > 1 ? __ldcg(lu + cur.rs0 + (int64_t)cur.rlen + o) : 0.0,
+                        c > 2 ? __ldcg(lu + cur.rs0 + 2 * (int64_t)cur.rlen + o) : 0.0,
+                        c > 3 ? __ldcg(lu + cur.rs0 + 3 * (int64_t)cur.rlen + o) : 0.0);
+              }
+              __syncthreads();
+              cur = nxt;
+            }
+          // ---- rows of the group eliminate each other ----
+          for (int b = 0; b + 1 < m; ++b)
+            {
+              const int pb = nl + b;
+              if (tid > b && tid < m)
+                {
+                  const double l      = sv[tid * maxlen + pb] / sv[b * maxlen + pb];
+                  sv[tid * maxlen + pb] = l;
+                  l4[tid]             = l;
+                }
+              __syncthreads();
+              for (int p = pb + 1 + tid; p < len; p += FC_T)
+                if (sc[p] < n)
+                  {
+                    const double ub = sv[b * maxlen + p];
+#pragma unroll
+                    for (int a = 1; a < 4; ++a)
+                      if (a > b && a < m)
+                        sv[a * maxlen + p] -= l4[a] * ub;
+                  }
+              __syncthreads();
+            }
+          for (int k = tid; k < len; k += FC_T)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (a < m)
+                lu[rs + (int64_t)a * len + k] = sv[a * maxlen + k];
+          if (tid < m && sv[tid * maxlen + nl + tid] == 0.0)
+            atomicExch(&counters[1], 1);
+          __threadfence(); // the rows, then (one barrier for all of them) their flags
+          __syncthreads();
+          if (tid < m)
+            *(volatile int *)(row_done + r0 + tid) = epoch;
+        }
+    }
+
     // flags of the rows no group covers (diagonal-only rows): final from the start
     __global__ void __launch_bounds__(256)
     ilu_mark_rows_kernel(const int32_t n_rows, const int32_t *__restrict__ rows, int *row_done,
@@ -1513,7 +1756,29 @@ namespace glsns
         static const bool by_pivot_rows = getenv("GLSNS_ILU_BY_PIVOT_ROWS") != nullptr;
         const size_t per_warp_r = per_warp + 128;
         const int    warps_r    = (int)std::min<size_t>(10, (size_t)(227 * 1024) / per_warp_r);
-        if (warps_r >= 2 && ctx->n_groups > 0 && !by_rows && !by_pivot_rows && ctx->grp_first.p && maxlen < 65536)
+        static const bool by_warp_runs = getenv("GLSNS_ILU_BY_WARP_RUNS") != nullptr;
+        const size_t      smem_cta     = per_warp + 128;
+        if (smem_cta <= (size_t)(227 * 1024) / 2 && ctx->n_groups > 0 && !by_rows && !by_pivot_rows && !by_warp_runs &&
+            ctx->grp_first.p && maxlen < 32768)
+          {
+            // one CTA of four warps per group, a pivot run's columns dealt to its threads
+            if (ctx->n_diag_rows)
+              ilu_mark_rows_kernel<<<(ctx->n_diag_rows + 255) / 256, 256, 0, ctx->stream>>>(
+                ctx->n_diag_rows, ctx->diag_rows.p, ctx->row_done.p, ctx->epoch);
+            GLSNS_CUDA(ctx, cudaFuncSetAttribute(ilu_factor_cta_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+            int per_sm = 0;
+            GLSNS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilu_factor_cta_kernel, FC_T, smem_cta));
+            const int grid = (int)std::min<int64_t>(ctx->n_groups, (int64_t)ctx->n_sm * std::max(per_sm, 1));
+            GLSNS_TRY(dev_alloc(ctx, ctx->rowdesc, (size_t)n));
+            ilu_rowdesc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+              n, ctx->rowptr.p, ctx->diag_pos.p, ctx->grp_first.p, ctx->rowdesc.p);
+            ilu_factor_cta_kernel<<<grid, FC_T, smem_cta, ctx->stream>>>(
+              ctx->n_groups, ctx->fgroups.p, n, ctx->rowptr.p, ctx->col.p, ctx->diag_pos.p,
+              ctx->rowdesc.p, ctx->lu.p, ctx->row_done.p, ctx->epoch, ctx->counters.p, maxlen, hbits);
+            ctx->kernel_launches += 4;
+          }
+        else if (warps_r >= 2 && ctx->n_groups > 0 && !by_rows && !by_pivot_rows && ctx->grp_first.p && maxlen < 65536)
           {
             // rows of a group share one warp, and so do the pivot rows of a run
             if (ctx->n_diag_rows)
