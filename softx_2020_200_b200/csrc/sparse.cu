@@ -1128,10 +1128,13 @@ namespace glsns
     // CTAs of four warps are resident per SM.  Arithmetic per entry: unchanged (every entry of the
     // group is updated by one thread per pivot, pivots in ascending order, one fused multiply-add
     // each), so the factors are bitwise those of the other kernels.
-    constexpr int FC_T   = 128;
+#ifndef GLSNS_ILU_CTA_THREADS
+#define GLSNS_ILU_CTA_THREADS 128
+#endif
+    constexpr int FC_T   = GLSNS_ILU_CTA_THREADS; // (64: 9 CTAs per SM)
     constexpr int FC_PRE = 2; // entries of a run per thread requested a run ahead
 
-    __global__ void __launch_bounds__(FC_T, 7)
+    __global__ void __launch_bounds__(FC_T, FC_T >= 128 ? 7 : 9)
     ilu_factor_cta_kernel(const int32_t n_groups, const int2 *__restrict__ groups,
                           const int64_t n, const int64_t *__restrict__ rowptr,
                           const int32_t *__restrict__ col, const int64_t *__restrict__ diag_pos,

@@ -104,15 +104,6 @@ namespace glsns
     constexpr int TS_NCS       = 8;                // ring slots of a helper warp: column indices (+ header)
     constexpr int TS_NVS       = GLSNS_TRSV_NSLOT; // ring slots of a helper warp: factor entries
     constexpr int TS_MAXWARPS  = GLSNS_TRSV_THREADS / 32;
-#ifndef GLSNS_TRSV_POLL_REFRESH
-#define GLSNS_TRSV_POLL_REFRESH 1
-#endif
-#ifndef GLSNS_TRSV_POLL_SLEEP
-#define GLSNS_TRSV_POLL_SLEEP 0
-#endif
-#ifndef GLSNS_TRSV_REFRESH
-#define GLSNS_TRSV_REFRESH 0
-#endif
 #ifndef GLSNS_TRSV_DEPTH
 #define GLSNS_TRSV_DEPTH 2
 #endif
@@ -757,19 +748,6 @@ namespace glsns
             slotG = slotG + 1 == TS_NCS ? 0 : slotG + 1;
             phaseG ^= slotG == 0;
           }
-#if GLSNS_TRSV_REFRESH
-        // the items between G and R: entries that were not there when last looked are requested
-        // again at every step, so that an item that reaches R has been looked at a step ago, not
-        // TS_D steps ago
-#pragma unroll
-        for (int u = 0; u < TS_U; ++u)
-          {
-            if ((pS[k1] & (1u << u)) && bS[k1][u] == SENTINEL)
-              bS[k1][u] = ld_relaxed_u64(x + cS[k1][u]);
-            if (NS > 3 && (pS[k2] & (1u << u)) && bS[k2][u] == SENTINEL)
-              bS[k2][u] = ld_relaxed_u64(x + cS[k2][u]);
-          }
-#endif
         // ---- R(it - TS_D): entries not there yet are re-read until they are; multiply ----
         if (it >= TS_D)
           {
@@ -811,7 +789,6 @@ namespace glsns
                 // the entries of the two items behind this one that were not there when they
                 // were first read are refreshed in the same round trip: when this item is
                 // done, they need no round trip of their own
-#if GLSNS_TRSV_POLL_REFRESH
 #pragma unroll
                 for (int u = 0; u < TS_U; ++u)
                   {
@@ -820,10 +797,6 @@ namespace glsns
                     if (NS > 3 && (pS[k2] & (1u << u)) && bS[k2][u] == SENTINEL)
                       bS[k2][u] = ld_relaxed_u64(x + cS[k2][u]);
                   }
-#endif
-#if GLSNS_TRSV_POLL_SLEEP
-                __nanosleep(GLSNS_TRSV_POLL_SLEEP);
-#endif
                 // bug guard: give up after seconds of waiting, or as soon as another
                 // warp has given up (the host reports GLSNS_ERR_CUDA)
                 if ((++spins & 1023) == 0 &&
@@ -1224,7 +1197,15 @@ namespace glsns
       // chains the front advances several levels in the time a level takes elsewhere) were
       // measured: -4 % at 32^3 cells, +5 % at 64^3.
       const int64_t cost_chain = getenv("GLSNS_TRSV_COST_CHAIN") ? atoi(getenv("GLSNS_TRSV_COST_CHAIN")) : 1;
-      const int64_t cost_cross = getenv("GLSNS_TRSV_COST_CROSS") ? atoi(getenv("GLSNS_TRSV_COST_CROSS")) : 1;
+      // Second session of round 2 (lean solver warp): cross = 3 is 9 % faster at 32^3 cells (2.17 ->
+      // 1.97 ms), 5 % slower at 64^3 (7.37 -> 7.72).  The difference is the width of the DAG against
+      // the number of teams: where a level has fewer groups than half the teams (the 32^3 mesh,
+      // the per-rank blocks of a strong-scaled run) the sweep is a few long chains and the order
+      // should follow the time a value needs to cross to another team; where every team has several
+      // groups per level the level order keeps the lists balanced.  A function of the sparsity
+      // pattern alone, like the rest of the schedule.
+      const int64_t cost_cross = getenv("GLSNS_TRSV_COST_CROSS") ? atoi(getenv("GLSNS_TRSV_COST_CROSS")) :
+                                 (ng < (int64_t)(nlev + 1) * (NW / 2) ? 3 : 1);
       for (int64_t b = 0; b < nb; ++b)
         {
           int32_t l = 0;
