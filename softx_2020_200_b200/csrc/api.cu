@@ -213,6 +213,8 @@ glsns_create(int32_t cuda_device, glsns_context **out)
   int sm = 0;
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cuda_device);
   ctx->n_sm = sm > 0 ? sm : 148;
+  if (const char *e = getenv("GLSNS_GMRES_FUSED"))
+    ctx->gmres_fused = atoi(e) != 0;
   if (const char *e = getenv("GLSNS_GMRES_LOOKAHEAD"))
     ctx->gmres_lookahead = atoi(e) != 0;
   if (dev_alloc(ctx, ctx->counters, 4) != GLSNS_OK)

@@ -161,6 +161,7 @@ struct glsns_context
   int32_t               epoch = 0;
   double               *h_pinned = nullptr; // 3 x 192 doubles: Hessenberg columns of two steps in flight, y
   cudaEvent_t           step_event[2] = {nullptr, nullptr}; // GMRES: a step's column has reached the host
+  bool                  gmres_fused = true;     // GLSNS_GMRES_FUSED=0: separate axpy / dot / scale kernels (same bits)
   bool                  gmres_lookahead = true; // GLSNS_GMRES_LOOKAHEAD=0: one step on the stream at a time
   int32_t               n_sm = 148;
 
