@@ -39,13 +39,15 @@
 //     stream the groups' factor entries, gather the solution entries, reduce, and
 //     post the totals in the block's mailbox entry); 2 teams x (1 + 7) warps per SM.
 //   * STREAMS.  After every factorisation the factor entries are re-packed, per
-//     sweep, into one contiguous byte stream per warp in exactly the order that warp
-//     consumes them: per helper item (<= 64 entries of one group) a 16-byte header,
-//     the column indices and the values of the group's rows; per solver item (one
-//     block) the header and the solved recurrence.  The solve then reads HBM strictly
-//     sequentially, and one lane moves a whole item into the warp's shared-memory
-//     ring with a single bulk copy (cp.async.bulk, completion on an mbarrier) several
-//     items ahead of the one being solved.
+//     sweep, into contiguous byte streams per warp in exactly the order that warp
+//     consumes them: per helper item (<= 64 entries of one group) a 16-byte header with
+//     the column indices in one stream and the values of the group's rows in another
+//     (the indices are needed when the solution entries are requested, the values two
+//     items later when they are used: two rings, 8 x 272 B and 4 x 2 KB per helper); per
+//     solver item (one block) the solved recurrence, lane by lane, with the header of the
+//     NEXT block.  The solve then reads HBM strictly sequentially, and one lane moves a
+//     whole blob into the warp's shared-memory ring with a single bulk copy
+//     (cp.async.bulk, completion on an mbarrier) several items ahead of the one in work.
 //   * The solution vector itself carries readiness: it is pre-filled with an
 //     all-ones NaN pattern and a consumer re-reads an entry until it has been
 //     overwritten (no flags, no fences).
