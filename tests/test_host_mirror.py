@@ -327,3 +327,36 @@ def test_rank_local_mesh_equals_the_partition_of_the_global_one(dim, n, pu, pp, 
             if name in ("periodic_slave", "periodic_master"):
                 continue
             assert np.array_equal(a.array(name), b.array(name)), (name, rank)
+
+
+@pytest.mark.parametrize("n,world", [(3, 3), (4, 2)])
+def test_rank_local_arrays_reproduce_the_block_jacobi_oracle(oracle, n, world):
+    """The reference side of tests/test_gpu_parity.py::test_rank_local_blocks_on_one_gpu, on the
+    CPU: a rank's local arrays (owned rows, sorted local columns with the ghosts behind the owned
+    ones) carry exactly the oracle's rows of its block, and the oracle's SpMV / triangular sweeps
+    over those local arrays equal its block-Jacobi results on the global matrix."""
+    import types
+    from tests.util import rank_local_reference
+    ref = rank_local_reference(oracle, n, world)
+    om, bp, x = ref["oracle_mesh"], ref["block_ptr"], ref["x"]
+    assert bp[-1] == om.ndof
+    for r, m in enumerate(ref["parts"]):
+        l2g, rp, col = m.array("local_to_global"), m.array("row_ptr"), m.array("col_idx")
+        assert np.array_equal(l2g[:m.n_owned], np.arange(bp[r], bp[r + 1]))
+        rows, col_g = slice(bp[r], bp[r + 1]), l2g[col]
+        a_loc, lu_loc = np.empty(m.nnz), np.empty(m.nnz)
+        for i in range(m.n_owned):
+            o = np.argsort(col_g[rp[i]:rp[i + 1]])
+            gr = slice(om.rowptr[bp[r] + i], om.rowptr[bp[r] + i + 1])
+            assert np.all(np.diff(col[rp[i]:rp[i + 1]]) > 0)
+            assert np.array_equal(col_g[rp[i]:rp[i + 1]][o], om.col[gr])
+            a_loc[rp[i]:rp[i + 1]][o] = ref["matrix"][gr]
+            lu_loc[rp[i]:rp[i + 1]][o] = ref["ilu"][gr]
+        loc = types.SimpleNamespace(ndof=m.n_owned, rowptr=rp, col=col)
+        # (the ghosts sit behind the owned columns: another summation order than the global row's)
+        assert np.max(np.abs(oracle.spmv(loc, a_loc, x[l2g]) - ref["spmv"][rows])) <= 1e-13 * np.max(np.abs(ref["spmv"]))
+        dp = np.array([rp[i] + np.searchsorted(col[rp[i]:rp[i + 1]], i) for i in range(m.n_owned)],
+                      dtype=np.int64)
+        z = oracle.ilu_apply(loc, lu_loc, dp, x[rows])
+        assert np.max(np.abs(z - ref["ilu_apply"][rows])) <= 1e-13 * np.max(np.abs(ref["ilu_apply"]))
+    ref["global_mesh"].close()
