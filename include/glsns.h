@@ -51,7 +51,8 @@ typedef enum
   GLSNS_ERR_ZERO_PIVOT     = 4, /* ILU breakdown */
   GLSNS_ERR_STATE          = 5, /* call order: e.g. solve before assemble */
   /* std::runtime_error("This solver is not allowed"), gls_navier_stokes.cc:1158,
-     and features not built yet (ILU fill > 0, hanging-node constraints) */
+     and what is refused: curved cells without mapping_laplacian, hanging-node lines on more
+     than one rank */
   GLSNS_ERR_UNSUPPORTED    = 6,
   GLSNS_ERR_COMM           = 7
 } glsns_status;
